@@ -1,0 +1,66 @@
+// oracle/decode_ref.cc — TEST INFRASTRUCTURE ONLY.  CPU receiver with the argv contract of the reference
+// (/root/reference/decode.cc:559-620): decode OUTPUT INPUT [SKIP]; same stderr lines; always writes 5380 bytes.
+// Extra env knobs (oracle only): REF_LIST=4|8, REF_OSD_LITERAL=1, REF_R0MAX=n.
+#include "ref_modem.hh"
+#include <fstream>
+#include <iostream>
+#include <iterator>
+using namespace ref;
+
+int main(int argc, char **argv)
+{
+	if (argc < 3 || argc > 4) {
+		std::cerr << "usage: " << argv[0] << " OUTPUT INPUT [SKIP]" << std::endl;
+		return 1;
+	}
+	std::string output_name = argv[1], input_name = argv[2];
+	if (output_name == "-") output_name = "/dev/stdout";
+	if (input_name == "-") input_name = "/dev/stdin";
+	std::ifstream in(input_name, std::ios::binary);
+	std::vector<uint8_t> raw((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+	WavData w;
+	if (!wav_parse(raw.data(), raw.size(), w)) { std::cerr << "Couldn't parse WAV input." << std::endl; return 1; }
+	if (w.channels < 1 || w.channels > 2) {
+		std::cerr << "Only real or analytic signal (one or two channels) supported." << std::endl;
+		return 1;
+	}
+	int skip = argc > 3 ? std::atoi(argv[3]) : 0;
+	if (w.rate != 8000 && w.rate != 16000 && w.rate != 44100 && w.rate != 48000) { std::cerr << "Unsupported sample rate." << std::endl; return 1; }
+	RxOptions opt;
+	if (const char *e = std::getenv("REF_LIST")) opt.list_size = std::atoi(e);
+	if (const char *e = std::getenv("REF_OSD_LITERAL")) opt.osd_literal = std::atoi(e) != 0;
+	if (const char *e = std::getenv("REF_R0MAX")) opt.r0_max = std::atoi(e);
+	Receiver rx(w.rate);
+	uint8_t out[kDataBytes];
+	std::memset(out, 0, sizeof(out));
+	int st = rx.run(out, w.samples.data(), w.frames(), w.channels, skip, opt);
+	const Taps &t = rx.taps;
+	if (t.detections && t.t_fire >= 0) {
+		std::cerr << "symbol pos: " << t.symbol_pos << std::endl;
+		std::cerr << "coarse cfo: " << t.cfo_rad * (w.rate / kTwoPi) << " Hz " << std::endl;
+	}
+	switch (st) {
+	case ST_OSD_FAIL: std::cerr << "OSD error." << std::endl; break;
+	case ST_HDR_CRC: std::cerr << "header CRC error." << std::endl; break;
+	case ST_BAD_MODE: std::cerr << "operation mode " << t.mode << " unsupported." << std::endl; break;
+	case ST_BAD_CALL: std::cerr << "oper mode: " << t.mode << std::endl << "call sign unsupported." << std::endl; break;
+	default: break;
+	}
+	if (st == ST_OK || st == ST_PAYLOAD_CRC) {
+		std::cerr << "oper mode: " << t.mode << std::endl;
+		std::cerr << "call sign: " << t.call_sign << std::endl;
+		std::cerr << "demod ";
+		for (size_t j = 0; j < t.slope.size(); ++j) std::cerr << ".";
+		std::cerr << " done" << std::endl;
+		std::cerr << "Es/N0 (dB):";
+		for (float p : t.precision) std::cerr << " " << 10.f * std::log10(p);
+		std::cerr << std::endl;
+		if (st == ST_OK) std::cerr << "bit flips: " << t.flips << std::endl;
+		else std::cerr << "payload decoding error." << std::endl;
+	}
+	descramble(out);
+	std::ofstream of(output_name, std::ios::binary | std::ios::trunc);
+	if (of.bad()) { std::cerr << "Couldn't open file \"" << output_name << "\" for writing." << std::endl; return 1; }
+	of.write(reinterpret_cast<const char *>(out), kDataBytes);
+	return 0;
+}
