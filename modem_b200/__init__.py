@@ -1,0 +1,214 @@
+"""modem_b200 — Python host mirror of the aicodix/modem receive path on B200 (sm_100a).
+
+The reference has no Python API; its interface for this path is `decode OUTPUT INPUT [SKIP]`
+(/root/reference/decode.cc:559-620).  This module is a thin ctypes layer over the C-ABI in include/ofdmrx.h
+(libofdmrx.so, hand-written CUDA) that mirrors that contract for batches of windows:
+
+    rx = Receiver(max_frames=4096)
+    payload, status = rx.decode(pcm_int16, channels=1, skip=0)        # == n x `decode out.dat window_i.wav [SKIP]`
+    payload, status = decode_wav("recorded.wav", skip=0)               # one WAV file, like the reference CLI
+
+There is NO CPU fallback: importing works anywhere, but creating a Receiver without the built extension or
+without a B200-class GPU raises.
+"""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libofdmrx.so")
+
+PAYLOAD_BYTES = 5380
+CODE_LEN = 65536
+FRAME_SAMPLES = 95200
+FMT_S16_MONO, FMT_S16_IQ, FMT_F32_IQ = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+ST_OK, ST_NO_SYNC, ST_OSD_FAIL, ST_HDR_CRC, ST_BAD_MODE, ST_BAD_CALL, ST_PAYLOAD_CRC, ST_UNSUPPORTED_MODE = range(8)
+STATUS_TEXT = {  # the reference's stderr strings (decode.cc:419,430,435,440,543)
+    ST_OK: "ok", ST_NO_SYNC: "no sync", ST_OSD_FAIL: "OSD error.", ST_HDR_CRC: "header CRC error.",
+    ST_BAD_MODE: "operation mode unsupported.", ST_BAD_CALL: "call sign unsupported.",
+    ST_PAYLOAD_CRC: "payload decoding error.", ST_UNSUPPORTED_MODE: "operation mode not built (7..13).",
+}
+TAP_IQ, TAP_TIMING, TAP_SOFT, TAP_CONS_RAW, TAP_CONS, TAP_TS, TAP_LLR = range(7)
+_TAP_DTYPE = {TAP_IQ: np.complex64, TAP_TIMING: np.float32, TAP_SOFT: np.int8, TAP_CONS_RAW: np.complex64,
+              TAP_CONS: np.complex64, TAP_TS: np.float32, TAP_LLR: np.float32}
+
+STATUS_DTYPE = np.dtype([
+    ("status", "<i4"), ("detections", "<i4"), ("t_fire", "<i4"), ("symbol_pos", "<i4"), ("sc_pos", "<i4"),
+    ("index_max", "<i4"), ("shift", "<i4"), ("pos_err", "<i4"), ("timing_max", "<f4"), ("frac_cfo", "<f4"),
+    ("cfo_rad", "<f4"), ("osd_unique", "<i4"), ("mode", "<i4"), ("md_lo", "<u4"), ("md_hi", "<u4"),
+    ("best_lane", "<i4"), ("flips", "<i4"), ("metrics", "<f4", (8,)), ("osd_visited", "<i4"), ("reserved", "<i4", (2,)),
+])
+assert STATUS_DTYPE.itemsize == 112
+
+EXPORTS = ["ofdmrx_create", "ofdmrx_destroy", "ofdmrx_set_option", "ofdmrx_decode_batch", "ofdmrx_polar_decode",
+           "ofdmrx_get_taps", "ofdmrx_tap_elems", "ofdmrx_last_launches", "ofdmrx_get_table", "ofdmrx_version"]
+
+_lib = None
+
+
+class OfdmrxError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libofdmrx.so (built in-tree by modem_b200/build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OfdmrxError("libofdmrx.so is not built (run `python -m modem_b200.build`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.ofdmrx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ofdmrx_destroy.argtypes = [C.c_void_p]
+    L.ofdmrx_destroy.restype = None
+    L.ofdmrx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    L.ofdmrx_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ofdmrx_polar_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ofdmrx_get_taps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.ofdmrx_tap_elems.argtypes = [C.c_void_p, C.c_int]
+    L.ofdmrx_tap_elems.restype = C.c_int64
+    L.ofdmrx_last_launches.argtypes = [C.c_void_p]
+    L.ofdmrx_get_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.ofdmrx_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise OfdmrxError("%s failed with code %d" % (what, rc))
+
+
+def base37_decode(val, length=9):
+    """decode.cc:155-159"""
+    tab = " 0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    out = []
+    for _ in range(length):
+        out.append(tab[val % 37])
+        val //= 37
+    return "".join(reversed(out))
+
+
+def call_sign(status_row):
+    md = (int(status_row["md_hi"]) << 32) | int(status_row["md_lo"])
+    return base37_decode(md >> 8)
+
+
+class Receiver:
+    """Batched stand-in for the reference's Decoder<float, Complex<float>, 8000> (decode.cc:161-557)."""
+
+    def __init__(self, device=0, max_frames=1024, max_samples=FRAME_SAMPLES, rate=8000, keep_taps=False, scl_ctas_per_sm=None):
+        self._lib = load()
+        self._h = C.c_void_p()
+        self.device, self.max_frames, self.max_samples = device, max_frames, max_samples
+        _check(self._lib.ofdmrx_create(C.byref(self._h), device, rate, max_frames, max_samples), "ofdmrx_create")
+        if scl_ctas_per_sm:
+            _check(self._lib.ofdmrx_set_option(self._h, b"scl_ctas_per_sm", int(scl_ctas_per_sm)), "set_option")
+        if keep_taps:
+            _check(self._lib.ofdmrx_set_option(self._h, b"keep_taps", 1), "set_option")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.ofdmrx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- host buffers (numpy; pass pinned memory for asynchronous copies) ------------------------------------
+    def decode(self, pcm, channels=1, n_samples=None, skip=0):
+        """pcm: int16 array [n_windows, stride*channels] (host).  Returns (payload uint8 [n,5380], status records)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if pcm.ndim == 1:
+            pcm = pcm.reshape(1, -1)
+        n, stride = pcm.shape[0], pcm.shape[1] // channels
+        payload = np.empty((n, PAYLOAD_BYTES), np.uint8)
+        status = np.zeros(n, STATUS_DTYPE)
+        ns = None if n_samples is None else np.ascontiguousarray(n_samples, np.int32)
+        self.decode_raw(pcm.ctypes.data, MEM_HOST, FMT_S16_MONO if channels == 1 else FMT_S16_IQ, n, stride,
+                        ns, skip, payload.ctypes.data, status.ctypes.data, None)
+        return payload, status
+
+    # ---- raw pointers (device memory from torch: tensor.data_ptr(); stream: torch.cuda.current_stream().cuda_stream)
+    def decode_raw(self, samples_ptr, mem_kind, fmt, n_frames, stride, n_samples, skip, payload_ptr, status_ptr, stream):
+        ns_ptr = n_samples.ctypes.data if n_samples is not None else None
+        _check(self._lib.ofdmrx_decode_batch(self._h, samples_ptr, mem_kind, fmt, n_frames, stride, ns_ptr, skip,
+                                             payload_ptr, status_ptr, stream), "ofdmrx_decode_batch")
+
+    def polar_decode(self, llr, want_xbits=False):
+        """llr: float32 [n, 65536] after lengthen().  Returns (payload, status[, xbits uint32 [n,8,2048]])."""
+        llr = np.ascontiguousarray(llr, np.float32).reshape(-1, CODE_LEN)
+        n = llr.shape[0]
+        payload = np.empty((n, PAYLOAD_BYTES), np.uint8)
+        status = np.zeros(n, STATUS_DTYPE)
+        xb = np.zeros((n, 8, 2048), np.uint32) if want_xbits else None
+        _check(self._lib.ofdmrx_polar_decode(self._h, llr.ctypes.data, n, payload.ctypes.data, status.ctypes.data,
+                                             xb.ctypes.data if xb is not None else None), "ofdmrx_polar_decode")
+        return (payload, status, xb) if want_xbits else (payload, status)
+
+    def taps(self, stage, first=0, count=1):
+        per = int(self._lib.ofdmrx_tap_elems(self._h, stage))
+        out = np.empty((count, per), _TAP_DTYPE[stage])
+        _check(self._lib.ofdmrx_get_taps(self._h, stage, first, count, out.ctypes.data, out.nbytes), "ofdmrx_get_taps")
+        if stage in (TAP_CONS_RAW, TAP_CONS):
+            return out.reshape(count, 50, 432)
+        if stage == TAP_TS:
+            return out.reshape(count, 50, 3)
+        return out
+
+    def table(self, which):
+        n = self._lib.ofdmrx_get_table(self._h, which, None, 0) if False else (2048 if which == 0 else 16384)
+        buf = np.zeros(n, np.uint32)
+        got = self._lib.ofdmrx_get_table(self._h, which, buf.ctypes.data, buf.nbytes)
+        if got < 0:
+            raise OfdmrxError("ofdmrx_get_table failed %d" % got)
+        return buf[:got]
+
+    @property
+    def last_launches(self):
+        return int(self._lib.ofdmrx_last_launches(self._h))
+
+
+def read_wav(path_or_bytes):
+    """Minimal RIFF/WAVE PCM reader (what DSP::ReadWAV delivers, decode.cc:576): returns (rate, channels, int16 [n, ch])."""
+    data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else open(path_or_bytes, "rb").read()
+    if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise ValueError("not a RIFF/WAVE file")
+    o, fmt = 12, None
+    while o + 8 <= len(data):
+        cid, sz = data[o:o + 4], struct.unpack("<I", data[o + 4:o + 8])[0]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", data[o + 8:o + 24])
+        elif cid == b"data":
+            if fmt is None or fmt[0] != 1:
+                raise ValueError("PCM WAV expected")
+            ch, rate, bits = fmt[1], fmt[2], fmt[5]
+            raw = data[o + 8:] if sz in (0, 0xFFFFFFFF) else data[o + 8:o + 8 + sz]
+            if bits == 16:
+                a = np.frombuffer(raw[:len(raw) // (2 * ch) * 2 * ch], "<i2").astype(np.int16)
+            elif bits == 8:  # to the 16-bit grid of v/127 -> nearest v16/32767
+                a8 = np.frombuffer(raw[:len(raw) // ch * ch], np.uint8).astype(np.float32) - 128.0
+                a = np.rint(a8 / 127.0 * 32767.0).astype(np.int16)
+            else:
+                raise ValueError("only 8/16-bit PCM is supported by this driver")
+            return rate, ch, a.reshape(-1, ch)
+        o += 8 + sz + (sz & 1)
+    raise ValueError("no data chunk")
+
+
+def decode_wav(path, skip=0, device=0):
+    """`decode OUTPUT INPUT [SKIP]` for one file: returns (5380 payload bytes, status record)."""
+    rate, ch, pcm = read_wav(path)
+    if rate != 8000:
+        raise OfdmrxError("Unsupported sample rate.")  # decode.cc:603-605 (16/44.1/48 kHz: not built yet)
+    if ch < 1 or ch > 2:
+        raise OfdmrxError("Only real or analytic signal (one or two channels) supported.")  # decode.cc:578-581
+    rx = Receiver(device=device, max_frames=1, max_samples=max(pcm.shape[0], 1))
+    try:
+        payload, status = rx.decode(pcm.reshape(1, -1), channels=ch, skip=skip)
+    finally:
+        rx.close()
+    return payload[0].tobytes(), status[0]

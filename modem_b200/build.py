@@ -1,0 +1,77 @@
+"""In-tree build of libofdmrx.so (CUDA kernels + C-ABI) and the `decode` host driver for sm_100a.
+
+nvcc cross-compiles without a GPU; the built artefacts stay in modem_b200/ (git-ignored, shipped to the GPU box).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "_build")
+LIB = os.path.join(PKG, "libofdmrx.so")
+DECODE = os.path.join(PKG, "decode")
+HOSTTEST = os.path.join(OBJ, "libhosttest.so")
+
+CU = ["polar.cu", "frontend.cu", "acquire.cu", "demod.cu", "ofdmrx.cu"]
+CC = ["host_tables.cc"]
+HDRS = ["common.cuh", "polar.cuh", "frontend.cuh", "fft.cuh", "host_tables.h", os.path.join("..", "..", "include", "ofdmrx.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
+              "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found: libofdmrx cannot be built (there is no CPU fallback)")
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _run(cmd, log):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log.append(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build step failed: " + " ".join(cmd))
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    hdrs = [os.path.join(CSRC, h) for h in HDRS] + [os.path.abspath(__file__)]
+    log, objs, rebuilt = [], [], False
+    for src in CU + CC:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            _run([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o], log)
+            rebuilt = True
+    if rebuilt or not os.path.exists(LIB):
+        _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"], log)
+    main = os.path.join(CSRC, "host", "decode_main.cc")
+    if os.path.exists(main) and (rebuilt or _stale(DECODE, [main, LIB])):
+        _run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), main, "-o", DECODE,
+              "-L", PKG, "-lofdmrx", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], log)
+    emu = os.path.join(ROOT, "tests", "scl_emulator.cc")
+    if os.path.exists(emu) and (force or _stale(HOSTTEST, [emu, os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "host_tables.h")])):
+        _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", emu, os.path.join(CSRC, "host_tables.cc"), "-o", HOSTTEST], log)
+    with open(os.path.join(OBJ, "build.log"), "a") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(LIB)

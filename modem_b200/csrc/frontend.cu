@@ -1,0 +1,362 @@
+// modem_b200/csrc/frontend.cu — sample ingest and Schmidl-Cox timing metric / detection.
+//
+// Replaces, for a batch of independent sample windows:
+//   K0  next_sample(): ReadWAV int16 -> float, BlockDC, Hilbert<21>          (/root/reference/decode.cc:294-301,386)
+//   K1a SchmidlCox::operator() metric part: P, R, timing = box161(|P|^2/R^2)  (decode.cc:86-91)
+//   K1b Schmitt trigger + falling edge + running arg-max -> detection list    (decode.cc:93-115)
+// The reference is a per-sample streaming state machine; here every sliding sum is a tile-parallel prefix-sum
+// difference, the IIR DC blocker is a linear-recurrence scan, and the hysteresis/arg-max logic is a scan over
+// {state -> state} maps, so a 95 200-sample window is processed by whole CTAs instead of one thread.
+// HBM-bound: K1a reads each IQ sample once from DRAM (8 B/sample; the 1439-sample tile halo comes from L2).
+#include "common.cuh"
+#include "frontend.cuh"
+
+namespace ofdmrx {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------ K0 mono
+// y[t] = b (x[t] - x[t-1]) + a y[t-1]  (BlockDC, a = 2879/2880), then the 21-tap Hilbert FIR.
+// One CTA per window, tiles of 2048 samples, 8 consecutive samples per thread; the recurrence is carried
+// across threads by a scan over (alpha, beta) pairs of the affine map y_out = alpha * y_in + beta.
+constexpr int kFeThreads = 256, kFePer = 8, kFeTile = kFeThreads * kFePer;
+
+__global__ void __launch_bounds__(kFeThreads) k_frontend_mono(const int16_t *pcm, int64_t pcm_stride, const int32_t *n_samples,
+	int n_default, cfx *iq, int64_t iq_stride, int iq_len, float dc_a, float dc_b, float reco, float im0, float im1, float im2, float im3, float im4)
+{
+	__shared__ float ybuf[20 + kFeTile];
+	__shared__ float2 wsum[kFeThreads / 32];
+	__shared__ float carry_y, carry_x;
+	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int n = n_samples ? n_samples[f] : n_default;
+	const int16_t *src = pcm + (size_t)f * pcm_stride;
+	cfx *dst = iq + (size_t)f * iq_stride;
+	if (tid < 20) ybuf[tid] = 0.f;
+	if (tid == 0) { carry_y = 0.f; carry_x = 0.f; }
+	__syncthreads();
+	float a8 = dc_a;
+	a8 = a8 * a8; a8 = a8 * a8; a8 = a8 * a8; // a^8
+	for (int t0 = 0; t0 < iq_len; t0 += kFeTile) {
+		float x[kFePer], u[kFePer];
+		const int tb = t0 + tid * kFePer;
+#pragma unroll
+		for (int k = 0; k < kFePer; ++k) {
+			const int t = tb + k;
+			x[k] = t < n ? (float)src[t] / 32767.f : 0.f;
+		}
+		float xprev = tid == 0 ? carry_x : (tb - 1 < n ? (float)src[tb - 1] / 32767.f : 0.f);
+		// local response with zero carry-in
+		float y = 0.f;
+#pragma unroll
+		for (int k = 0; k < kFePer; ++k) {
+			u[k] = dc_b * (x[k] - xprev);
+			xprev = x[k];
+			y = u[k] + dc_a * y;
+		}
+		// inclusive scan of (alpha, beta) over threads: compose earlier (A,B) then mine (a8,y) -> (A*a8, a8*B + y)
+		float al = a8, be = y;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const float pa = __shfl_up_sync(FULL, al, d), pb = __shfl_up_sync(FULL, be, d);
+			if (lane >= d) { be = al * pb + be; al = al * pa; }
+		}
+		if (lane == 31) wsum[wid] = make_float2(al, be);
+		__syncthreads();
+		// carry into this thread = state after all previous threads of the tile, starting from carry_y
+		float cy = carry_y;
+		for (int w = 0; w < wid; ++w) cy = wsum[w].x * cy + wsum[w].y;
+		{
+			const float pa = __shfl_up_sync(FULL, al, 1), pb = __shfl_up_sync(FULL, be, 1);
+			if (lane > 0) cy = pa * cy + pb;
+		}
+		float yy = cy;
+#pragma unroll
+		for (int k = 0; k < kFePer; ++k) {
+			yy = u[k] + dc_a * yy;
+			ybuf[20 + tid * kFePer + k] = yy;
+		}
+		__syncthreads();
+		if (tid == kFeThreads - 1) { carry_y = yy; carry_x = x[kFePer - 1]; }
+		// Hilbert: output t uses y[t-20 .. t-2]; ybuf[j] = y[t0 - 20 + j]
+#pragma unroll
+		for (int k = 0; k < kFePer; ++k) {
+			const int j = k * kFeThreads + tid; // coalesced store order
+			const int t = t0 + j;
+			if (t < iq_len) {
+				const float *c = &ybuf[j + 9]; // y[t-11]
+				const float re = reco * c[0];
+				float im = im0 * (c[-1] - c[1]);
+				im += im1 * (c[-3] - c[3]);
+				im += im2 * (c[-5] - c[5]);
+				im += im3 * (c[-7] - c[7]);
+				im += im4 * (c[-9] - c[9]);
+				dst[t] = make_float2(re, im);
+			}
+		}
+		__syncthreads();
+		if (tid < 20) ybuf[tid] = ybuf[kFeTile + tid];
+		__syncthreads();
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ K0 IQ int16 / float2
+__global__ void k_frontend_iq16(const int16_t *pcm, int64_t pcm_stride, const int32_t *n_samples, int n_default,
+	cfx *iq, int64_t iq_stride, int iq_len)
+{
+	const int f = blockIdx.y;
+	const int n = n_samples ? n_samples[f] : n_default;
+	const short2 *src = reinterpret_cast<const short2 *>(pcm + (size_t)f * pcm_stride * 2);
+	cfx *dst = iq + (size_t)f * iq_stride;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < iq_len; t += gridDim.x * blockDim.x) {
+		cfx v = make_float2(0.f, 0.f);
+		if (t < n) { const short2 s = src[t]; v = make_float2((float)s.x / 32767.f, (float)s.y / 32767.f); }
+		dst[t] = v;
+	}
+}
+__global__ void k_frontend_f32(const cfx *in, int64_t in_stride, const int32_t *n_samples, int n_default,
+	cfx *iq, int64_t iq_stride, int iq_len)
+{
+	const int f = blockIdx.y;
+	const int n = n_samples ? n_samples[f] : n_default;
+	const cfx *src = in + (size_t)f * in_stride;
+	cfx *dst = iq + (size_t)f * iq_stride;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < iq_len; t += gridDim.x * blockDim.x)
+		dst[t] = t < n ? src[t] : make_float2(0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ K1a timing metric
+// For stream index t (the sample just pushed): c[t] = a[t-5119] conj(a[t-4479]), e[t] = |a[t-4479]|^2,
+// P[t] = sum_{k<640} c[t-k], R[t] = max(0.5 sum_{k<1280} e[t-k], 0.064), m[t] = |P|^2/R^2,
+// timing[t] = sum_{k<161} m[t-k]  (decode.cc:86-90 with search_pos = 2880, buffer_len = 8640).
+// Tile of kMtTile outputs; extended index j = t - t0 + kMtHalo addresses a[t0 - 5918 + j].
+constexpr int kMtThreads = 256, kMtTile = 2048, kMtHalo = 1439, kMtExt = kMtTile + kMtHalo; // 3487
+constexpr int kMtPer = (kMtExt + kMtThreads - 1) / kMtThreads;                                 // 14
+constexpr int kMtPad = kMtThreads * kMtPer;                                                    // 3584
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v, int lane)
+{
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const T o = __shfl_up_sync(FULL, v, d);
+		if (lane >= d) v += o;
+	}
+	return v;
+}
+
+__global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples,
+	int n_default, float *timing, int64_t timing_stride)
+{
+	extern __shared__ float sm[];
+	cfx *sa = reinterpret_cast<cfx *>(sm);              // [kMtPad] samples
+	float *sre = sm + 2 * kMtPad;                       // prefix of c.re, later prefix of m
+	float *sim = sre + kMtPad;                          // prefix of c.im
+	float *se = sim + kMtPad;                           // prefix of e
+	__shared__ float wtot[3][kMtThreads / 32];
+	const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	const int n = n_samples ? n_samples[f] : n_default;
+	const int t0 = blockIdx.x * kMtTile;
+	if (t0 > n) return; // stream has n+1 steps: t = 0..n
+	const cfx *a = iq + (size_t)f * iq_stride;
+	const int base = t0 - 5918;
+	for (int j = tid; j < kMtPad; j += kMtThreads) {
+		const int idx = base + j;
+		sa[j] = (j < kMtExt && idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
+	}
+	__syncthreads();
+	// per-thread chunk [j0, j0+kMtPer): local sums of c and e, then block scan
+	const int j0 = tid * kMtPer;
+	float cre[kMtPer], cim[kMtPer], ce[kMtPer];
+	float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+	for (int k = 0; k < kMtPer; ++k) {
+		const int j = j0 + k;
+		const cfx cur = sa[j];
+		const cfx old = j >= 640 ? sa[j - 640] : make_float2(0.f, 0.f);
+		const cfx c = cmulc(old, cur);
+		s0 += c.x; s1 += c.y; s2 += cnorm(cur);
+		cre[k] = s0; cim[k] = s1; ce[k] = s2;
+	}
+	float w0 = warp_incl_scan(s0, lane), w1 = warp_incl_scan(s1, lane), w2 = warp_incl_scan(s2, lane);
+	if (lane == 31) { wtot[0][wid] = w0; wtot[1][wid] = w1; wtot[2][wid] = w2; }
+	__syncthreads();
+	float o0 = w0 - s0, o1 = w1 - s1, o2 = w2 - s2; // exclusive within warp
+	for (int w = 0; w < wid; ++w) { o0 += wtot[0][w]; o1 += wtot[1][w]; o2 += wtot[2][w]; }
+#pragma unroll
+	for (int k = 0; k < kMtPer; ++k) {
+		sre[j0 + k] = o0 + cre[k];
+		sim[j0 + k] = o1 + cim[k];
+		se[j0 + k] = o2 + ce[k];
+	}
+	__syncthreads();
+	// m[j] for j in [1279, kMtExt): needs prefix[j] - prefix[j-640] (c) and prefix[j] - prefix[j-1280] (e)
+	float mloc[kMtPer];
+	float ms = 0.f;
+#pragma unroll
+	for (int k = 0; k < kMtPer; ++k) {
+		const int j = j0 + k;
+		float m = 0.f;
+		if (j >= 1279 && j < kMtExt) {
+			const float pr = sre[j] - sre[j - 640], pi = sim[j] - sim[j - 640];
+			float r = 0.5f * (se[j] - (j >= 1280 ? se[j - 1280] : 0.f));
+			r = fmaxf(r, 0.064f);
+			m = __fdiv_rn(pr * pr + pi * pi, r * r);
+			// windows that start before the stream did (t < 0 contributions) are zero because a[<0] = 0
+		}
+		ms += m;
+		mloc[k] = ms;
+	}
+	__syncthreads(); // everyone is done reading sre before it is overwritten with the prefix of m
+	float wm = warp_incl_scan(ms, lane);
+	if (lane == 31) wtot[0][wid] = wm;
+	__syncthreads();
+	float om = wm - ms;
+	for (int w = 0; w < wid; ++w) om += wtot[0][w];
+#pragma unroll
+	for (int k = 0; k < kMtPer; ++k) sre[j0 + k] = om + mloc[k];
+	__syncthreads();
+	float *out = timing + (size_t)f * timing_stride;
+	for (int i = tid; i < kMtTile; i += kMtThreads) {
+		const int t = t0 + i;
+		if (t > n) break;
+		const int j = i + kMtHalo;
+		out[t] = sre[j] - sre[j - 161];
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ K1b detection
+// Schmitt trigger (low 0.17*161, high 0.19*161) + falling edge + first strict maximum inside each
+// [rise, fall] segment (decode.cc:93-108).  One CTA per window; the hysteresis is resolved with a scan over
+// the 4 possible {0,1}->{0,1} maps of each thread's chunk.
+constexpr int kDtThreads = 256;
+
+__global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples,
+	int n_default, Detection *det, int32_t *det_count)
+{
+	__shared__ unsigned char fmap[kDtThreads]; // bit0 = f(0), bit1 = f(1)
+	__shared__ unsigned char instate[kDtThreads];
+	__shared__ int ev_cnt[kDtThreads], ev_off[kDtThreads + 1];
+	__shared__ int ev_t[2 * kMaxDet + 2];
+	__shared__ int first_is_fall;
+	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+	const int n = (n_samples ? n_samples[f] : n_default) + 1; // steps t = 0..n_samples
+	const float *tm = timing + (size_t)f * timing_stride;
+	const float low = (float)(0.17 * kMatchLen), high = (float)(0.19 * kMatchLen);
+	const int per = (n + kDtThreads - 1) / kDtThreads;
+	const int b = tid * per, e = min(n, b + per);
+	// pass 1: the chunk as a map on the trigger state
+	bool s0 = false, s1 = true;
+	for (int t = b; t < e; ++t) {
+		const float v = tm[t];
+		if (s0) { if (v < low) s0 = false; } else { if (v > high) s0 = true; }
+		if (s1) { if (v < low) s1 = false; } else { if (v > high) s1 = true; }
+	}
+	fmap[tid] = (unsigned char)((s0 ? 1 : 0) | (s1 ? 2 : 0));
+	__syncthreads();
+	if (tid == 0) {
+		bool s = false;
+		for (int k = 0; k < kDtThreads; ++k) { instate[k] = s; s = (fmap[k] >> (s ? 1 : 0)) & 1; }
+	}
+	__syncthreads();
+	// pass 2: count edges (rise or fall) in my chunk, then write them in stream order
+	bool s = instate[tid];
+	int cnt = 0;
+	for (int t = b; t < e; ++t) {
+		const float v = tm[t];
+		const bool ns = s ? !(v < low) : (v > high);
+		cnt += ns != s;
+		s = ns;
+	}
+	ev_cnt[tid] = cnt;
+	__syncthreads();
+	if (tid == 0) {
+		int acc = 0;
+		for (int k = 0; k < kDtThreads; ++k) { ev_off[k] = acc; acc += ev_cnt[k]; }
+		ev_off[kDtThreads] = acc;
+		first_is_fall = 0; // the trigger starts low, so the first edge is always a rise
+	}
+	__syncthreads();
+	s = instate[tid];
+	int pos = ev_off[tid];
+	for (int t = b; t < e; ++t) {
+		const float v = tm[t];
+		const bool ns = s ? !(v < low) : (v > high);
+		if (ns != s) { if (pos < 2 * kMaxDet) ev_t[pos] = t; ++pos; }
+		s = ns;
+	}
+	__syncthreads();
+	const int n_ev = min(ev_off[kDtThreads], 2 * kMaxDet);
+	const int n_seg = n_ev / 2; // (rise, fall) pairs; an unfinished segment never fires
+	// segments: edges alternate rise, fall, rise, ...  One warp per segment finds the first strict maximum.
+	for (int sgi = tid >> 5; sgi < n_seg; sgi += kDtThreads / 32) {
+		const int rise = ev_t[2 * sgi], fall = ev_t[2 * sgi + 1];
+		float best = 0.f; // timing_max starts at 0 and only a strictly larger value replaces it
+		int bi = -1;
+		for (int t = rise + lane; t <= fall; t += 32) {
+			const float v = tm[t];
+			if (v > best) { best = v; bi = t; }
+		}
+#pragma unroll
+		for (int d = 16; d; d >>= 1) {
+			const float ob = __shfl_xor_sync(FULL, best, d);
+			const int oi = __shfl_xor_sync(FULL, bi, d);
+			if (oi >= 0 && (ob > best || (ob == best && (bi < 0 || oi < bi)))) { best = ob; bi = oi; }
+		}
+		if (lane == 0) {
+			Detection d;
+			d.t_fall = fall;
+			d.t_max = bi;
+			d.timing_max = best;
+			// index_max: match_del at the maximum, +1 per later collect/process step, capped (decode.cc:99-105)
+			d.index_max = bi < 0 ? 0 : min(kMatchDel + (fall - bi), kHalf + kGuardLen + kMatchDel);
+			det[(size_t)f * kMaxDet + sgi] = d;
+		}
+	}
+	if (tid == 0) det_count[f] = n_seg;
+}
+
+} // namespace
+
+cudaError_t launch_frontend(int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
+	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s)
+{
+	if (n_frames <= 0) return cudaSuccess;
+	if (format == 0) {
+		k_frontend_mono<<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len,
+			fc.dc_a, fc.dc_b, fc.reco, fc.imco[0], fc.imco[1], fc.imco[2], fc.imco[3], fc.imco[4]);
+	} else if (format == 1) {
+		dim3 g((iq_len + 1023) / 1024, n_frames);
+		k_frontend_iq16<<<g, 256, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len);
+	} else {
+		dim3 g((iq_len + 1023) / 1024, n_frames);
+		k_frontend_f32<<<g, 256, 0, s>>>((const cfx *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len);
+	}
+	return cudaGetLastError();
+}
+
+size_t sync_metric_smem() { return (size_t)5 * kMtPad * sizeof(float); }
+
+cudaError_t launch_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
+	float *timing, int64_t timing_stride, cudaStream_t s)
+{
+	if (n_frames <= 0) return cudaSuccess;
+	static bool attr = false;
+	if (!attr) {
+		cudaFuncSetAttribute(k_sync_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_metric_smem());
+		attr = true;
+	}
+	dim3 g((n_max + 1 + kMtTile - 1) / kMtTile, n_frames);
+	k_sync_metric<<<g, kMtThreads, sync_metric_smem(), s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
+	Detection *det, int32_t *det_count, cudaStream_t s)
+{
+	if (n_frames <= 0) return cudaSuccess;
+	k_sync_detect<<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count);
+	return cudaGetLastError();
+}
+
+} // namespace ofdmrx

@@ -1,0 +1,40 @@
+// modem_b200/csrc/frontend.cuh — interface of frontend.cu / acquire.cu / demod.cu launchers.
+#pragma once
+#include "common.cuh"
+
+namespace ofdmrx {
+
+constexpr int kMaxDet = 16; // Schmidl-Cox detections kept per window (more are dropped, documented in DESIGN.md)
+
+struct Detection {
+	int32_t t_fall;    // stream index of the falling-edge step (decode.cc:94)
+	int32_t t_max;     // stream index of the first strict maximum of the timing metric inside the segment
+	float timing_max;
+	int32_t index_max; // decode.cc:99-105
+};
+
+struct FrontendConsts {
+	float dc_a, dc_b;  // BlockDC for 2*(1280+160) samples (decode.cc:386)
+	float reco, imco[5];
+};
+
+struct AcquireConsts {
+	const cfx *tw1280, *tw640; // forward twiddles exp(-2 pi j k / N)
+	const cfx *kern640;        // conj(FFT640(MLS0 template)) / 640 (decode.cc:76-83)
+	const uint8_t *mls1;       // 255 scrambler bits (decode.cc:407)
+	const uint32_t *bch_rows;  // 71 x 8 words, systematic generator (decode.cc:378-384)
+};
+
+cudaError_t launch_frontend(int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
+	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s);
+cudaError_t launch_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
+	float *timing, int64_t timing_stride, cudaStream_t s);
+cudaError_t launch_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
+	Detection *det, int32_t *det_count, cudaStream_t s);
+cudaError_t launch_acquire(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s);
+cudaError_t launch_demod(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *st, int n_frames, const cfx *tw1280,
+	cfx *cons_raw, cfx *cons, float *ts_out, float *llr, cudaStream_t s);
+cudaError_t launch_compact(const FrameState *st, int n_frames, int *cw_list, int *n_cw, cudaStream_t s);
+
+} // namespace ofdmrx

@@ -1,0 +1,54 @@
+// modem_b200/csrc/host_tables.h — host-side constants of the mode-6 / 8 kHz receive path.
+//
+// Everything here is computed at handle creation from first principles (no table is copied from the
+// reference): frozen set (construction of /root/reference/freezer.cc:14-32), the successive-cancellation
+// node schedule derived from it, MLS sequences (decode.cc:184,187,238,407), the BCH(255,71) generator
+// (decode.cc:378-384), Hilbert coefficients (decode.cc:172,193), FFT twiddles, CRC tables (decode.cc:197-198).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace ofdmrx {
+
+// ---- fixed geometry: mode 6 at 8000 Hz (decode.cc:171-189, 305-312) ------------------------------------
+constexpr int kRate = 8000;
+constexpr int kSymLen = 1280, kGuardLen = 160, kPitch = 1440, kHalf = 640;
+constexpr int kBufferLen = 6 * kPitch;            // 8640
+constexpr int kSearchPos = kBufferLen - 4 * kPitch; // 2880
+constexpr int kMatchLen = 161, kMatchDel = 80;
+constexpr int kFilterLen = 21;
+constexpr int kConsCols = 432, kConsRows = 50, kModBits = 3, kConsCnt = 21600, kConsBits = 64800;
+constexpr int kCodeOrder = 16, kCodeLen = 65536, kMesgBits = 43808, kDataBits = 43040, kCrcBits = 43072, kDataBytes = 5380;
+constexpr int kHdrBits = 255, kHdrK = 71;
+constexpr long long kCallSignLimit = 129961739795077LL;
+
+// ---- frozen set ---------------------------------------------------------------------------------------------
+// bit i of word i/32 set => index i frozen.  make_frozen(16, 64800, 43072) == reference frozen_64800_43072.
+std::vector<uint32_t> make_frozen(int order, int n_tx, int k_info);
+
+// ---- SCL schedule -------------------------------------------------------------------------------------------
+// The decoder walks the polar tree above 32-leaf "word" blocks with a precomputed op list (identical for every
+// codeword, so a warp never diverges on it):
+//   F(l, idx)    alpha_{l-1}[i]   = f(alpha_l[i], alpha_l[i+h])                h = 2^(l-1)
+//   G(l, idx)    alpha_{l-1}[i]   = g(alpha_l[i], alpha_l[i+h], beta[idx+i])   (parent read through the left child's lane map)
+//   WORD(idx)    decode the 32 leaves idx..idx+31 (frozen mask word idx/32)
+//   R0(l, idx)   maximal all-frozen node: metric += sum of negative alpha_l, beta = 0
+//   C(l, idx)    beta[idx..idx+h) = perm(beta[idx..idx+h)) ^ beta[idx+h..idx+2h), compose lane maps
+enum SclOp : uint32_t { OP_F = 0, OP_G = 1, OP_WORD = 2, OP_R0 = 3, OP_C = 4, OP_END = 7 };
+static inline uint32_t scl_pack(uint32_t op, uint32_t level, uint32_t index) { return op | (level << 3) | ((index / 32) << 8); }
+static inline uint32_t scl_op(uint32_t w) { return w & 7; }
+static inline uint32_t scl_level(uint32_t w) { return (w >> 3) & 31; }
+static inline uint32_t scl_index(uint32_t w) { return (w >> 8) * 32; }
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order);
+
+// ---- misc sequences / codes -----------------------------------------------------------------------------------
+std::vector<uint8_t> mls_bits(int poly, int n);              // first n outputs of the Galois LFSR (reg = 1)
+std::vector<uint32_t> bch_generator_rows();                  // 71 rows x 8 words, bit j of row i = G[i][j], systematic [I|P]
+std::vector<float> hilbert_coeffs(int taps, float *reco);    // imag-branch coefficients for odd offsets 1,3,..
+std::vector<float> twiddles(int n, int sign);                // n complex values exp(sign*2*pi*j*k/n) as (re,im) pairs
+std::vector<float> mls0_kernel();                            // conj(FFT640(template))/640, 640 complex (decode.cc:76-83,236-244)
+void crc32_table(uint32_t poly, uint32_t *lut256);
+uint16_t crc16_u64(uint64_t v);                              // CRC-16 0xA8F4 over the 8 LE bytes (decode.cc:428-429)
+void base37_decode(char *str, long long val, int len);       // decode.cc:155-159
+
+} // namespace ofdmrx

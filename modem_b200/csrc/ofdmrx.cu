@@ -1,0 +1,350 @@
+// modem_b200/csrc/ofdmrx.cu — C-ABI (include/ofdmrx.h) and per-chunk orchestration of the receive kernels.
+//
+// Pipeline per chunk of windows (all on one stream, no host synchronisation between stages):
+//   K0 frontend (int16 -> analytic IQ)            frontend.cu     decode.cc:294-301
+//   K1a timing metric, K1b detection list         frontend.cu     decode.cc:84-108
+//   K2 fine sync + header (OSD, CRC-16)           acquire.cu      decode.cc:110-151, 398-447
+//   K3/K4 demod + Theil-Sen + LLRs                demod.cu        decode.cc:456-529
+//   compaction of header-ok windows -> K5 SCL     polar.cu        decode.cc:530-555, 613-615
+#include "common.cuh"
+#include "frontend.cuh"
+#include "polar.cuh"
+#include "../../include/ofdmrx.h"
+#include <cstring>
+#include <cstdlib>
+#include <vector>
+#include <new>
+
+using namespace ofdmrx;
+
+static_assert(sizeof(ofdmrx_frame_status) == sizeof(FrameState), "ABI status struct must mirror the device struct");
+
+struct ofdmrx_handle {
+	int device = 0, n_sm = 0;
+	int max_frames = 0, max_samples = 0, iq_len = 0;
+	bool keep_taps = false;
+	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0;
+	int launches = 0;
+	// constants
+	uint32_t *d_frozen = nullptr, *d_ops = nullptr, *d_msg_off = nullptr, *d_scr = nullptr, *d_bch = nullptr;
+	uint8_t *d_mls1 = nullptr;
+	cfx *d_tw1280 = nullptr, *d_tw640 = nullptr, *d_kern = nullptr;
+	FrontendConsts fc;
+	std::vector<uint32_t> h_frozen, h_ops;
+	// per-chunk scratch
+	void *d_in = nullptr; size_t in_bytes = 0;
+	int32_t *d_nsamp = nullptr;
+	cfx *d_iq = nullptr;
+	float *d_timing = nullptr;
+	Detection *d_det = nullptr;
+	int32_t *d_detcnt = nullptr;
+	FrameState *d_st = nullptr;
+	int8_t *d_soft = nullptr;
+	cfx *d_cons_raw = nullptr, *d_cons = nullptr;
+	float *d_ts = nullptr, *d_llr = nullptr;
+	int *d_cwlist = nullptr, *d_ncw = nullptr;
+	uint32_t *d_payload = nullptr;
+	float *d_A = nullptr; uint32_t *d_B = nullptr;
+	uint32_t *d_xbits = nullptr; size_t xbits_frames = 0;
+	int last_chunk_frames = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T **p, size_t count)
+{
+	OFDMRX_CUDA_TRY(cudaMalloc((void **)p, count * sizeof(T)));
+	return 0;
+}
+template <typename T>
+int dev_upload(T **p, const void *src, size_t count)
+{
+	OFDMRX_CUDA_TRY(cudaMalloc((void **)p, count * sizeof(T)));
+	OFDMRX_CUDA_TRY(cudaMemcpy(*p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+int ensure_scl_scratch(ofdmrx_handle *h)
+{
+	if (h->d_A) return 0;
+	int occ = scl_occupancy_ctas_per_sm();
+	if (occ < 1) occ = 1;
+	int want = h->scl_ctas_per_sm > 0 ? h->scl_ctas_per_sm : 2;
+	if (const char *e = std::getenv("OFDMRX_SCL_CTAS_PER_SM")) want = std::atoi(e);
+	if (want > occ) want = occ;
+	if (want < 1) want = 1;
+	h->scl_ctas_per_sm = want;
+	h->scl_grid = want * h->n_sm;
+	// never allocate scratch for more warps than a full chunk can occupy
+	int need_warps = (h->max_frames + 3) / 4;
+	int warps = h->scl_grid * (kSclThreads / 32);
+	while (h->scl_grid > 1 && (h->scl_grid - 1) * (kSclThreads / 32) >= need_warps) { --h->scl_grid; }
+	warps = h->scl_grid * (kSclThreads / 32);
+	h->scl_warps = warps;
+	if (int r = dev_alloc(&h->d_A, (size_t)warps * kSclWarpFloats)) return r;
+	if (int r = dev_alloc(&h->d_B, (size_t)warps * kSclWarpWords)) return r;
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ofdmrx_version(void) { return "ofdmrx 0.1 (sm_100a; mode 6 @ 8 kHz; SCL L=8)"; }
+
+int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int max_samples)
+{
+	if (!out || rate_hz != kRate || max_frames < 1 || max_samples < 1) return -22;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
+		std::fprintf(stderr, "ofdmrx: no CUDA device %d (there is no CPU fallback)\n", device);
+		return -19;
+	}
+	OFDMRX_CUDA_TRY(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	OFDMRX_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) {
+		std::fprintf(stderr, "ofdmrx: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
+		return -19;
+	}
+	ofdmrx_handle *h = new (std::nothrow) ofdmrx_handle;
+	if (!h) return -12;
+	h->device = device;
+	h->n_sm = prop.multiProcessorCount;
+	h->max_frames = max_frames;
+	h->max_samples = max_samples;
+	h->iq_len = ((max_samples + 1 + 127) / 128) * 128; // stream steps t = 0..n, padded
+	// ---- constant tables
+	h->h_frozen = make_frozen(kCodeOrder, kConsBits, kCrcBits);
+	h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder);
+	std::vector<uint32_t> msg_off(2048);
+	{
+		uint32_t acc = 0;
+		for (int w = 0; w < 2048; ++w) { msg_off[w] = acc; acc += 32 - __builtin_popcount(h->h_frozen[w]); }
+	}
+	std::vector<uint32_t> scr(kDataBytes / 4, 0);
+	{
+		uint32_t y = 2463534242u; // CODE::Xorshift32 (decode.cc:613-615)
+		for (int i = 0; i < kDataBytes; ++i) {
+			y ^= y << 13; y ^= y >> 17; y ^= y << 5;
+			scr[i / 4] |= (uint32_t)(y & 255u) << (8 * (i % 4));
+		}
+	}
+	std::vector<uint32_t> bch = bch_generator_rows();
+	std::vector<uint8_t> mls1 = mls_bits(0b100101011, 255);
+	std::vector<float> tw1280 = twiddles(kSymLen, -1), tw640 = twiddles(kHalf, -1), kern = mls0_kernel();
+	float reco;
+	std::vector<float> imco = hilbert_coeffs(kFilterLen, &reco);
+	h->fc.dc_a = float(2 * kPitch - 1) / float(2 * kPitch);
+	h->fc.dc_b = (1.f + h->fc.dc_a) / 2.f;
+	h->fc.reco = reco;
+	for (int i = 0; i < 5; ++i) h->fc.imco[i] = imco[i];
+	int r = 0;
+	if (!r) r = dev_upload(&h->d_frozen, h->h_frozen.data(), 2048);
+	if (!r) r = dev_upload(&h->d_ops, h->h_ops.data(), h->h_ops.size());
+	if (!r) r = dev_upload(&h->d_msg_off, msg_off.data(), 2048);
+	if (!r) r = dev_upload(&h->d_scr, scr.data(), scr.size());
+	if (!r) r = dev_upload(&h->d_bch, bch.data(), bch.size());
+	if (!r) r = dev_upload(&h->d_mls1, mls1.data(), mls1.size());
+	if (!r) r = dev_upload(&h->d_tw1280, tw1280.data(), (size_t)kSymLen);
+	if (!r) r = dev_upload(&h->d_tw640, tw640.data(), (size_t)kHalf);
+	if (!r) r = dev_upload(&h->d_kern, kern.data(), (size_t)kHalf);
+	// ---- per-chunk scratch
+	const size_t F = (size_t)max_frames;
+	h->in_bytes = F * (size_t)max_samples * sizeof(cfx); // large enough for any supported input format
+	if (!r) r = dev_alloc((char **)&h->d_in, F * (size_t)max_samples * 4); // int16 IQ is the widest staged host format (float2 is staged in two halves? no: see decode)
+	if (!r) r = dev_alloc(&h->d_nsamp, F);
+	if (!r) r = dev_alloc(&h->d_iq, F * (size_t)h->iq_len);
+	if (!r) r = dev_alloc(&h->d_timing, F * (size_t)h->iq_len);
+	if (!r) r = dev_alloc(&h->d_det, F * kMaxDet);
+	if (!r) r = dev_alloc(&h->d_detcnt, F);
+	if (!r) r = dev_alloc(&h->d_st, F);
+	if (!r) r = dev_alloc(&h->d_soft, F * 256);
+	if (!r) r = dev_alloc(&h->d_llr, F * (size_t)kCodeLen);
+	if (!r) r = dev_alloc(&h->d_cwlist, F);
+	if (!r) r = dev_alloc(&h->d_ncw, (size_t)1);
+	if (!r) r = dev_alloc(&h->d_payload, F * (size_t)(kDataBytes / 4));
+	if (r) { ofdmrx_destroy(h); return r; }
+	h->in_bytes = F * (size_t)max_samples * 4;
+	*out = h;
+	return 0;
+}
+
+void ofdmrx_destroy(ofdmrx_t *h)
+{
+	if (!h) return;
+	cudaSetDevice(h->device);
+	void *ptrs[] = {h->d_frozen, h->d_ops, h->d_msg_off, h->d_scr, h->d_bch, h->d_mls1, h->d_tw1280, h->d_tw640, h->d_kern, h->d_in,
+		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr,
+		h->d_cwlist, h->d_ncw, h->d_payload, h->d_A, h->d_B, h->d_xbits};
+	for (void *p : ptrs) if (p) cudaFree(p);
+	delete h;
+}
+
+int ofdmrx_set_option(ofdmrx_t *h, const char *key, int value)
+{
+	if (!h || !key) return -22;
+	if (!std::strcmp(key, "keep_taps")) {
+		h->keep_taps = value != 0;
+		if (h->keep_taps && !h->d_cons) {
+			cudaSetDevice(h->device);
+			const size_t F = (size_t)h->max_frames;
+			int r = dev_alloc(&h->d_cons_raw, F * kConsCnt);
+			if (!r) r = dev_alloc(&h->d_cons, F * kConsCnt);
+			if (!r) r = dev_alloc(&h->d_ts, F * kConsRows * 3);
+			return r;
+		}
+		return 0;
+	}
+	if (!std::strcmp(key, "scl_ctas_per_sm")) {
+		if (h->d_A) return -16; // scratch already sized
+		h->scl_ctas_per_sm = value;
+		return 0;
+	}
+	return -22;
+}
+
+int ofdmrx_last_launches(ofdmrx_t *h) { return h ? h->launches : -22; }
+
+int ofdmrx_get_table(ofdmrx_t *h, int which, void *dst, size_t bytes)
+{
+	if (!h || !dst) return -22;
+	cudaSetDevice(h->device);
+	const void *src = which == 0 ? (const void *)h->d_frozen : (const void *)h->d_ops;
+	const size_t have = which == 0 ? 2048 * 4 : h->h_ops.size() * 4;
+	if (bytes > have) bytes = have;
+	OFDMRX_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+	return (int)(have / 4);
+}
+
+static int run_chunk(ofdmrx_handle *h, const void *d_samples, int format, int nf, int64_t stride, const int32_t *h_nsamp, int skip, cudaStream_t s)
+{
+	int n_default = (int)std::min<int64_t>(stride, h->max_samples), n_max = n_default;
+	const int32_t *d_ns = nullptr;
+	if (h_nsamp) {
+		n_max = 0;
+		for (int i = 0; i < nf; ++i) {
+			if (h_nsamp[i] < 0 || h_nsamp[i] > h->max_samples || h_nsamp[i] > stride) return -22;
+			n_max = std::max(n_max, (int)h_nsamp[i]);
+		}
+		OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_nsamp, h_nsamp, (size_t)nf * 4, cudaMemcpyHostToDevice, s));
+		d_ns = h->d_nsamp;
+	}
+	OFDMRX_CUDA_TRY(launch_frontend(format, d_samples, stride, d_ns, n_default, nf, h->d_iq, h->iq_len, h->iq_len, h->fc, s));
+	OFDMRX_CUDA_TRY(launch_sync_metric(h->d_iq, h->iq_len, h->iq_len, d_ns, n_default, n_max, nf, h->d_timing, h->iq_len, s));
+	OFDMRX_CUDA_TRY(launch_sync_detect(h->d_timing, h->iq_len, d_ns, n_default, nf, h->d_det, h->d_detcnt, s));
+	AcquireConsts ac{h->d_tw1280, h->d_tw640, h->d_kern, h->d_mls1, h->d_bch};
+	OFDMRX_CUDA_TRY(launch_acquire(h->d_iq, h->iq_len, h->iq_len, h->d_det, h->d_detcnt, skip, nf, h->d_st, h->d_soft, ac, s));
+	OFDMRX_CUDA_TRY(launch_demod(h->d_iq, h->iq_len, h->iq_len, h->d_st, nf, h->d_tw1280, h->keep_taps ? h->d_cons_raw : nullptr,
+		h->keep_taps ? h->d_cons : nullptr, h->keep_taps ? h->d_ts : nullptr, h->d_llr, s));
+	OFDMRX_CUDA_TRY(launch_compact(h->d_st, nf, h->d_cwlist, h->d_ncw, s));
+	OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, s));
+	if (int r = ensure_scl_scratch(h)) return r;
+	SclParams p{};
+	p.llr = h->d_llr; p.cw_list = h->d_cwlist; p.n_cw = 0; p.n_cw_ptr = h->d_ncw; p.A = h->d_A; p.B = h->d_B;
+	p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr;
+	OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
+	h->launches += 8;
+	h->last_chunk_frames = nf;
+	return 0;
+}
+
+int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int format, int n_frames, int64_t stride,
+	const int32_t *n_samples, int skip, uint8_t *payload_out, ofdmrx_frame_status *status_out, void *stream)
+{
+	if (!h || !samples || n_frames < 0 || stride < 1 || format < 0 || format > 2 || skip < 0 || !payload_out) return -22;
+	if (format == OFDMRX_FMT_F32_IQ && mem_kind == OFDMRX_MEM_HOST) return -22; // float2 windows are accepted from device memory only
+	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
+	cudaStream_t s = (cudaStream_t)stream;
+	h->launches = 0;
+	const size_t frame_bytes = (size_t)stride * (format == 0 ? 2 : format == 1 ? 4 : 8);
+	for (int f0 = 0; f0 < n_frames; f0 += h->max_frames) {
+		const int nf = std::min(h->max_frames, n_frames - f0);
+		const char *src = (const char *)samples + (size_t)f0 * frame_bytes;
+		const void *d_src = src;
+		if (mem_kind == OFDMRX_MEM_HOST) {
+			if ((size_t)nf * frame_bytes > h->in_bytes) return -27;
+			OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_in, src, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, s));
+			d_src = h->d_in;
+		}
+		if (int r = run_chunk(h, d_src, format, nf, stride, n_samples ? n_samples + f0 : nullptr, skip, s)) return r;
+		const cudaMemcpyKind k = mem_kind == OFDMRX_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+		OFDMRX_CUDA_TRY(cudaMemcpyAsync(payload_out + (size_t)f0 * kDataBytes, h->d_payload, (size_t)nf * kDataBytes, k, s));
+		if (status_out) OFDMRX_CUDA_TRY(cudaMemcpyAsync(status_out + f0, h->d_st, (size_t)nf * sizeof(FrameState), k, s));
+		// the chunk scratch is reused by the next chunk: order the copies before it (same stream) — nothing to do
+	}
+	if (mem_kind == OFDMRX_MEM_HOST) OFDMRX_CUDA_TRY(cudaStreamSynchronize(s));
+	return 0;
+}
+
+int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_out, ofdmrx_frame_status *status_out, uint32_t *xbits)
+{
+	if (!h || !llr || n < 0 || !payload_out) return -22;
+	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
+	h->launches = 0;
+	if (int r = ensure_scl_scratch(h)) return r;
+	cudaStream_t s = nullptr;
+	for (int f0 = 0; f0 < n; f0 += h->max_frames) {
+		const int nf = std::min(h->max_frames, n - f0);
+		OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_llr, llr + (size_t)f0 * kCodeLen, (size_t)nf * kCodeLen * 4, cudaMemcpyHostToDevice, s));
+		OFDMRX_CUDA_TRY(cudaMemsetAsync(h->d_st, 0, (size_t)nf * sizeof(FrameState), s));
+		OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, s));
+		if (xbits && h->xbits_frames < (size_t)nf) {
+			if (h->d_xbits) cudaFree(h->d_xbits);
+			h->d_xbits = nullptr;
+			if (int r = dev_alloc(&h->d_xbits, (size_t)nf * 8 * 2048)) return r;
+			h->xbits_frames = nf;
+		}
+		SclParams p{};
+		p.llr = h->d_llr; p.cw_list = nullptr; p.n_cw = nf; p.n_cw_ptr = nullptr; p.A = h->d_A; p.B = h->d_B;
+		p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st;
+		p.xbits = xbits ? h->d_xbits : nullptr;
+		OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
+		h->launches += 2;
+		OFDMRX_CUDA_TRY(cudaMemcpyAsync(payload_out + (size_t)f0 * kDataBytes, h->d_payload, (size_t)nf * kDataBytes, cudaMemcpyDeviceToHost, s));
+		if (status_out) OFDMRX_CUDA_TRY(cudaMemcpyAsync(status_out + f0, h->d_st, (size_t)nf * sizeof(FrameState), cudaMemcpyDeviceToHost, s));
+		if (xbits) OFDMRX_CUDA_TRY(cudaMemcpyAsync(xbits + (size_t)f0 * 8 * 2048, h->d_xbits, (size_t)nf * 8 * 2048 * 4, cudaMemcpyDeviceToHost, s));
+		OFDMRX_CUDA_TRY(cudaStreamSynchronize(s));
+	}
+	return 0;
+}
+
+int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage)
+{
+	if (!h) return -22;
+	switch (stage) {
+	case OFDMRX_TAP_IQ: case OFDMRX_TAP_TIMING: return h->iq_len;
+	case OFDMRX_TAP_SOFT: return 256;
+	case OFDMRX_TAP_CONS_RAW: case OFDMRX_TAP_CONS: return kConsCnt;
+	case OFDMRX_TAP_TS: return kConsRows * 3;
+	case OFDMRX_TAP_LLR: return kCodeLen;
+	}
+	return -22;
+}
+
+int ofdmrx_get_taps(ofdmrx_t *h, int stage, int first, int count, void *dst, size_t bytes)
+{
+	if (!h || !dst || first < 0 || count < 0 || first + count > h->max_frames) return -22;
+	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
+	const void *src = nullptr;
+	size_t esz = 0;
+	switch (stage) {
+	case OFDMRX_TAP_IQ: src = h->d_iq; esz = sizeof(cfx); break;
+	case OFDMRX_TAP_TIMING: src = h->d_timing; esz = 4; break;
+	case OFDMRX_TAP_SOFT: src = h->d_soft; esz = 1; break;
+	case OFDMRX_TAP_CONS_RAW: src = h->d_cons_raw; esz = sizeof(cfx); break;
+	case OFDMRX_TAP_CONS: src = h->d_cons; esz = sizeof(cfx); break;
+	case OFDMRX_TAP_TS: src = h->d_ts; esz = 4; break;
+	case OFDMRX_TAP_LLR: src = h->d_llr; esz = 4; break;
+	default: return -22;
+	}
+	if (!src) return -61; // keep_taps was off
+	const size_t per = (size_t)ofdmrx_tap_elems(h, stage) * esz;
+	if (bytes < per * count) return -27;
+	OFDMRX_CUDA_TRY(cudaDeviceSynchronize());
+	OFDMRX_CUDA_TRY(cudaMemcpy(dst, (const char *)src + per * first, per * count, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,32 @@
+// modem_b200/csrc/polar.cuh — interface of the list decoder kernel (polar.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ofdmrx {
+
+constexpr int kSclThreads = 256;                       // 8 warps = 32 codewords per CTA
+constexpr size_t kSclWarpFloats = (size_t)(65536 - 32) * 32; // alpha levels 5..15, [element][warp lane]
+constexpr size_t kSclWarpWords = (size_t)2048 * 32;          // beta bits, [word][warp lane]
+__host__ __device__ constexpr size_t scl_off(int l) { return (size_t)((1 << l) - 32) * 32; }
+
+struct SclParams {
+	const float *llr;        // [frames][65536] channel LLRs after lengthen() (decode.cc:529)
+	const int *cw_list;      // frames to decode (compacted header-ok list) or nullptr for identity
+	int n_cw;                // number of codewords, or read from n_cw_ptr (device) when that is set
+	const int *n_cw_ptr;
+	float *A;                // scratch: resident warps x kSclWarpFloats
+	uint32_t *B;             // scratch: resident warps x kSclWarpWords
+	const uint32_t *ops;     // schedule (host_tables.cc)
+	const uint32_t *frozen;  // 2048 words
+	const uint32_t *msg_off; // number of non-frozen indices before word w
+	uint32_t *payload;       // [frames][1345] words pre-filled with the scrambler sequence
+	FrameState *st;
+	uint32_t *xbits;         // optional [n_cw][8][2048]: all candidates' codeword bits in rank order (tests)
+};
+
+int scl_resident_warps(int ctas_per_sm, int n_sm);
+int scl_occupancy_ctas_per_sm();
+cudaError_t launch_payload_init(uint32_t *payload, const uint32_t *scr_words, int n_frames, cudaStream_t s);
+cudaError_t launch_polar_scl(const SclParams &p, int grid, cudaStream_t s);
+
+} // namespace ofdmrx
