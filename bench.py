@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — decoded payload throughput of the mode-6 OFDM receive path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one pass of the whole hot path (ingest, Schmidl-Cox sync, header, demod, Theil-Sen, soft demap, polar list
+decoding, CRC, de-scramble) over one batch of F synthetic windows per GPU — BASELINE.json configs[1]: 10 000 mode-6
+frames, 8000 Hz 16-bit real, clean channel, produced by the oracle's restatement of the reference encoder.
+`value`: inputs resident in HBM, CUDA-event timed, max over ranks, one NCCL all-gather of the payload bytes per step
+when N > 1.  `e2e`: the same batch through the reference-facing C-ABI with HOST (pinned) buffers: H2D of the int16
+windows and D2H of payload + status inside the timed region.  `--impl reference` times the CPU oracle port
+(oracle/, "-Ofast -march=native" like the reference Makefile) on a bounded sample with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PAYLOAD_BITS = 43040
+FRAME_SAMPLES = 95200
+ALG_BYTES_SCL = 65536 * 4 + 5380            # per window: channel LLRs in, payload out
+ALG_FLOP_SCL = 25690112                     # L*(N/2*log2N)*6 + L*N at L = 8
+ALG_BYTES_CORR = FRAME_SAMPLES * 8          # one float2 read per IQ sample
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal CUDA-core peak; MEASURED_PEAKS.json has no FP32 figure
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(n, seed0, threads):
+    import oracle_lib as O
+    return O.encode_batch(n, seed0=seed0, nthreads=threads)
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of decode.cc on the box's host cores (the reference itself cannot be built: DESIGN.md)."""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    O.build()
+    cores = os.cpu_count() or 1
+    sample = max(64, min(2 * cores, 512))
+    pcm, ns, sent = make_batch(sample, 424242, cores)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        st, out = O.decode_batch(pcm, nthreads=cores, fast=True)
+        dt = time.perf_counter() - t
+        if it >= args.warmup:
+            times.append(dt)
+        assert (st == 0).all() and (out == sent).all()
+    total = sum(times)
+    fps = sample * len(times) / total
+    val = fps * PAYLOAD_BITS / 1e6
+    line = {
+        "impl": "reference", "metric": "decoded_payload_mbit_per_s", "value": val, "unit": "Mbit/s", "frames_per_s": fps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_note="bounded sample of %d windows per step on the host cores" % sample),
+        "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": "port",
+                         "sample": "%d clean mode-6 windows per step, %d steps, %d threads, oracle port built -Ofast -march=native" % (sample, len(times), cores)},
+        "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_note=None):
+    c = {"workload": "BASELINE configs[1]: %d mode-6 frames per GPU, 8000 Hz 16-bit real (1 channel) windows of 95200 samples, clean channel, batched decode" % args.frames,
+         "frames_per_gpu": args.frames, "list_size": 8, "parallelism": "frame-sharded x%d, one payload all-gather per step" % args.gpus,
+         "l2_policy": "inputs (%.2f GB int16 per GPU) and per-step scratch exceed the 126 MB L2" % (args.frames * FRAME_SAMPLES * 2 / 1e9)}
+    if sample_note:
+        c["sample"] = sample_note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=10000, help="windows per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="windows for the cpu_baseline leg (0 = 2 x cores)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import modem_b200 as M
+    from modem_b200.shard import gather_payload
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.frames
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    pcm_np, ns, sent = make_batch(n, 1000003 * rank, max(1, cores // world))
+    gen_s = time.time() - t0
+    host = torch.empty(pcm_np.shape, dtype=torch.int16).pin_memory()
+    host.copy_(torch.from_numpy(pcm_np))
+    dev_in = host.cuda(non_blocking=False)
+    payload = torch.empty((n, M.PAYLOAD_BYTES), dtype=torch.uint8, device="cuda")
+    status = torch.empty((n, 112), dtype=torch.uint8, device="cuda")
+    host_payload = torch.empty((n, M.PAYLOAD_BYTES), dtype=torch.uint8).pin_memory()
+    host_status = torch.empty((n, 112), dtype=torch.uint8).pin_memory()
+    rx = M.Receiver(device=local_rank, max_frames=n, scl_ctas_per_sm=int(os.environ.get("OFDMRX_SCL_CTAS_PER_SM", "3")))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        rx.decode_raw(dev_in.data_ptr(), M.MEM_DEVICE, M.FMT_S16_MONO, n, FRAME_SAMPLES, None, 0, payload.data_ptr(), status.data_ptr(), stream)
+        return gather_payload(payload, n * world) if world > 1 else payload
+
+    def step_e2e():
+        rx.decode_raw(host.data_ptr(), M.MEM_HOST, M.FMT_S16_MONO, n, FRAME_SAMPLES, None, 0, host_payload.data_ptr(), host_status.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        clk = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clk
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    total_ms, clocks = timed(step_device, args.steps, sampler)
+    stage_ms, n_chunk = rx.stage_times()
+    launches = rx.last_launches + (1 if world > 1 else 0)
+    # parity gate on the timed output (outside the timed region): every payload must equal the sent bytes
+    got = payload.cpu().numpy()
+    st = status.cpu().numpy().view(M.STATUS_DTYPE).reshape(-1)
+    bit_errors = int(np.unpackbits(got ^ sent, axis=1).sum())
+    frames_ok = int((st["status"] == 0).sum())
+    # e2e through the host-buffer C-ABI path
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+    e2e_err = int(np.unpackbits(host_payload.numpy() ^ sent, axis=1).sum())
+
+    if world > 1:
+        tot = torch.tensor([bit_errors + e2e_err, frames_ok], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tot)
+        bit_errors, frames_ok = int(tot[0].item()), int(tot[1].item())
+    if rank == 0:
+        ms_step = total_ms / args.steps
+        fps = n * world / (ms_step / 1e3)
+        e2e_fps = n * world / (e2e_ms / args.steps / 1e3)
+        hbm_peak, peak_src = measured_peaks()
+        scl_s = stage_ms["polar_scl"] / 1e3
+        corr_s = stage_ms["sync_metric"] / 1e3
+        line = {
+            "metric": "decoded_payload_mbit_per_s", "value": fps * PAYLOAD_BITS / 1e6, "unit": "Mbit/s", "frames_per_s": fps,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks,
+            "e2e": {"value": e2e_fps * PAYLOAD_BITS / 1e6, "unit": "Mbit/s", "frames_per_s": e2e_fps,
+                    "h2d_bytes_per_step": int(n * FRAME_SAMPLES * 2), "d2h_bytes_per_step": int(n * (M.PAYLOAD_BYTES + 112)),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches * args.steps,
+            "parity": {"payload_bit_errors_vs_sent": bit_errors, "frames_ok": frames_ok, "frames": n * world},
+            # dominant kernel = polar list decoder (k_polar_scl): share of the step from CUDA events on the launching stream
+            "roofline": {"kernel": "k_polar_scl", "bound": "hbm", "achieved": n_chunk * ALG_BYTES_SCL / scl_s / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": n_chunk * ALG_BYTES_SCL / scl_s / 1e9 / hbm_peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": stage_ms["polar_scl"], "share_of_step": stage_ms["polar_scl"] / sum(stage_ms.values()),
+                         "algorithmic_bytes_per_window": ALG_BYTES_SCL,
+                         "fp32": {"achieved_tflops": n_chunk * ALG_FLOP_SCL / scl_s / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
+                                  "frac": n_chunk * ALG_FLOP_SCL / scl_s / 1e12 / FP32_PEAK_TFLOPS,
+                                  "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak on file)",
+                                  "flop_per_window": ALG_FLOP_SCL}},
+            "roofline_correlator": {"kernel": "k_sync_metric", "bound": "hbm", "achieved": n_chunk * ALG_BYTES_CORR / corr_s / 1e9, "peak": hbm_peak,
+                                    "unit": "GB/s", "frac": n_chunk * ALG_BYTES_CORR / corr_s / 1e9 / hbm_peak, "traffic": None,
+                                    "kernel_ms": stage_ms["sync_metric"], "algorithmic_bytes_per_window": ALG_BYTES_CORR},
+            "stage_ms": stage_ms, "stimulus_gen_s": gen_s,
+        }
+        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(prof):
+            try:
+                t = json.load(open(prof))
+                line["roofline"]["traffic"] = t.get("k_polar_scl_dram_bytes_per_window")
+                line["roofline_correlator"]["traffic"] = t.get("k_sync_metric_dram_bytes_per_window")
+                line["roofline"]["traffic_note"] = "per window, from the committed ncu --set full capture (profiles/)"
+            except (ValueError, OSError):
+                pass
+        # CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N=1 only
+        if world == 1:
+            import oracle_lib as O
+            sample = args.cpu_sample or max(64, min(2 * cores, 512))
+            t = time.perf_counter()
+            cst, cout = O.decode_batch(pcm_np[:sample], nthreads=cores, fast=True)
+            dt = time.perf_counter() - t
+            assert (cout == got[:sample]).all(), "GPU payload differs from the CPU oracle"
+            line["cpu_baseline"] = {"value": sample / dt * PAYLOAD_BITS / 1e6, "unit": "Mbit/s", "frames_per_s": sample / dt, "cores": cores,
+                                    "kind": "port", "sample": "first %d windows of the same batch, %d threads, oracle port -Ofast -march=native; payloads equal the GPU's" % (sample, cores)}
+        print(json.dumps(line), flush=True)
+    rx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,10 @@ int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage);
 
 /* kernels launched by the last ofdmrx_decode_batch / ofdmrx_polar_decode call (bench.py's gpu_launches) */
 int ofdmrx_last_launches(ofdmrx_t *h);
+/* CUDA-event durations (ms, on the launching stream) of the stages of the LAST chunk processed by decode_batch:
+ * ms[0] frontend, [1] timing metric, [2] detection, [3] acquire (fine sync + header), [4] demod (FFT/Theil-Sen/LLR),
+ * [5] compaction + payload init, [6] polar list decoder.  Returns the number of windows in that chunk (<0 on error). */
+int ofdmrx_stage_times(ofdmrx_t *h, float *ms, int n);
 /* device-side copies of the constant tables, for tests: which = 0 frozen set (2048 u32), 1 SCL schedule */
 int ofdmrx_get_table(ofdmrx_t *h, int which, void *dst, size_t bytes);
 const char *ofdmrx_version(void);

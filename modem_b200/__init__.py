@@ -44,7 +44,9 @@ STATUS_DTYPE = np.dtype([
 assert STATUS_DTYPE.itemsize == 112
 
 EXPORTS = ["ofdmrx_create", "ofdmrx_destroy", "ofdmrx_set_option", "ofdmrx_decode_batch", "ofdmrx_polar_decode",
-           "ofdmrx_get_taps", "ofdmrx_tap_elems", "ofdmrx_last_launches", "ofdmrx_get_table", "ofdmrx_version"]
+           "ofdmrx_get_taps", "ofdmrx_tap_elems", "ofdmrx_last_launches", "ofdmrx_stage_times", "ofdmrx_get_table",
+           "ofdmrx_version"]
+STAGES = ["frontend", "sync_metric", "sync_detect", "acquire", "demod", "compact_init", "polar_scl"]
 
 _lib = None
 
@@ -72,6 +74,7 @@ def load():
     L.ofdmrx_tap_elems.argtypes = [C.c_void_p, C.c_int]
     L.ofdmrx_tap_elems.restype = C.c_int64
     L.ofdmrx_last_launches.argtypes = [C.c_void_p]
+    L.ofdmrx_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.ofdmrx_get_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.ofdmrx_version.restype = C.c_char_p
     _lib = L
@@ -112,9 +115,10 @@ class Receiver:
             _check(self._lib.ofdmrx_set_option(self._h, b"keep_taps", 1), "set_option")
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            self._lib.ofdmrx_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.ofdmrx_destroy(h)
+            h.value = None
 
     __del__ = close
 
@@ -166,6 +170,14 @@ class Receiver:
         if got < 0:
             raise OfdmrxError("ofdmrx_get_table failed %d" % got)
         return buf[:got]
+
+    def stage_times(self):
+        """CUDA-event durations (ms) of the stages of the last chunk -> (dict, windows in that chunk)."""
+        ms = np.zeros(7, np.float32)
+        n = self._lib.ofdmrx_stage_times(self._h, ms.ctypes.data, 7)
+        if n < 0:
+            raise OfdmrxError("ofdmrx_stage_times failed %d" % n)
+        return dict(zip(STAGES, [float(x) for x in ms])), int(n)
 
     @property
     def last_launches(self):

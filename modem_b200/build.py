@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
             _run([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o], log)
             rebuilt = True
     if rebuilt or not os.path.exists(LIB):
-        _run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"], log)
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"], log)
     main = os.path.join(CSRC, "host", "decode_main.cc")
     if os.path.exists(main) and (rebuilt or _stale(DECODE, [main, LIB])):
         _run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), main, "-o", DECODE,

@@ -1,0 +1,136 @@
+// modem_b200/csrc/host/decode_main.cc — `decode OUTPUT INPUT [SKIP]`: the reference receiver's command line
+// (/root/reference/decode.cc:559-620) as a thin C++ host driver over libofdmrx (include/ofdmrx.h).
+// Same argv rules, "-" for stdin/stdout, same stderr lines, always writes 5380 bytes and exits 0 once the WAV opened.
+// Extension: `decode --batch OUTPUT INPUT [SKIP]` treats INPUT as N back-to-back windows of 95200 frames (one
+// single-frame recording each) and writes N x 5380 bytes.  There is no CPU fallback: without a B200 it exits 1.
+#include "ofdmrx.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Wav {
+	int rate = 0, channels = 0, bits = 0;
+	std::vector<int16_t> pcm; // interleaved, converted to the 16-bit grid
+};
+
+bool parse_wav(const std::vector<uint8_t> &d, Wav &w)
+{
+	auto rd32 = [&](size_t o) { return (uint32_t)d[o] | (uint32_t)d[o + 1] << 8 | (uint32_t)d[o + 2] << 16 | (uint32_t)d[o + 3] << 24; };
+	auto rd16 = [&](size_t o) { return (uint32_t)d[o] | (uint32_t)d[o + 1] << 8; };
+	if (d.size() < 44 || std::memcmp(&d[0], "RIFF", 4) || std::memcmp(&d[8], "WAVE", 4)) return false;
+	size_t o = 12;
+	bool fmt = false;
+	while (o + 8 <= d.size()) {
+		uint32_t sz = rd32(o + 4);
+		if (!std::memcmp(&d[o], "fmt ", 4)) {
+			if (rd16(o + 8) != 1) return false;
+			w.channels = rd16(o + 10); w.rate = rd32(o + 12); w.bits = rd16(o + 22);
+			fmt = true;
+		} else if (!std::memcmp(&d[o], "data", 4)) {
+			if (!fmt || w.channels < 1) return false;
+			size_t avail = d.size() - (o + 8), n = (sz == 0 || sz == 0xffffffffu) ? avail : std::min<size_t>(sz, avail);
+			int bytes = w.bits / 8;
+			if (bytes < 1 || bytes > 4) return false;
+			size_t cnt = n / bytes / w.channels * w.channels;
+			w.pcm.resize(cnt);
+			for (size_t i = 0; i < cnt; ++i) {
+				const uint8_t *p = &d[o + 8 + i * bytes];
+				int32_t v = 0;
+				for (int b = 0; b < bytes; ++b) v |= (int32_t)p[b] << (8 * b);
+				if (bytes > 1 && bytes < 4 && (v & (1 << (8 * bytes - 1)))) v |= ~((1 << (8 * bytes)) - 1);
+				if (bytes == 1) v -= 128;
+				// ReadWAV scales by 1/(2^(bits-1)-1); the device ingests the 16-bit grid, so other depths are re-quantised
+				double x = (double)v / (double)((1u << (w.bits - 1)) - 1u);
+				w.pcm[i] = bytes == 2 ? (int16_t)v : (int16_t)std::lrint(std::max(-1.0, std::min(1.0, x)) * 32767.0);
+			}
+			return true;
+		}
+		o += 8 + sz + (sz & 1);
+	}
+	return false;
+}
+
+void base37(char *str, long long val, int len)
+{
+	for (int i = len - 1; i >= 0; --i, val /= 37) str[i] = " 0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ"[val % 37];
+}
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+	bool batch = argc > 1 && !std::strcmp(argv[1], "--batch");
+	if (batch) { --argc; ++argv; }
+	if (argc < 3 || argc > 4) {
+		std::cerr << "usage: " << argv[0] << " OUTPUT INPUT [SKIP]" << std::endl;
+		return 1;
+	}
+	std::string output_name = argv[1], input_name = argv[2];
+	if (output_name == "-") output_name = "/dev/stdout";
+	if (input_name == "-") input_name = "/dev/stdin";
+	std::ifstream in(input_name, std::ios::binary);
+	std::vector<uint8_t> raw((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+	Wav w;
+	if (!parse_wav(raw, w)) { std::cerr << "Couldn't open file \"" << input_name << "\" for reading." << std::endl; return 1; }
+	if (w.channels < 1 || w.channels > 2) {
+		std::cerr << "Only real or analytic signal (one or two channels) supported." << std::endl;
+		return 1;
+	}
+	int skip = argc > 3 ? std::atoi(argv[3]) : 0;
+	if (skip < 0) skip = 0;
+	if (w.rate != 8000) { // 16000/44100/48000 are valid for the reference (decode.cc:590-606) but not built here yet
+		std::cerr << "Unsupported sample rate." << std::endl;
+		return 1;
+	}
+	const int64_t total = (int64_t)w.pcm.size() / w.channels;
+	const int64_t stride = batch ? 95200 : std::max<int64_t>(total, 1);
+	const int n_frames = batch ? (int)(total / stride) : 1;
+	if (n_frames < 1) { std::cerr << "input shorter than one window" << std::endl; return 1; }
+	ofdmrx_t *h = nullptr;
+	int rc = ofdmrx_create(&h, 0, 8000, std::min(n_frames, 4096), (int)stride);
+	if (rc) { std::cerr << "ofdmrx_create failed (" << rc << "): a B200 is required, there is no CPU path" << std::endl; return 1; }
+	std::vector<uint8_t> out((size_t)n_frames * OFDMRX_PAYLOAD_BYTES);
+	std::vector<ofdmrx_frame_status> st(n_frames);
+	if (w.pcm.size() < (size_t)n_frames * stride * w.channels) w.pcm.resize((size_t)n_frames * stride * w.channels, 0);
+	std::vector<int32_t> ns(n_frames, (int32_t)std::min<int64_t>(stride, total));
+	rc = ofdmrx_decode_batch(h, w.pcm.data(), OFDMRX_MEM_HOST, w.channels == 1 ? OFDMRX_FMT_S16_MONO : OFDMRX_FMT_S16_IQ, n_frames, stride,
+		ns.data(), skip, out.data(), st.data(), nullptr);
+	ofdmrx_destroy(h);
+	if (rc) { std::cerr << "ofdmrx_decode_batch failed (" << rc << ")" << std::endl; return 1; }
+	for (int i = 0; i < n_frames; ++i) {
+		const ofdmrx_frame_status &s = st[i];
+		if (batch) std::cerr << "window " << i << ":" << std::endl;
+		if (s.detections > 0) {
+			std::cerr << "symbol pos: " << s.symbol_pos << std::endl;
+			std::cerr << "coarse cfo: " << s.cfo_rad * (8000 / 6.28318530717958647692f) << " Hz " << std::endl;
+		}
+		switch (s.status) {
+		case OFDMRX_ST_OSD_FAIL: std::cerr << "OSD error." << std::endl; break;
+		case OFDMRX_ST_HDR_CRC: std::cerr << "header CRC error." << std::endl; break;
+		case OFDMRX_ST_BAD_MODE: case OFDMRX_ST_UNSUPPORTED_MODE: std::cerr << "operation mode " << s.mode << " unsupported." << std::endl; break;
+		case OFDMRX_ST_BAD_CALL: std::cerr << "oper mode: " << s.mode << std::endl << "call sign unsupported." << std::endl; break;
+		default: break;
+		}
+		if (s.status == OFDMRX_ST_OK || s.status == OFDMRX_ST_PAYLOAD_CRC) {
+			char cs[10];
+			base37(cs, (long long)((((uint64_t)s.md_hi << 32) | s.md_lo) >> 8), 9);
+			cs[9] = 0;
+			std::cerr << "oper mode: " << s.mode << std::endl << "call sign: " << cs << std::endl;
+			std::cerr << "demod .................................................. done" << std::endl;
+			if (s.status == OFDMRX_ST_OK) std::cerr << "bit flips: " << s.flips << std::endl;
+			else std::cerr << "payload decoding error." << std::endl;
+		}
+	}
+	std::ofstream of(output_name, std::ios::binary | std::ios::trunc);
+	if (of.bad()) { std::cerr << "Couldn't open file \"" << output_name << "\" for writing." << std::endl; return 1; }
+	of.write(reinterpret_cast<const char *>(out.data()), out.size());
+	return 0;
+}

@@ -47,6 +47,8 @@ struct ofdmrx_handle {
 	float *d_A = nullptr; uint32_t *d_B = nullptr;
 	uint32_t *d_xbits = nullptr; size_t xbits_frames = 0;
 	int last_chunk_frames = 0;
+	cudaEvent_t ev[10] = {};
+	bool ev_valid = false;
 };
 
 namespace {
@@ -165,6 +167,7 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_cwlist, F);
 	if (!r) r = dev_alloc(&h->d_ncw, (size_t)1);
 	if (!r) r = dev_alloc(&h->d_payload, F * (size_t)(kDataBytes / 4));
+	for (int i = 0; i < 10 && !r; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) r = -12;
 	if (r) { ofdmrx_destroy(h); return r; }
 	h->in_bytes = F * (size_t)max_samples * 4;
 	*out = h;
@@ -179,6 +182,7 @@ void ofdmrx_destroy(ofdmrx_t *h)
 		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr,
 		h->d_cwlist, h->d_ncw, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
+	for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
 	delete h;
 }
 
@@ -207,6 +211,16 @@ int ofdmrx_set_option(ofdmrx_t *h, const char *key, int value)
 
 int ofdmrx_last_launches(ofdmrx_t *h) { return h ? h->launches : -22; }
 
+int ofdmrx_stage_times(ofdmrx_t *h, float *ms, int n)
+{
+	if (!h || !ms || n < 7) return -22;
+	if (!h->ev_valid) return -61;
+	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
+	OFDMRX_CUDA_TRY(cudaEventSynchronize(h->ev[7]));
+	for (int i = 0; i < 7; ++i) OFDMRX_CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+	return h->last_chunk_frames;
+}
+
 int ofdmrx_get_table(ofdmrx_t *h, int which, void *dst, size_t bytes)
 {
 	if (!h || !dst) return -22;
@@ -231,20 +245,29 @@ static int run_chunk(ofdmrx_handle *h, const void *d_samples, int format, int nf
 		OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_nsamp, h_nsamp, (size_t)nf * 4, cudaMemcpyHostToDevice, s));
 		d_ns = h->d_nsamp;
 	}
+	cudaEventRecord(h->ev[0], s);
 	OFDMRX_CUDA_TRY(launch_frontend(format, d_samples, stride, d_ns, n_default, nf, h->d_iq, h->iq_len, h->iq_len, h->fc, s));
+	cudaEventRecord(h->ev[1], s);
 	OFDMRX_CUDA_TRY(launch_sync_metric(h->d_iq, h->iq_len, h->iq_len, d_ns, n_default, n_max, nf, h->d_timing, h->iq_len, s));
+	cudaEventRecord(h->ev[2], s);
 	OFDMRX_CUDA_TRY(launch_sync_detect(h->d_timing, h->iq_len, d_ns, n_default, nf, h->d_det, h->d_detcnt, s));
+	cudaEventRecord(h->ev[3], s);
 	AcquireConsts ac{h->d_tw1280, h->d_tw640, h->d_kern, h->d_mls1, h->d_bch};
 	OFDMRX_CUDA_TRY(launch_acquire(h->d_iq, h->iq_len, h->iq_len, h->d_det, h->d_detcnt, skip, nf, h->d_st, h->d_soft, ac, s));
+	cudaEventRecord(h->ev[4], s);
 	OFDMRX_CUDA_TRY(launch_demod(h->d_iq, h->iq_len, h->iq_len, h->d_st, nf, h->d_tw1280, h->keep_taps ? h->d_cons_raw : nullptr,
 		h->keep_taps ? h->d_cons : nullptr, h->keep_taps ? h->d_ts : nullptr, h->d_llr, s));
+	cudaEventRecord(h->ev[5], s);
 	OFDMRX_CUDA_TRY(launch_compact(h->d_st, nf, h->d_cwlist, h->d_ncw, s));
 	OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, s));
 	if (int r = ensure_scl_scratch(h)) return r;
+	cudaEventRecord(h->ev[6], s);
 	SclParams p{};
 	p.llr = h->d_llr; p.cw_list = h->d_cwlist; p.n_cw = 0; p.n_cw_ptr = h->d_ncw; p.A = h->d_A; p.B = h->d_B;
 	p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr;
 	OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
+	cudaEventRecord(h->ev[7], s);
+	h->ev_valid = true;
 	h->launches += 8;
 	h->last_chunk_frames = nf;
 	return 0;

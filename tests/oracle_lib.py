@@ -93,7 +93,7 @@ def impair(multipath=False, cfo_hz=0.0, sfo_ppm=0.0, awgn_db=None, seed=1):
 def encode(payloads, rate=8000, channels=1, freq_off=2000, call_sign=b"CALLSIGN", mode=6, imp=None):
     payloads = np.ascontiguousarray(payloads, np.uint8).reshape(-1, DATA_BYTES)
     count = payloads.shape[0]
-    cap = 2 * rate + (2 + 53 * count) * (1440 * rate // 8000) + 64
+    cap = 2 * rate + (4 + 130 * count) * (1440 * rate // 8000) + 64  # up to 126 rows + 3 per frame (mode 13)
     out = np.zeros(cap * channels, np.int16)
     n = lib().ref_encode_pcm16(_p(payloads), count, rate, channels, freq_off, call_sign, mode,
                                C.byref(imp) if imp is not None else None, _p(out), cap)

@@ -1,0 +1,90 @@
+"""Host-side product logic (modem_b200/csrc/host_tables.cc) against the oracle, and the lane-array emulation of the
+CUDA list decoder's schedule / map algebra (tests/scl_emulator.cc) — all on CPU."""
+import ctypes as C
+
+import numpy as np
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_frozen_sets_match(oracle, hostlib):
+    for fn, table in (("host_frozen", 0), ("host_frozen_alt", 1)):
+        a, b = np.zeros(2048, np.uint32), np.zeros(2048, np.uint32)
+        getattr(hostlib, fn)(_p(a))
+        oracle.lib().ref_frozen_table(table, _p(b))
+        assert (a == b).all()
+
+
+def test_schedule_structure(hostlib):
+    n = hostlib.host_schedule(None, 0)
+    ops = np.zeros(n, np.uint32)
+    hostlib.host_schedule(_p(ops), n)
+    op, lvl, idx = ops & 7, (ops >> 3) & 31, (ops >> 8) * 32
+    assert op[-1] == 7 and (op[:-1] != 7).all()
+    fr = np.zeros(2048, np.uint32)
+    hostlib.host_frozen(_p(fr))
+    # every non-all-frozen word is decoded exactly once, in order; rate-0 nodes cover exactly the all-frozen words
+    words = idx[op == 2] // 32
+    assert (np.diff(words) > 0).all() and set(words) == set(np.nonzero(fr != 0xFFFFFFFF)[0])
+    covered = np.zeros(2048, bool)
+    for l, i in zip(lvl[op == 3], idx[op == 3]):
+        covered[i // 32:(i + (1 << l)) // 32] = True
+    assert (covered == (fr == 0xFFFFFFFF)).all()
+    # F, G, C come in matched triples per internal node
+    assert (op == 0).sum() == (op == 1).sum() == (op == 4).sum()
+    assert lvl[op == 0].max() == 16 and lvl[op == 0].min() == 6
+
+
+def test_tables_match_oracle(oracle, hostlib):
+    rows = np.zeros(71 * 8, np.uint32)
+    hostlib.host_bch_rows(_p(rows))
+    bits = np.unpackbits(rows.view(np.uint8), bitorder="little").reshape(71, 256)[:, :255]
+    G = np.zeros((71, 255), np.int8)
+    oracle.lib().ref_bch_genmat(_p(G))
+    assert (bits == G).all()
+    for poly, n in ((0b10001001, 127), (0b100101011, 255)):
+        a, b = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        hostlib.host_mls(poly, n, _p(a))
+        oracle.lib().ref_mls(poly, n, _p(b))
+        assert (a == b).all()
+    hostlib.host_crc16.restype = C.c_uint
+    hostlib.host_crc16.argtypes = [C.c_uint64]
+    assert hostlib.host_crc16(323559855980806 << 9) == 0xE724
+
+
+def _noisy(oracle, seed, sigma):
+    rng = np.random.default_rng(seed)
+    pl = oracle.make_payload(500 + seed)
+    code = np.zeros(64800, np.uint8)
+    oracle.lib().ref_payload_to_code(_p(pl), 6, _p(code))
+    y = (1.0 - 2.0 * code) + sigma * rng.standard_normal(64800)
+    llr = np.concatenate([2 * y / max(sigma, 0.3) ** 2, np.full(736, 9000.0)]).astype(np.float32)
+    return pl, llr
+
+
+def test_emulator_matches_oracle_bit_exact(oracle, hostlib):
+    """Same survivors (all 8 lanes), same fp32 metrics, at SNRs from clean to hopeless."""
+    for seed, sigma in enumerate([0.0, 0.55, 0.7, 0.76, 0.85]):
+        pl, llr = _noisy(oracle, seed, sigma)
+        best, lanes, met, payload, flips = oracle.polar_decode(llr)
+        el, em = np.zeros((8, 65536), np.uint8), np.zeros(8, np.float32)
+        hostlib.emu_polar_decode(_p(llr), _p(el), _p(em), None)
+        assert (el == lanes).all() and (em == met).all(), sigma
+        if sigma <= 0.7:
+            assert best == 0 and (payload == pl).all()
+
+
+def test_emulator_ties_and_zero_llrs(oracle, hostlib):
+    """Degenerate inputs: all-equal magnitudes (every fork ties) and exact zeros."""
+    pl, llr = _noisy(oracle, 9, 0.0)
+    for variant in range(2):
+        x = np.sign(llr).astype(np.float32) * 4.0
+        if variant:
+            x[::7] = 0.0
+        x[64800:] = 9000.0
+        best, lanes, met, payload, flips = oracle.polar_decode(x)
+        el, em = np.zeros((8, 65536), np.uint8), np.zeros(8, np.float32)
+        hostlib.emu_polar_decode(_p(x), _p(el), _p(em), None)
+        assert (el == lanes).all() and (em == met).all()
