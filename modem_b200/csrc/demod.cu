@@ -22,7 +22,7 @@ constexpr int kCols = kConsCols;           // 432
 constexpr int kPairs = kCols * (kCols - 1) / 2; // 93096
 constexpr int kRankSlope = kPairs / 2;      // element count/2 after nth_element
 constexpr int kRankYint = kCols / 2;
-constexpr int kBins = 256, kCandCap = 2048, kBinCap = 512;
+constexpr int kBins = 256, kCandCap = 4096, kBinCap = 2048;
 
 struct DmShared {
 	cfx buf0[kSymLen];
@@ -34,6 +34,8 @@ struct DmShared {
 	float cand[kCandCap];
 	int hist[kBins];
 	float red[kDmWarps][2];
+	double redd[kDmWarps][2];
+	int sel_lo, sel_shift, sel_k, sel_done;
 	int below, ncand, sel_bin, state;
 	int cmin, cmax; // ordered-int images of the smallest / largest collected quotient
 	float lo, hi, blo, bhi, result;
@@ -59,12 +61,126 @@ __device__ __forceinline__ void pair_terms(const float *y, float yi, int i, int 
 	else { diff = y[j] - yi; dist = dx; }
 }
 
+// k-th smallest (0-based) of v[0..n) in shared memory, exact: radix select on the order-preserving integer image of
+// the floats, 8 bits per level inside the [min,max] range, 256-bin shared histogram.  All threads of the CTA call.
+__device__ float select_kth(DmShared &s, const float *v, int n, int k, int tid)
+{
+	const int lane = tid & 31;
+	int mn = 0x7fffffff, mx = (int)0x80000000;
+	for (int i = tid; i < n; i += kDmThreads) { const int o = f2ord(v[i]); mn = min(mn, o); mx = max(mx, o); }
+#pragma unroll
+	for (int d = 16; d; d >>= 1) { mn = min(mn, __shfl_xor_sync(FULL, mn, d)); mx = max(mx, __shfl_xor_sync(FULL, mx, d)); }
+	if (tid == 0) { s.cmin = 0x7fffffff; s.cmax = (int)0x80000000; }
+	__syncthreads();
+	if (lane == 0) { atomicMin(&s.cmin, mn); atomicMax(&s.cmax, mx); }
+	__syncthreads();
+	if (tid == 0) {
+		const unsigned range = (unsigned)s.cmax - (unsigned)s.cmin;
+		int bits = 32 - __clz(range | 1u);
+		s.sel_lo = s.cmin;
+		s.sel_shift = max(0, bits - 8);
+		s.sel_k = k;
+		s.sel_done = 0;
+	}
+	__syncthreads();
+	for (int level = 0; level < 5; ++level) {
+		for (int b = tid; b < kBins; b += kDmThreads) s.hist[b] = 0;
+		__syncthreads();
+		const int lo = s.sel_lo, sh = s.sel_shift;
+		for (int i = tid; i < n; i += kDmThreads) {
+			const unsigned d = (unsigned)f2ord(v[i]) - (unsigned)lo; // wraps to a huge value when below lo
+			const unsigned b = d >> sh;
+			if (b < (unsigned)kBins) atomicAdd(&s.hist[b], 1);
+		}
+		__syncthreads();
+		if (tid == 0) {
+			int kk = s.sel_k, b = 0;
+			for (; b < kBins - 1; ++b) { if (kk < s.hist[b]) break; kk -= s.hist[b]; }
+			s.sel_lo = lo + (int)((unsigned)b << sh);
+			s.sel_k = kk;
+			if (sh == 0) s.sel_done = 1;
+			s.sel_shift = max(0, sh - 8);
+		}
+		__syncthreads();
+		if (s.sel_done) break;
+	}
+	return ord2f(s.sel_lo);
+}
+
+// pilot bracket: ordinary least squares slope c of y on x = i - 216 and the residual standard deviation.  The exact
+// Theil–Sen median lies within a few 1e-4 * sigma of c for Gaussian-like phase noise (its efficiency relative to OLS is
+// 0.955), so a sweep over [c - d, c + d) with d = 3.5e-4 sigma usually contains rank 46 548 and <= ~2500 quotients.
+__device__ void ols_pilot(DmShared &s, int tid, float &c, float &sigma)
+{
+	const int lane = tid & 31, wid = tid >> 5;
+	const bool act = tid < kCols;
+	const double x = (double)(tid - kCols / 2) + 0.5; // centred abscissa
+	const double yv = act ? (double)s.y[tid] : 0.0;
+	double a0 = yv, a1 = act ? x * yv : 0.0;
+#pragma unroll
+	for (int d = 16; d; d >>= 1) { a0 += __shfl_xor_sync(FULL, a0, d); a1 += __shfl_xor_sync(FULL, a1, d); }
+	if (lane == 0) { s.redd[wid][0] = a0; s.redd[wid][1] = a1; }
+	__syncthreads();
+	double sy = 0.0, sxy = 0.0;
+	for (int w = 0; w < kDmWarps; ++w) { sy += s.redd[w][0]; sxy += s.redd[w][1]; }
+	const double sxx = (double)kCols * ((double)kCols * kCols - 1.0) / 12.0;
+	const double slope = sxy / sxx, mean = sy / kCols;
+	__syncthreads();
+	double r = act ? yv - mean - slope * x : 0.0;
+	double r2 = r * r;
+#pragma unroll
+	for (int d = 16; d; d >>= 1) r2 += __shfl_xor_sync(FULL, r2, d);
+	if (lane == 0) s.redd[wid][0] = r2;
+	__syncthreads();
+	double ss = 0.0;
+	for (int w = 0; w < kDmWarps; ++w) ss += s.redd[w][0];
+	__syncthreads();
+	c = (float)slope;
+	sigma = (float)sqrt(ss / (kCols - 2));
+}
+
 // exact upper median of the pairwise slopes of (x = i - 216, y[i]); all threads of the CTA call
 __device__ float theil_sen_slope(DmShared &s, int tid)
 {
 	const int lane = tid & 31;
 	const bool act = tid < kCols;
 	const float yi = act ? s.y[tid] : 0.f;
+	// ---- fast path: one exact sweep over the OLS pilot bracket
+	{
+		float c, sigma;
+		ols_pilot(s, tid, c, sigma);
+		const float dlt = fmaxf(3.5e-4f * sigma, fmaxf(fabsf(c) * 4e-6f, 1e-10f));
+		const float blo = c - dlt, bhi = c + dlt;
+		if (tid == 0) { s.below = 0; s.ncand = 0; }
+		__syncthreads();
+		int cb = 0;
+		if (act) {
+			for (int dx = 1; dx <= 216; ++dx) {
+				if (dx == 216 && tid >= 216) break;
+				float diff; int dist;
+				pair_terms(s.y, yi, tid, dx, diff, dist);
+				const float sl = diff * __frcp_rn((float)dist);
+				const float mg = 1e-6f * fabsf(sl) + 1e-30f;
+				if (sl < blo - mg) ++cb;
+				else if (sl < bhi + mg) {
+					const float q = __fdiv_rn(diff, (float)dist);
+					if (q < blo) ++cb;
+					else if (q < bhi) {
+						const int p = atomicAdd(&s.ncand, 1);
+						if (p < kCandCap) s.cand[p] = q;
+					}
+				}
+			}
+		}
+#pragma unroll
+		for (int d = 16; d; d >>= 1) cb += __shfl_xor_sync(FULL, cb, d);
+		if (lane == 0 && cb) atomicAdd(&s.below, cb);
+		__syncthreads();
+		const int kk = kRankSlope - s.below, nc = s.ncand;
+		__syncthreads();
+		if (kk >= 0 && kk < nc && nc <= kCandCap) return select_kth(s, s.cand, nc, kk, tid);
+	}
+	// ---- general path (pilot missed: outliers, erased rows, very low SNR)
 	// seed bracket: quartiles of the 216 slopes with baseline 216
 	if (tid < 216) s.z[tid] = (s.y[tid + 216] - s.y[tid]) / 216.f;
 	__syncthreads();
@@ -162,16 +278,7 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 			if (lane == 0 && cb) atomicAdd(&s.below, cb);
 			__syncthreads();
 			const int kk = kRankSlope - s.below, nc = s.ncand;
-			if (kk >= 0 && kk < nc && nc <= kCandCap) {
-				for (int t = tid; t < nc; t += kDmThreads) {
-					const float v = s.cand[t];
-					int r = 0;
-					for (int j = 0; j < nc; ++j) { const float o = s.cand[j]; r += (o < v) || (o == v && j < t); }
-					if (r == kk) s.result = v;
-				}
-				__syncthreads();
-				return s.result;
-			}
+			if (kk >= 0 && kk < nc && nc <= kCandCap) { __syncthreads(); return select_kth(s, s.cand, nc, kk, tid); }
 			if (kk >= 0 && kk < nc && nc > kCandCap) {
 				// overflow: if every quotient of the bin is the same value (erased rows: all phases equal) that value is the answer
 				for (int t = tid; t < kCandCap; t += kDmThreads) { atomicMin(&s.cmin, f2ord(s.cand[t])); atomicMax(&s.cmax, f2ord(s.cand[t])); }
@@ -237,14 +344,7 @@ __global__ void __launch_bounds__(kDmThreads) k_demod(const cfx *iq, int64_t iq_
 		// intercept: upper median of y_i - slope * x_i (theil_sen.hh, recalled)
 		if (tid < kCols) s.z[tid] = __fsub_rn(s.y[tid], __fmul_rn(slope, (float)(tid - kCols / 2)));
 		__syncthreads();
-		if (tid < kCols) {
-			const float v = s.z[tid];
-			int r = 0;
-			for (int j = 0; j < kCols; ++j) { const float o = s.z[j]; r += (o < v) || (o == v && j < tid); }
-			if (r == kRankYint) s.result = v;
-		}
-		__syncthreads();
-		const float yint = s.result;
+		const float yint = select_kth(s, s.z, kCols, kRankYint, tid);
 		float lsp = 0.f, lnp = 0.f;
 		if (tid < kCols) {
 			const float th = -__fadd_rn(yint, __fmul_rn(slope, (float)(tid - kCols / 2)));

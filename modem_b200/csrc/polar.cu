@@ -5,8 +5,9 @@
 //   * one list lane per THREAD, one codeword per 8 threads, four codewords per warp.  Every codeword walks the
 //     same precomputed op schedule (host_tables.cc: the frozen set is fixed), so a warp never diverges and the
 //     only cross-thread traffic is 8-wide shuffles (lane permutation after a fork, fork ranking).
-//   * alpha (LLR) buffers of tree levels 5..15 live in a per-warp HBM/L2 scratch laid out [element][warp lane]
-//     so that every warp access is one coalesced 128-byte line, also when a thread reads through the lane map;
+//   * alpha (LLR) buffers of tree levels 5..15 live in a per-warp HBM/L2 scratch laid out [quad][warp lane][4]
+//     (a quad = 4 consecutive tree positions) so that every warp access is 512 coalesced bytes of 128-bit loads,
+//     also when a thread reads through the lane map;
 //     levels 0..4 (a 32-leaf "word") are fully unrolled and live in registers.
 //   * partial sums (beta) are bit-packed, 32 tree positions per word; at the root they ARE the re-encoded
 //     codeword, whose non-frozen positions are the systematic message (decode.cc:254-261) — no message/map
@@ -40,39 +41,43 @@ struct SclCtx {
 	uint32_t W;       // partial sums of the current 32-leaf word
 	uint32_t fmask;   // frozen mask of the current word
 	int t, gbase;     // my list lane (0..7), warp lane of lane 0 of my codeword
-	const float *A5;  // level-5 alpha buffer of this warp ([32][32])
+	const float4 *A5; // level-5 alpha buffer of this warp ([8 quads][32 lanes])
 };
 
+struct ForkResult { float metric; int src_bit; };
+
 // Free leaf: 2L forks, keep the L smallest by (metric, fork index); survivors land in rank order.
-__device__ __forceinline__ void leaf_fork(SclCtx &c, float a, int pos)
+// Not inlined: the 32-leaf word is fully unrolled around it and would otherwise carry 32 copies (I-cache).
+__device__ __noinline__ ForkResult leaf_fork(float metric, float a, int t, int gbase)
 {
 	const float pen = fabsf(a);
-	const float m0 = a < 0.f ? __fadd_rn(c.metric, pen) : c.metric; // decide 0
-	const float m1 = a < 0.f ? c.metric : __fadd_rn(c.metric, pen); // decide 1
+	const float m0 = a < 0.f ? __fadd_rn(metric, pen) : metric; // decide 0
+	const float m1 = a < 0.f ? metric : __fadd_rn(metric, pen); // decide 1
 	float o0[8], o1[8];
 	int r0 = 0, r1 = 0;
 #pragma unroll
 	for (int j = 0; j < 8; ++j) {
-		o0[j] = __shfl_sync(FULL, m0, c.gbase + j);
-		o1[j] = __shfl_sync(FULL, m1, c.gbase + j);
-		const bool lt = j < c.t, le = j <= c.t;
+		o0[j] = __shfl_sync(FULL, m0, gbase + j);
+		o1[j] = __shfl_sync(FULL, m1, gbase + j);
+		const bool lt = j < t, le = j <= t;
 		r0 += (o0[j] < m0) || (o0[j] == m0 && lt);
 		r0 += (o1[j] < m0) || (o1[j] == m0 && lt);
 		r1 += (o0[j] < m1) || (o0[j] == m1 && le);
 		r1 += (o1[j] < m1) || (o1[j] == m1 && lt);
 	}
 	const int packed = r0 | (r1 << 8);
-	int src = 0, bit = 0;
+	int sb = 0;
 	float nm = 0.f;
 #pragma unroll
 	for (int j = 0; j < 8; ++j) {
-		const int pr = __shfl_sync(FULL, packed, c.gbase + j);
-		if ((pr & 255) == c.t) { src = j; bit = 0; nm = o0[j]; }
-		if ((pr >> 8) == c.t) { src = j; bit = 1; nm = o1[j]; }
+		const int pr = __shfl_sync(FULL, packed, gbase + j);
+		if ((pr & 255) == t) { sb = j; nm = o0[j]; }
+		if ((pr >> 8) == t) { sb = j | 8; nm = o1[j]; }
 	}
-	c.metric = nm;
-	c.ret = src;
-	c.W |= (uint32_t)bit << pos;
+	ForkResult r;
+	r.metric = nm;
+	r.src_bit = sb;
+	return r;
 }
 
 // One node of the 32-leaf word, LVL = log2(size), BASE = first leaf.  `a` = this node's alpha values in
@@ -94,27 +99,50 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 		}
 	}
 	if constexpr (LVL == 0) {
-		leaf_fork(c, a[0], BASE);
+		const ForkResult r = leaf_fork(c.metric, a[0], c.t, c.gbase);
+		c.metric = r.metric;
+		c.ret = r.src_bit & 7;
+		c.W |= (uint32_t)(r.src_bit >> 3) << BASE;
 	} else {
 		constexpr int H = N / 2;
 		float ch[H];
-		const int own = c.gbase + c.t;
+		if constexpr (LVL == 5) {
+			float4 v[8];
+			const int own = c.gbase + c.t;
 #pragma unroll
-		for (int k = 0; k < H; ++k) {
-			float pa, pb;
-			if constexpr (LVL == 5) { pa = c.A5[k * 32 + own]; pb = c.A5[(k + H) * 32 + own]; }
-			else { pa = a[k]; pb = a[k + H]; }
-			ch[k] = f_op(pa, pb);
+			for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + own];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				ch[4 * q + 0] = f_op(v[q].x, v[q + 4].x);
+				ch[4 * q + 1] = f_op(v[q].y, v[q + 4].y);
+				ch[4 * q + 2] = f_op(v[q].z, v[q + 4].z);
+				ch[4 * q + 3] = f_op(v[q].w, v[q + 4].w);
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < H; ++k) ch[k] = f_op(a[k], a[k + H]);
 		}
 		blk_node<LVL - 1, BASE>(c, ch);
 		const int lmap = c.ret;
 		const int srcl = c.gbase + lmap;
+		if constexpr (LVL == 5) {
+			float4 v[8];
 #pragma unroll
-		for (int k = 0; k < H; ++k) {
-			float pa, pb;
-			if constexpr (LVL == 5) { pa = c.A5[k * 32 + srcl]; pb = c.A5[(k + H) * 32 + srcl]; }
-			else { pa = __shfl_sync(FULL, a[k], srcl); pb = __shfl_sync(FULL, a[k + H], srcl); }
-			ch[k] = g_op(pa, pb, (c.W >> (BASE + k)) & 1u);
+			for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + srcl];
+			const uint32_t wb = c.W >> BASE;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				ch[4 * q + 0] = g_op(v[q].x, v[q + 4].x, (wb >> (4 * q + 0)) & 1u);
+				ch[4 * q + 1] = g_op(v[q].y, v[q + 4].y, (wb >> (4 * q + 1)) & 1u);
+				ch[4 * q + 2] = g_op(v[q].z, v[q + 4].z, (wb >> (4 * q + 2)) & 1u);
+				ch[4 * q + 3] = g_op(v[q].w, v[q + 4].w, (wb >> (4 * q + 3)) & 1u);
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < H; ++k) {
+				const float pa = __shfl_sync(FULL, a[k], srcl), pb = __shfl_sync(FULL, a[k + H], srcl);
+				ch[k] = g_op(pa, pb, (c.W >> (BASE + k)) & 1u);
+			}
 		}
 		blk_node<LVL - 1, BASE + H>(c, ch);
 		constexpr uint32_t MASKL = ((1u << H) - 1u) << BASE;
@@ -125,17 +153,36 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 	}
 }
 
-__global__ void __launch_bounds__(kSclThreads) k_polar_scl(SclParams p)
+__device__ __forceinline__ float4 f_op4(float4 a, float4 b) { return make_float4(f_op(a.x, b.x), f_op(a.y, b.y), f_op(a.z, b.z), f_op(a.w, b.w)); }
+__device__ __forceinline__ float4 g_op4(float4 a, float4 b, uint32_t bits)
+{
+	return make_float4(g_op(a.x, b.x, bits & 1u), g_op(a.y, b.y, (bits >> 1) & 1u), g_op(a.z, b.z, (bits >> 2) & 1u), g_op(a.w, b.w, (bits >> 3) & 1u));
+}
+__device__ __forceinline__ float r0_acc(float m, float4 v)
+{
+	if (v.x < 0.f) m = __fsub_rn(m, v.x);
+	if (v.y < 0.f) m = __fsub_rn(m, v.y);
+	if (v.z < 0.f) m = __fsub_rn(m, v.z);
+	if (v.w < 0.f) m = __fsub_rn(m, v.w);
+	return m;
+}
+
+// Upper-level ops work on quads (float4 = 4 consecutive tree positions of one lane); loads of a batch of U quads are
+// issued before anything is stored so that U*2 128-bit loads are in flight per thread (the stores may alias the loads
+// as far as the compiler knows, so the batching has to be explicit).
+constexpr int kU = 4;
+
+__global__ void __launch_bounds__(kSclThreads, 2) k_polar_scl(SclParams p)
 {
 	const int lane32 = threadIdx.x & 31;
 	const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int n_warps = (gridDim.x * blockDim.x) >> 5;
-	float *A = p.A + (size_t)warp_global * kSclWarpFloats;
+	float4 *A = reinterpret_cast<float4 *>(p.A + (size_t)warp_global * kSclWarpFloats);
 	uint32_t *B = p.B + (size_t)warp_global * kSclWarpWords;
 	SclCtx c;
 	c.t = lane32 & 7;
 	c.gbase = lane32 & ~7;
-	c.A5 = A + scl_off(5);
+	c.A5 = A + scl_off4(5);
 
 	const int n_cw = p.n_cw_ptr ? *p.n_cw_ptr : p.n_cw;
 	for (int g4 = warp_global; g4 * 4 < n_cw; g4 += n_warps) {
@@ -143,6 +190,7 @@ __global__ void __launch_bounds__(kSclThreads) k_polar_scl(SclParams p)
 		const bool active = slot < n_cw;
 		const int frame = p.cw_list ? p.cw_list[active ? slot : n_cw - 1] : (active ? slot : n_cw - 1);
 		const float *C = p.llr + (size_t)frame * kCodeLen;
+		const float4 *C4 = reinterpret_cast<const float4 *>(C);
 		c.metric = c.t == 0 ? 0.f : 1000.f;
 		c.ret = c.t;
 		uint64_t lmstack = 0;
@@ -151,36 +199,41 @@ __global__ void __launch_bounds__(kSclThreads) k_polar_scl(SclParams p)
 			const uint32_t opw = __ldg(&p.ops[pc]);
 			const uint32_t op = opw & 7u, l = (opw >> 3) & 31u, iw = opw >> 8; // iw = first word of the node
 			if (op == OP_END) break;
-			const int h = 1 << (l - 1);
-			const float *P = A + scl_off(l);   // parent level (valid for l <= 15)
-			float *D = A + scl_off(l - 1);
+			const int hq = 1 << (l - 3);               // quads per half node
+			const float4 *P = A + scl_off4(l);          // parent level (valid for l <= 15)
+			float4 *D = A + scl_off4(l - 1);
 			if (op == OP_F) {
-				if (l == 16) {
-#pragma unroll 4
-					for (int i = 0; i < h; ++i) D[i * 32 + lane32] = f_op(C[i], C[i + h]);
-				} else {
-#pragma unroll 4
-					for (int i = 0; i < h; ++i) D[i * 32 + lane32] = f_op(P[i * 32 + lane32], P[(i + h) * 32 + lane32]);
+				for (int q0 = 0; q0 < hq; q0 += kU) {
+					float4 pa[kU], pb[kU];
+					if (l == 16) {
+#pragma unroll
+						for (int u = 0; u < kU; ++u) { pa[u] = __ldg(&C4[q0 + u]); pb[u] = __ldg(&C4[q0 + u + hq]); }
+					} else {
+#pragma unroll
+						for (int u = 0; u < kU; ++u) { pa[u] = P[(q0 + u) * 32 + lane32]; pb[u] = P[(q0 + u + hq) * 32 + lane32]; }
+					}
+#pragma unroll
+					for (int u = 0; u < kU; ++u) D[(q0 + u) * 32 + lane32] = f_op4(pa[u], pb[u]);
 				}
 				__syncwarp();
 			} else if (op == OP_G) {
 				lmstack = (lmstack & ~(7ull << (3 * l))) | ((uint64_t)c.ret << (3 * l));
 				const int src = c.gbase + c.ret;
 				const uint32_t *Bw = B + (size_t)iw * 32 + lane32;
-				for (int i0 = 0; i0 < h; i0 += 32) {
-					const uint32_t bw = Bw[(i0 >> 5) * 32];
-					if (l == 16) {
-#pragma unroll 8
-						for (int k = 0; k < 32; ++k) {
-							const int i = i0 + k;
-							D[i * 32 + lane32] = g_op(C[i], C[i + h], (bw >> k) & 1u);
+				for (int q0 = 0; q0 < hq; q0 += 8) { // 8 quads = one 32-bit word of partial sums
+					const uint32_t bw = Bw[(q0 >> 3) * 32];
+#pragma unroll
+					for (int h2 = 0; h2 < 8; h2 += kU) {
+						float4 pa[kU], pb[kU];
+						if (l == 16) {
+#pragma unroll
+							for (int u = 0; u < kU; ++u) { pa[u] = __ldg(&C4[q0 + h2 + u]); pb[u] = __ldg(&C4[q0 + h2 + u + hq]); }
+						} else {
+#pragma unroll
+							for (int u = 0; u < kU; ++u) { pa[u] = P[(q0 + h2 + u) * 32 + src]; pb[u] = P[(q0 + h2 + u + hq) * 32 + src]; }
 						}
-					} else {
-#pragma unroll 8
-						for (int k = 0; k < 32; ++k) {
-							const int i = i0 + k;
-							D[i * 32 + lane32] = g_op(P[i * 32 + src], P[(i + h) * 32 + src], (bw >> k) & 1u);
-						}
+#pragma unroll
+						for (int u = 0; u < kU; ++u) D[(q0 + h2 + u) * 32 + lane32] = g_op4(pa[u], pb[u], (bw >> (4 * (h2 + u))) & 15u);
 					}
 				}
 				__syncwarp();
@@ -191,20 +244,26 @@ __global__ void __launch_bounds__(kSclThreads) k_polar_scl(SclParams p)
 				B[(size_t)iw * 32 + lane32] = c.W;
 				__syncwarp();
 			} else if (op == OP_R0) {
-				const int n = 2 * h;
+				const int nq = 2 * hq;
 				float m = c.metric;
-				if (l == 16) {
-					for (int i = 0; i < n; ++i) { const float v = C[i]; if (v < 0.f) m = __fsub_rn(m, v); }
-				} else {
-#pragma unroll 4
-					for (int i = 0; i < n; ++i) { const float v = P[i * 32 + lane32]; if (v < 0.f) m = __fsub_rn(m, v); }
+				for (int q0 = 0; q0 < nq; q0 += 2 * kU) {
+					float4 v[2 * kU];
+					if (l == 16) {
+#pragma unroll
+						for (int u = 0; u < 2 * kU; ++u) v[u] = __ldg(&C4[q0 + u]);
+					} else {
+#pragma unroll
+						for (int u = 0; u < 2 * kU; ++u) v[u] = P[(q0 + u) * 32 + lane32];
+					}
+#pragma unroll
+					for (int u = 0; u < 2 * kU; ++u) m = r0_acc(m, v[u]);
 				}
 				c.metric = m;
-				for (int w = 0; w < n / 32; ++w) B[(size_t)(iw + w) * 32 + lane32] = 0u;
+				for (int w = 0; w < nq / 8; ++w) B[(size_t)(iw + w) * 32 + lane32] = 0u;
 				c.ret = c.t;
 				__syncwarp();
 			} else { // OP_C
-				const int hw = h >> 5;
+				const int hw = hq >> 3;
 				const int src = c.gbase + c.ret;
 				for (int w0 = 0; w0 < hw; w0 += 8) {
 					uint32_t x[8];

@@ -8,6 +8,8 @@ constexpr int kSclThreads = 256;                       // 8 warps = 32 codewords
 constexpr size_t kSclWarpFloats = (size_t)(65536 - 32) * 32; // alpha levels 5..15, [element][warp lane]
 constexpr size_t kSclWarpWords = (size_t)2048 * 32;          // beta bits, [word][warp lane]
 __host__ __device__ constexpr size_t scl_off(int l) { return (size_t)((1 << l) - 32) * 32; }
+// same offset in float4 units: level l holds 2^l/4 quads per lane, laid out [quad][warp lane]
+__host__ __device__ constexpr size_t scl_off4(int l) { return (size_t)((1 << l) - 32) * 8; }
 
 struct SclParams {
 	const float *llr;        // [frames][65536] channel LLRs after lengthen() (decode.cc:529)

@@ -83,7 +83,8 @@ def _compare_frames(rx, oracle, pcm, channels, sent, strict_payload=True):
         if tp.detections:
             assert (s["sc_pos"], s["shift"], s["pos_err"]) == (tp.sc_pos, tp.shift, tp.pos_err)
             assert abs(s["cfo_rad"] - tp.cfo_rad) < 1e-5
-            assert (rx.taps(M.TAP_SOFT, i, 1)[0][:255] == oracle.taps_np(tp, "soft")[:255]).all()
+            dsoft = np.abs(rx.taps(M.TAP_SOFT, i, 1)[0][:255].astype(int) - oracle.taps_np(tp, "soft")[:255].astype(int))
+            assert dsoft.max() <= 1 and (dsoft != 0).sum() <= 4   # rint() of a float that differs in the last ulps
             assert ((int(s["md_hi"]) << 32) | int(s["md_lo"])) == tp.md and s["mode"] == tp.mode
         if ost in (0, 6):
             assert np.abs(rx.taps(M.TAP_CONS_RAW, i, 1)[0] - oracle.taps_np(tp, "cons_raw")).max() < TOL_CONS
