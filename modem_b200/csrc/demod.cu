@@ -30,12 +30,14 @@ struct DmShared {
 	cfx prev[kCols];
 	cfx cons[kCols];
 	float y[kCols];
+	float rcp[kCols];   // 1/d for d = 1..431 (index 0 unused)
 	float z[kCols];
 	float cand[kCandCap];
 	int hist[kBins];
 	float red[kDmWarps][2];
 	double redd[kDmWarps][2];
-	int sel_lo, sel_shift, sel_k, sel_done;
+	int sel_lo, sel_k, sel_cnt, ncand2;
+	int small[32];
 	int below, ncand, sel_bin, state;
 	int cmin, cmax; // ordered-int images of the smallest / largest collected quotient
 	float lo, hi, blo, bhi, result;
@@ -53,16 +55,44 @@ __device__ __forceinline__ void psk8_hard_map(cfx c, cfx &m)
 	m = make_float2(c.x < 0.f ? -re : re, c.y < 0.f ? -im : im);
 }
 
-// slope of the pair {i, (i + dx) mod 432} ordered by index, as the reference forms it: (y_hi - y_lo) / (x_hi - x_lo)
-__device__ __forceinline__ void pair_terms(const float *y, float yi, int i, int dx, float &diff, int &dist)
+// pair {i, (i + dx) mod 432} ordered by index as the reference forms it: diff = y_hi - y_lo, dist = x_hi - x_lo;
+// rd/rw = 1/dx and 1/(432-dx) (uniform per iteration)
+__device__ __forceinline__ void pair_terms(const float *y, float yi, int i, int dx, float rd, float rw, float &diff, int &dist, float &rcp)
 {
 	int j = i + dx;
-	if (j >= kCols) { j -= kCols; diff = yi - y[j]; dist = kCols - dx; }
-	else { diff = y[j] - yi; dist = dx; }
+	if (j >= kCols) { j -= kCols; diff = yi - y[j]; dist = kCols - dx; rcp = rw; }
+	else { diff = y[j] - yi; dist = dx; rcp = rd; }
+}
+
+// warp 0: locate rank k inside a 256-bin histogram without a serial scan: 8 bins per lane, shuffle prefix.
+// Writes s.sel_bin (bin holding rank k, or -1 if k >= total), s.sel_k (rank inside that bin), s.sel_cnt (its count).
+__device__ __forceinline__ void find_bin(DmShared &s, int k, int tid)
+{
+	if (tid >= 32) return;
+	const int lane = tid;
+	int h[8], sum = 0;
+#pragma unroll
+	for (int i = 0; i < 8; ++i) { h[i] = s.hist[lane * 8 + i]; sum += h[i]; }
+	int incl = sum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+	const int excl = incl - sum;
+	const bool mine = k >= excl && k < incl;
+	const unsigned bal = __ballot_sync(FULL, mine);
+	if (bal == 0u) { if (lane == 0) { s.sel_bin = -1; s.sel_k = k - __shfl_sync(FULL, incl, 31); s.sel_cnt = 0; } return; }
+	if (mine) {
+		int kk = k - excl, b = 0;
+#pragma unroll
+		for (int i = 0; i < 8; ++i) { if (b == i && kk >= h[i]) { kk -= h[i]; b = i + 1; } }
+		s.sel_bin = lane * 8 + b;
+		s.sel_k = kk;
+		s.sel_cnt = h[b < 8 ? b : 7];
+	}
 }
 
 // k-th smallest (0-based) of v[0..n) in shared memory, exact: radix select on the order-preserving integer image of
-// the floats, 8 bits per level inside the [min,max] range, 256-bin shared histogram.  All threads of the CTA call.
+// the floats, 8 bits per level inside the [min,max] range, 256-bin shared histogram; as soon as the selected bin
+// holds <= 32 values they are gathered and ranked by one warp.  All threads of the CTA call.
 __device__ float select_kth(DmShared &s, const float *v, int n, int k, int tid)
 {
 	const int lane = tid & 31;
@@ -74,37 +104,42 @@ __device__ float select_kth(DmShared &s, const float *v, int n, int k, int tid)
 	__syncthreads();
 	if (lane == 0) { atomicMin(&s.cmin, mn); atomicMax(&s.cmax, mx); }
 	__syncthreads();
-	if (tid == 0) {
-		const unsigned range = (unsigned)s.cmax - (unsigned)s.cmin;
-		int bits = 32 - __clz(range | 1u);
-		s.sel_lo = s.cmin;
-		s.sel_shift = max(0, bits - 8);
-		s.sel_k = k;
-		s.sel_done = 0;
-	}
-	__syncthreads();
+	int lo = s.cmin, kk = k;
+	int sh = max(0, 32 - __clz(((unsigned)s.cmax - (unsigned)s.cmin) | 1u) - 8);
 	for (int level = 0; level < 5; ++level) {
 		for (int b = tid; b < kBins; b += kDmThreads) s.hist[b] = 0;
+		if (tid == 0) s.ncand2 = 0;
 		__syncthreads();
-		const int lo = s.sel_lo, sh = s.sel_shift;
 		for (int i = tid; i < n; i += kDmThreads) {
-			const unsigned d = (unsigned)f2ord(v[i]) - (unsigned)lo; // wraps to a huge value when below lo
-			const unsigned b = d >> sh;
+			const unsigned b = ((unsigned)f2ord(v[i]) - (unsigned)lo) >> sh; // values below lo wrap to huge bins
 			if (b < (unsigned)kBins) atomicAdd(&s.hist[b], 1);
 		}
 		__syncthreads();
-		if (tid == 0) {
-			int kk = s.sel_k, b = 0;
-			for (; b < kBins - 1; ++b) { if (kk < s.hist[b]) break; kk -= s.hist[b]; }
-			s.sel_lo = lo + (int)((unsigned)b << sh);
-			s.sel_k = kk;
-			if (sh == 0) s.sel_done = 1;
-			s.sel_shift = max(0, sh - 8);
-		}
+		find_bin(s, kk, tid);
 		__syncthreads();
-		if (s.sel_done) break;
+		const int b = s.sel_bin, cnt = s.sel_cnt;
+		kk = s.sel_k;
+		lo += (int)((unsigned)b << sh);
+		if (sh == 0) break;               // bins are single values: lo is the answer
+		if (cnt <= 32) {                  // finish: gather the bin's members, rank them in one warp
+			for (int i = tid; i < n; i += kDmThreads) {
+				const int o = f2ord(v[i]);
+				if ((((unsigned)o - (unsigned)lo) >> sh) == 0u) s.small[atomicAdd(&s.ncand2, 1) & 31] = o;
+			}
+			__syncthreads();
+			if (tid < 32) {
+				const int m = s.ncand2;
+				const int mine = lane < m ? s.small[lane] : 0x7fffffff;
+				int r = 0;
+				for (int j = 0; j < m; ++j) { const int o = __shfl_sync(FULL, mine, j); r += (o < mine) || (o == mine && j < lane); }
+				if (lane < m && r == kk) s.sel_lo = mine;
+			}
+			__syncthreads();
+			return ord2f(s.sel_lo);
+		}
+		sh = max(0, sh - 8);
 	}
-	return ord2f(s.sel_lo);
+	return ord2f(lo);
 }
 
 // pilot bracket: ordinary least squares slope c of y on x = i - 216 and the residual standard deviation.  The exact
@@ -151,18 +186,21 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 		ols_pilot(s, tid, c, sigma);
 		const float dlt = fmaxf(3.5e-4f * sigma, fmaxf(fabsf(c) * 4e-6f, 1e-10f));
 		const float blo = c - dlt, bhi = c + dlt;
+		// approximate slopes (diff * 1/d) are within 2 ulp of the exact quotient: anything within mg of the bracket is
+		// re-evaluated exactly, the rest is classified by the approximation
+		const float mg = 2e-6f * fmaxf(fabsf(blo), fabsf(bhi)) + 1e-30f;
+		const float blo_m = blo - mg, bhi_m = bhi + mg;
 		if (tid == 0) { s.below = 0; s.ncand = 0; }
 		__syncthreads();
 		int cb = 0;
 		if (act) {
 			for (int dx = 1; dx <= 216; ++dx) {
 				if (dx == 216 && tid >= 216) break;
-				float diff; int dist;
-				pair_terms(s.y, yi, tid, dx, diff, dist);
-				const float sl = diff * __frcp_rn((float)dist);
-				const float mg = 1e-6f * fabsf(sl) + 1e-30f;
-				if (sl < blo - mg) ++cb;
-				else if (sl < bhi + mg) {
+				float diff, rc; int dist;
+				pair_terms(s.y, yi, tid, dx, s.rcp[dx], s.rcp[kCols - dx], diff, dist, rc);
+				const float sl = diff * rc;
+				if (sl < blo_m) ++cb;
+				else if (sl < bhi_m) {
 					const float q = __fdiv_rn(diff, (float)dist);
 					if (q < blo) ++cb;
 					else if (q < bhi) {
@@ -212,9 +250,9 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 		if (act) {
 			for (int dx = 1; dx <= 216; ++dx) {
 				if (dx == 216 && tid >= 216) break;
-				float diff; int dist;
-				pair_terms(s.y, yi, tid, dx, diff, dist);
-				const float sl = diff * __frcp_rn((float)dist);
+				float diff, rc; int dist;
+				pair_terms(s.y, yi, tid, dx, s.rcp[dx], s.rcp[kCols - dx], diff, dist, rc);
+				const float sl = diff * rc;
 				if (sl < lo) ++below;
 				else if (sl < hi) {
 					int b = (int)((sl - lo) * inv_w);
@@ -227,14 +265,10 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 		for (int d = 16; d; d >>= 1) below += __shfl_xor_sync(FULL, below, d);
 		if (lane == 0 && below) atomicAdd(&s.below, below);
 		__syncthreads();
+		find_bin(s, kRankSlope - s.below, tid);
+		__syncthreads();
 		if (tid == 0) {
-			int cum = s.below, bsel = -1;
-			if (kRankSlope >= cum) {
-				for (int b = 0; b < kBins; ++b) {
-					if (kRankSlope < cum + s.hist[b]) { bsel = b; break; }
-					cum += s.hist[b];
-				}
-			}
+			const int bsel = s.sel_bin;
 			const float w = (hi - lo) / (float)kBins;
 			if (kRankSlope < s.below) { // rank lies below the bracket: slide down and widen
 				s.hi = lo; s.lo = lo - 16.f * (hi - lo); s.state = 0;
@@ -242,7 +276,7 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 				s.lo = hi; s.hi = hi + 16.f * (hi - lo); s.state = 0;
 			} else {
 				const float blo = lo + (float)bsel * w, bhi = bsel == kBins - 1 ? hi : lo + (float)(bsel + 1) * w;
-				if (s.hist[bsel] > kBinCap && bhi > blo && (bhi - blo) > 1e-30f) { s.lo = blo; s.hi = bhi; s.state = 0; }
+				if (s.sel_cnt > kBinCap && bhi > blo && (bhi - blo) > 1e-30f) { s.lo = blo; s.hi = bhi; s.state = 0; }
 				else { s.blo = blo; s.bhi = bhi; s.state = 1; }
 			}
 		}
@@ -253,16 +287,17 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 			if (tid == 0) { s.below = 0; s.ncand = 0; s.cmin = 0x7fffffff; s.cmax = (int)0x80000000; }
 			__syncthreads();
 			const float blo = s.blo, bhi = s.bhi;
+			const float mg = 2e-6f * fmaxf(fabsf(blo), fabsf(bhi)) + 1e-30f;
+			const float blo_m = blo - mg, bhi_m = bhi + mg;
 			int cb = 0;
 			if (act) {
 				for (int dx = 1; dx <= 216; ++dx) {
 					if (dx == 216 && tid >= 216) break;
-					float diff; int dist;
-					pair_terms(s.y, yi, tid, dx, diff, dist);
-					const float sl = diff * __frcp_rn((float)dist);
-					const float mg = 1e-6f * fabsf(sl) + 1e-30f;
-					if (sl < blo - mg) ++cb;
-					else if (sl < bhi + mg) {
+					float diff, rc; int dist;
+					pair_terms(s.y, yi, tid, dx, s.rcp[dx], s.rcp[kCols - dx], diff, dist, rc);
+					const float sl = diff * rc;
+					if (sl < blo_m) ++cb;
+					else if (sl < bhi_m) {
 						const float q = __fdiv_rn(diff, (float)dist);
 						if (q < blo) ++cb;
 						else if (q < bhi) {
@@ -311,6 +346,7 @@ __global__ void __launch_bounds__(kDmThreads) k_demod(const cfx *iq, int64_t iq_
 	float *code = llr + (size_t)f * kCodeLen;
 	const int p0 = st.sc_pos + 2 * kPitch; // pilot body (decode.cc:456-459)
 	const double turns = -(double)st.cfo_rad / 6.283185307179586476925286766559;
+	if (tid < kCols) s.rcp[tid] = tid ? __frcp_rn((float)tid) : 0.f;
 	float sp = 0.f, np = 0.f; // cumulative, never reset (decode.cc:507)
 	for (int sym = 0; sym <= kConsRows; ++sym) {
 		const int w0 = p0 + kPitch * sym;

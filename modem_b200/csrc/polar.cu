@@ -99,10 +99,24 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 		}
 	}
 	if constexpr (LVL == 0) {
-		const ForkResult r = leaf_fork(c.metric, a[0], c.t, c.gbase);
-		c.metric = r.metric;
-		c.ret = r.src_bit & 7;
-		c.W |= (uint32_t)(r.src_bit >> 3) << BASE;
+		// Fast path (exact): if every "follow the sign" fork beats every "flip" fork and the lanes are already in
+		// (metric, lane) order, the 8 survivors are the 8 keeps in place — no ranking, no permutation.  Metrics are
+		// non-negative, so their bit patterns order like unsigned integers (REDUX instead of shuffle trees).
+		const float a0 = a[0];
+		const unsigned gmask = 0xffu << c.gbase;
+		const uint32_t maxk = __reduce_max_sync(gmask, __float_as_uint(c.metric));
+		const uint32_t minf = __reduce_min_sync(gmask, __float_as_uint(__fadd_rn(c.metric, fabsf(a0))));
+		const float prev = __shfl_up_sync(FULL, c.metric, 1);
+		const bool easy = maxk < minf && (c.t == 0 || prev <= c.metric);
+		if (__all_sync(FULL, easy)) {
+			c.ret = c.t;
+			c.W |= (a0 < 0.f ? 1u : 0u) << BASE;
+		} else {
+			const ForkResult r = leaf_fork(c.metric, a0, c.t, c.gbase);
+			c.metric = r.metric;
+			c.ret = r.src_bit & 7;
+			c.W |= (uint32_t)(r.src_bit >> 3) << BASE;
+		}
 	} else {
 		constexpr int H = N / 2;
 		float ch[H];
@@ -137,6 +151,9 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 				ch[4 * q + 2] = g_op(v[q].z, v[q + 4].z, (wb >> (4 * q + 2)) & 1u);
 				ch[4 * q + 3] = g_op(v[q].w, v[q + 4].w, (wb >> (4 * q + 3)) & 1u);
 			}
+		} else if (__all_sync(FULL, lmap == c.t)) { // no lane moved inside the left child: parents are my own registers
+#pragma unroll
+			for (int k = 0; k < H; ++k) ch[k] = g_op(a[k], a[k + H], (c.W >> (BASE + k)) & 1u);
 		} else {
 #pragma unroll
 			for (int k = 0; k < H; ++k) {
@@ -146,10 +163,15 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 		}
 		blk_node<LVL - 1, BASE + H>(c, ch);
 		constexpr uint32_t MASKL = ((1u << H) - 1u) << BASE;
-		const int srcr = c.gbase + c.ret;
-		const uint32_t Wl = __shfl_sync(FULL, c.W, srcr);
-		c.W = (c.W & ~MASKL) | ((Wl ^ (c.W >> H)) & MASKL);
-		c.ret = __shfl_sync(FULL, lmap, srcr);
+		if (__all_sync(FULL, c.ret == c.t)) {
+			c.W = (c.W & ~MASKL) | ((c.W ^ (c.W >> H)) & MASKL);
+			c.ret = lmap;
+		} else {
+			const int srcr = c.gbase + c.ret;
+			const uint32_t Wl = __shfl_sync(FULL, c.W, srcr);
+			c.W = (c.W & ~MASKL) | ((Wl ^ (c.W >> H)) & MASKL);
+			c.ret = __shfl_sync(FULL, lmap, srcr);
+		}
 	}
 }
 

@@ -33,7 +33,7 @@ struct Emu {
 	float metric[L];
 	int ret[L];
 	int lm[17][L];
-	long long forks = 0;
+	long long forks = 0, fast_hits = 0, keep_all = 0;
 
 	void fork_leaf(const float *llr, uint32_t *bit_out)
 	{
@@ -43,6 +43,11 @@ struct Emu {
 			float a = llr[t], pen = std::fabs(a);
 			m0[t] = metric[t] + (a < 0.f ? pen : 0.f);
 			m1[t] = metric[t] + (a < 0.f ? 0.f : pen);
+		}
+		{ // statistics: would the 'all keeps survive and lanes already sorted' shortcut apply?
+			float maxK = metric[0], minF = 1e30f; bool sorted = true;
+			for (int t = 0; t < L; ++t) { maxK = std::max(maxK, metric[t]); minF = std::min(minF, metric[t] + std::fabs(llr[t])); if (t && metric[t] < metric[t-1]) sorted = false; }
+			if (maxK < minF) { ++keep_all; if (sorted) ++fast_hits; }
 		}
 		int src[L], bit[L];
 		float nm[L];
@@ -137,7 +142,7 @@ struct Emu {
 		metric[0] = 0.f;
 		for (int t = 1; t < L; ++t) metric[t] = 1000.f;
 		for (int t = 0; t < L; ++t) ret[t] = t;
-		forks = 0;
+		forks = 0; fast_hits = 0; keep_all = 0;
 		for (size_t pc = 0;; ++pc) {
 			uint32_t w = ops[pc];
 			uint32_t op = scl_op(w), l = scl_level(w), index = scl_index(w);
@@ -213,7 +218,7 @@ void emu_polar_decode(const float *llr, uint8_t *lanes_out, float *metrics_out, 
 		metrics_out[k] = e.metric[perm[k]];
 		for (int i = 0; i < kCodeLen; ++i) lanes_out[(size_t)k * kCodeLen + i] = (e.B[(size_t)(i / 32) * L + perm[k]] >> (i % 32)) & 1;
 	}
-	if (forks) *forks = e.forks;
+	if (forks) { forks[0] = e.forks; forks[1] = e.fast_hits; forks[2] = e.keep_all; }
 }
 void host_frozen(uint32_t *out) { auto f = make_frozen(kCodeOrder, kConsBits, kCrcBits); std::memcpy(out, f.data(), 2048 * 4); }
 void host_frozen_alt(uint32_t *out) { auto f = make_frozen(kCodeOrder, 64512, kCrcBits); std::memcpy(out, f.data(), 2048 * 4); }
