@@ -22,7 +22,7 @@ constexpr int kCols = kConsCols;           // 432
 constexpr int kPairs = kCols * (kCols - 1) / 2; // 93096
 constexpr int kRankSlope = kPairs / 2;      // element count/2 after nth_element
 constexpr int kRankYint = kCols / 2;
-constexpr int kBins = 256, kCandCap = 4096, kBinCap = 2048;
+constexpr int kBins = 256, kCandCap = 4096, kBinCap = 2048, kMineCap = 24;
 
 struct DmShared {
 	cfx buf0[kSymLen];
@@ -38,6 +38,7 @@ struct DmShared {
 	double redd[kDmWarps][2];
 	int sel_lo, sel_k, sel_cnt, ncand2;
 	int small[32];
+	unsigned short mine[kMineCap][kCols]; // per-thread list of pairs whose approximate slope falls in the bracket
 	int below, ncand, sel_bin, state;
 	int cmin, cmax; // ordered-int images of the smallest / largest collected quotient
 	float lo, hi, blo, bhi, result;
@@ -190,33 +191,51 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 		// re-evaluated exactly, the rest is classified by the approximation
 		const float mg = 2e-6f * fmaxf(fabsf(blo), fabsf(bhi)) + 1e-30f;
 		const float blo_m = blo - mg, bhi_m = bhi + mg;
-		if (tid == 0) { s.below = 0; s.ncand = 0; }
+		if (tid == 0) { s.below = 0; s.ncand = 0; s.state = 0; }
 		__syncthreads();
-		int cb = 0;
+		int cb = 0, cnt = 0;
 		if (act) {
-			for (int dx = 1; dx <= 216; ++dx) {
-				if (dx == 216 && tid >= 216) break;
-				float diff, rc; int dist;
-				pair_terms(s.y, yi, tid, dx, s.rcp[dx], s.rcp[kCols - dx], diff, dist, rc);
-				const float sl = diff * rc;
+			// phase 1: classify by the approximate slope only; remember the few pairs near/inside the bracket.
+			// Thread i owns the pairs (i, i+d), d <= min(216, 431-i), and the far pairs (j, i), i-j >= 217: every unordered
+			// pair exactly once, 215 or 216 per thread, and no wrap-around logic inside the loops.
+			const int nA = min(216, kCols - 1 - tid);
+			const float *yp = s.y + tid;
+#pragma unroll 4
+			for (int d = 1; d <= nA; ++d) {
+				const float sl = (yp[d] - yi) * s.rcp[d];
 				if (sl < blo_m) ++cb;
-				else if (sl < bhi_m) {
-					const float q = __fdiv_rn(diff, (float)dist);
-					if (q < blo) ++cb;
-					else if (q < bhi) {
-						const int p = atomicAdd(&s.ncand, 1);
-						if (p < kCandCap) s.cand[p] = q;
-					}
+				else if (sl < bhi_m) { if (cnt < kMineCap) s.mine[cnt][tid] = (unsigned short)d; ++cnt; }
+			}
+			const float *rp = s.rcp + tid;
+#pragma unroll 4
+			for (int j = 0; j <= tid - 217; ++j) {
+				const float sl = (yi - s.y[j]) * rp[-j];
+				if (sl < blo_m) ++cb;
+				else if (sl < bhi_m) { if (cnt < kMineCap) s.mine[cnt][tid] = (unsigned short)(0x8000 | j); ++cnt; }
+			}
+			// phase 2: exact quotients of the remembered pairs (dense: every lane has work)
+			const int m = min(cnt, kMineCap);
+			for (int k = 0; k < m; ++k) {
+				const int code = s.mine[k][tid];
+				float diff; int dist;
+				if (code & 0x8000) { const int j = code & 0x7fff; diff = yi - s.y[j]; dist = tid - j; }
+				else { diff = yp[code] - yi; dist = code; }
+				const float q = __fdiv_rn(diff, (float)dist);
+				if (q < blo) ++cb;
+				else if (q < bhi) {
+					const int p = atomicAdd(&s.ncand, 1);
+					if (p < kCandCap) s.cand[p] = q;
 				}
 			}
+			if (cnt > kMineCap) s.state = 1; // list overflow: take the general path
 		}
 #pragma unroll
 		for (int d = 16; d; d >>= 1) cb += __shfl_xor_sync(FULL, cb, d);
 		if (lane == 0 && cb) atomicAdd(&s.below, cb);
 		__syncthreads();
-		const int kk = kRankSlope - s.below, nc = s.ncand;
+		const int kk = kRankSlope - s.below, nc = s.ncand, ovf = s.state;
 		__syncthreads();
-		if (kk >= 0 && kk < nc && nc <= kCandCap) return select_kth(s, s.cand, nc, kk, tid);
+		if (!ovf && kk >= 0 && kk < nc && nc <= kCandCap) return select_kth(s, s.cand, nc, kk, tid);
 	}
 	// ---- general path (pilot missed: outliers, erased rows, very low SNR)
 	// seed bracket: quartiles of the 216 slopes with baseline 216

@@ -38,21 +38,37 @@ static bool all_frozen(const std::vector<uint32_t> &fr, int index, int n)
 		if (fr[w] != 0xffffffffu) return false;
 	return true;
 }
-static void gen(std::vector<uint32_t> &ops, const std::vector<uint32_t> &fr, int level, int index)
+// number of F steps that can be chained below a node of `level` at `index` whose alpha has just been produced:
+// the node must be an internal node above the 32-leaf words (level >= 6) and must not be a rate-0 node.
+static int chain_len(const std::vector<uint32_t> &fr, int level, int index, int max_more)
+{
+	int n = 0;
+	while (n < max_more && level >= 6 && !all_frozen(fr, index, 1 << level)) { ++n; --level; }
+	return n;
+}
+// skip_f: this node's own F step was already performed by a fused op of an ancestor (skip_f - 1 more follow)
+static void gen(std::vector<uint32_t> &ops, const std::vector<uint32_t> &fr, int level, int index, int skip_f, int max_depth)
 {
 	const int n = 1 << level;
 	if (all_frozen(fr, index, n)) { ops.push_back(scl_pack(OP_R0, level, index)); return; }
 	if (level == 5) { ops.push_back(scl_pack(OP_WORD, level, index)); return; }
-	ops.push_back(scl_pack(OP_F, level, index));
-	gen(ops, fr, level - 1, index);
-	ops.push_back(scl_pack(OP_G, level, index));
-	gen(ops, fr, level - 1, index + n / 2);
+	int pass_down = 0;
+	if (skip_f > 0) pass_down = skip_f - 1;
+	else {
+		const int more = chain_len(fr, level - 1, index, max_depth - 1);
+		ops.push_back(scl_pack(OP_F, level, index, 1 + more));
+		pass_down = more;
+	}
+	gen(ops, fr, level - 1, index, pass_down, max_depth);
+	const int more = chain_len(fr, level - 1, index + n / 2, max_depth - 1);
+	ops.push_back(scl_pack(OP_G, level, index, 1 + more));
+	gen(ops, fr, level - 1, index + n / 2, more, max_depth);
 	ops.push_back(scl_pack(OP_C, level, index));
 }
-std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order)
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth)
 {
 	std::vector<uint32_t> ops;
-	gen(ops, frozen, order, 0);
+	gen(ops, frozen, order, 0, 0, max_depth);
 	ops.push_back(scl_pack(OP_END, 0, 0));
 	return ops;
 }

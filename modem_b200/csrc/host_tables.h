@@ -35,11 +35,14 @@ std::vector<uint32_t> make_frozen(int order, int n_tx, int k_info);
 //   R0(l, idx)   maximal all-frozen node: metric += sum of negative alpha_l, beta = 0
 //   C(l, idx)    beta[idx..idx+h) = perm(beta[idx..idx+h)) ^ beta[idx+h..idx+2h), compose lane maps
 enum SclOp : uint32_t { OP_F = 0, OP_G = 1, OP_WORD = 2, OP_R0 = 3, OP_C = 4, OP_END = 7 };
-static inline uint32_t scl_pack(uint32_t op, uint32_t level, uint32_t index) { return op | (level << 3) | ((index / 32) << 8); }
+// F and G carry a fusion depth d = 1..3 in bits 30..31 (stored as d-1): the op also performs the d-1 F steps that always
+// follow it on the way down the left spine (F(l-1), F(l-2)), so those levels are produced in registers and written once.
+static inline uint32_t scl_pack(uint32_t op, uint32_t level, uint32_t index, uint32_t depth = 1) { return op | (level << 3) | ((index / 32) << 8) | ((depth - 1) << 30); }
 static inline uint32_t scl_op(uint32_t w) { return w & 7; }
 static inline uint32_t scl_level(uint32_t w) { return (w >> 3) & 31; }
-static inline uint32_t scl_index(uint32_t w) { return (w >> 8) * 32; }
-std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order);
+static inline uint32_t scl_index(uint32_t w) { return ((w >> 8) & 0x3fffffu) * 32; }
+static inline uint32_t scl_depth(uint32_t w) { return (w >> 30) + 1; }
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth = 3);
 
 // ---- misc sequences / codes -----------------------------------------------------------------------------------
 std::vector<uint8_t> mls_bits(int poly, int n);              // first n outputs of the Galois LFSR (reg = 1)

@@ -189,6 +189,61 @@ __device__ __forceinline__ float r0_acc(float m, float4 v)
 	return m;
 }
 
+// F or G at level l fused with the D-1 F steps that follow it down the left spine (host_tables.cc: depth field).
+// One iteration takes the 2^(D-1) quad pairs of the parent whose results meet again in the chained F steps, so the
+// intermediate levels are produced in registers, written once (the later G needs them) and never re-read by an F.
+// 8 x 128-bit loads are in flight per thread for every D.
+template <int D, bool IS_G>
+__device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32)
+{
+	constexpr int M = 1 << (D - 1), U = 4 / M;
+	const int hq = 1 << (l - 3), step = hq >> (D - 1);
+	const float4 *P = A + scl_off4(l);
+	float4 *D1 = A + scl_off4(l - 1);
+	float4 *D2 = A + scl_off4(D >= 2 ? l - 2 : l - 1);
+	float4 *D3 = A + scl_off4(D >= 3 ? l - 3 : l - 1);
+	const bool root = l == 16;
+	for (int q0 = 0; q0 < step; q0 += 8) {
+		uint32_t bw[M];
+		if constexpr (IS_G) {
+#pragma unroll
+			for (int m = 0; m < M; ++m) bw[m] = Bw[((q0 + m * step) >> 3) * 32];
+		}
+#pragma unroll
+		for (int k = 0; k < 8; k += U) {
+			float4 pa[U][M], pb[U][M];
+#pragma unroll
+			for (int u = 0; u < U; ++u)
+#pragma unroll
+				for (int m = 0; m < M; ++m) {
+					const int q = q0 + k + u + m * step;
+					if (root) { pa[u][m] = __ldg(&C4[q]); pb[u][m] = __ldg(&C4[q + hq]); }
+					else { pa[u][m] = P[q * 32 + src]; pb[u][m] = P[(q + hq) * 32 + src]; }
+				}
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				float4 v1[M];
+#pragma unroll
+				for (int m = 0; m < M; ++m) {
+					const int q = q0 + k + u + m * step;
+					if constexpr (IS_G) v1[m] = g_op4(pa[u][m], pb[u][m], (bw[m] >> (4 * (k + u))) & 15u);
+					else v1[m] = f_op4(pa[u][m], pb[u][m]);
+					D1[q * 32 + lane32] = v1[m];
+				}
+				if constexpr (D >= 2) {
+					float4 v2[M / 2];
+#pragma unroll
+					for (int m = 0; m < M / 2; ++m) {
+						v2[m] = f_op4(v1[m], v1[m + M / 2]);
+						D2[(q0 + k + u + m * step) * 32 + lane32] = v2[m];
+					}
+					if constexpr (D >= 3) D3[(q0 + k + u) * 32 + lane32] = f_op4(v2[0], v2[1]);
+				}
+			}
+		}
+	}
+}
+
 // Upper-level ops work on quads (float4 = 4 consecutive tree positions of one lane); loads of a batch of U quads are
 // issued before anything is stored so that U*2 128-bit loads are in flight per thread (the stores may alias the loads
 // as far as the compiler knows, so the batching has to be explicit).
@@ -219,44 +274,24 @@ __global__ void __launch_bounds__(kSclThreads, 2) k_polar_scl(SclParams p)
 
 		for (int pc = 0;; ++pc) {
 			const uint32_t opw = __ldg(&p.ops[pc]);
-			const uint32_t op = opw & 7u, l = (opw >> 3) & 31u, iw = opw >> 8; // iw = first word of the node
+			const uint32_t op = opw & 7u, l = (opw >> 3) & 31u, iw = (opw >> 8) & 0x3fffffu; // iw = first word of the node
 			if (op == OP_END) break;
 			const int hq = 1 << (l - 3);               // quads per half node
 			const float4 *P = A + scl_off4(l);          // parent level (valid for l <= 15)
 			float4 *D = A + scl_off4(l - 1);
-			if (op == OP_F) {
-				for (int q0 = 0; q0 < hq; q0 += kU) {
-					float4 pa[kU], pb[kU];
-					if (l == 16) {
-#pragma unroll
-						for (int u = 0; u < kU; ++u) { pa[u] = __ldg(&C4[q0 + u]); pb[u] = __ldg(&C4[q0 + u + hq]); }
-					} else {
-#pragma unroll
-						for (int u = 0; u < kU; ++u) { pa[u] = P[(q0 + u) * 32 + lane32]; pb[u] = P[(q0 + u + hq) * 32 + lane32]; }
-					}
-#pragma unroll
-					for (int u = 0; u < kU; ++u) D[(q0 + u) * 32 + lane32] = f_op4(pa[u], pb[u]);
-				}
-				__syncwarp();
-			} else if (op == OP_G) {
-				lmstack = (lmstack & ~(7ull << (3 * l))) | ((uint64_t)c.ret << (3 * l));
-				const int src = c.gbase + c.ret;
+			if (op == OP_F || op == OP_G) {
+				const uint32_t depth = opw >> 30; // fused F steps that follow (0..2)
+				if (op == OP_G) lmstack = (lmstack & ~(7ull << (3 * l))) | ((uint64_t)c.ret << (3 * l));
+				const int src = op == OP_G ? c.gbase + c.ret : lane32;
 				const uint32_t *Bw = B + (size_t)iw * 32 + lane32;
-				for (int q0 = 0; q0 < hq; q0 += 8) { // 8 quads = one 32-bit word of partial sums
-					const uint32_t bw = Bw[(q0 >> 3) * 32];
-#pragma unroll
-					for (int h2 = 0; h2 < 8; h2 += kU) {
-						float4 pa[kU], pb[kU];
-						if (l == 16) {
-#pragma unroll
-							for (int u = 0; u < kU; ++u) { pa[u] = __ldg(&C4[q0 + h2 + u]); pb[u] = __ldg(&C4[q0 + h2 + u + hq]); }
-						} else {
-#pragma unroll
-							for (int u = 0; u < kU; ++u) { pa[u] = P[(q0 + h2 + u) * 32 + src]; pb[u] = P[(q0 + h2 + u + hq) * 32 + src]; }
-						}
-#pragma unroll
-						for (int u = 0; u < kU; ++u) D[(q0 + h2 + u) * 32 + lane32] = g_op4(pa[u], pb[u], (bw >> (4 * (h2 + u))) & 15u);
-					}
+				if (op == OP_F) {
+					if (depth == 2) fused_op<3, false>(A, C4, Bw, l, src, lane32);
+					else if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32);
+					else fused_op<1, false>(A, C4, Bw, l, src, lane32);
+				} else {
+					if (depth == 2) fused_op<3, true>(A, C4, Bw, l, src, lane32);
+					else if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32);
+					else fused_op<1, true>(A, C4, Bw, l, src, lane32);
 				}
 				__syncwarp();
 			} else if (op == OP_WORD) {

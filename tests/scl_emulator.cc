@@ -150,24 +150,29 @@ struct Emu {
 			int n = 1 << l, h = n / 2;
 			switch (op) {
 			case OP_F:
+			case OP_G: {
+				if (op == OP_G) for (int t = 0; t < L; ++t) lm[l][t] = ret[t];
 				for (int i = 0; i < h; ++i)
 					for (int t = 0; t < L; ++t) {
-						float pa = l == 16 ? llr[i] : A[l][(size_t)i * L + t];
-						float pb = l == 16 ? llr[i + h] : A[l][(size_t)(i + h) * L + t];
-						A[l - 1][(size_t)i * L + t] = ff(pa, pb);
-					}
-				break;
-			case OP_G:
-				for (int t = 0; t < L; ++t) lm[l][t] = ret[t];
-				for (int i = 0; i < h; ++i)
-					for (int t = 0; t < L; ++t) {
-						int s = ret[t];
+						int s = op == OP_G ? ret[t] : t;
 						float pa = l == 16 ? llr[i] : A[l][(size_t)i * L + s];
 						float pb = l == 16 ? llr[i + h] : A[l][(size_t)(i + h) * L + s];
-						uint32_t bit = (B[(size_t)((index + i) / 32) * L + t] >> ((index + i) % 32)) & 1;
-						A[l - 1][(size_t)i * L + t] = gg(pa, pb, bit);
+						if (op == OP_G) {
+							uint32_t bit = (B[(size_t)((index + i) / 32) * L + t] >> ((index + i) % 32)) & 1;
+							A[l - 1][(size_t)i * L + t] = gg(pa, pb, bit);
+						} else {
+							A[l - 1][(size_t)i * L + t] = ff(pa, pb);
+						}
 					}
+				// fused F steps down the left spine of the child just produced
+				for (uint32_t d = 1; d < scl_depth(w); ++d) {
+					int ll = l - d, hh = 1 << (ll - 1);
+					for (int i = 0; i < hh; ++i)
+						for (int t = 0; t < L; ++t)
+							A[ll - 1][(size_t)i * L + t] = ff(A[ll][(size_t)i * L + t], A[ll][(size_t)(i + hh) * L + t]);
+				}
 				break;
+			}
 			case OP_WORD:
 				word_block(index);
 				break;

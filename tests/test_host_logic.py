@@ -21,7 +21,7 @@ def test_schedule_structure(hostlib):
     n = hostlib.host_schedule(None, 0)
     ops = np.zeros(n, np.uint32)
     hostlib.host_schedule(_p(ops), n)
-    op, lvl, idx = ops & 7, (ops >> 3) & 31, (ops >> 8) * 32
+    op, lvl, idx, depth = ops & 7, (ops >> 3) & 31, ((ops >> 8) & 0x3FFFFF) * 32, (ops >> 30) + 1
     assert op[-1] == 7 and (op[:-1] != 7).all()
     fr = np.zeros(2048, np.uint32)
     hostlib.host_frozen(_p(fr))
@@ -32,9 +32,11 @@ def test_schedule_structure(hostlib):
     for l, i in zip(lvl[op == 3], idx[op == 3]):
         covered[i // 32:(i + (1 << l)) // 32] = True
     assert (covered == (fr == 0xFFFFFFFF)).all()
-    # F, G, C come in matched triples per internal node
-    assert (op == 0).sum() == (op == 1).sum() == (op == 4).sum()
-    assert lvl[op == 0].max() == 16 and lvl[op == 0].min() == 6
+    # every internal node has one F step, one G and one C; F steps are either explicit or fused into the F/G above them
+    f_steps = depth[op == 0].sum() + (depth[op == 1] - 1).sum()
+    assert f_steps == (op == 1).sum() == (op == 4).sum()
+    assert lvl[op == 0].max() == 16 and (lvl[op == 1] - depth[op == 1] + 1).min() >= 6 and depth.max() == 3
+    assert (depth[(op != 0) & (op != 1)] == 1).all()
 
 
 def test_tables_match_oracle(oracle, hostlib):
