@@ -29,8 +29,9 @@ struct DmShared {
 	cfx buf1[kSymLen];
 	cfx prev[kCols];
 	cfx cons[kCols];
-	float y[kCols];
-	float rcp[kCols];   // 1/d for d = 1..431 (index 0 unused)
+	float y[kCols + 8];  // 8 entries of +inf padding: overshoot of the unrolled pair loops never counts
+	float rcp[kCols];    // 1/d for d = 1..431 (index 0 unused)
+	float rcpfar[kCols]; // 1/d for d >= 217, NaN below: pairs closer than 217 belong to the near loop of the other thread
 	float z[kCols];
 	float cand[kCandCap];
 	int hist[kBins];
@@ -181,12 +182,12 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 	const int lane = tid & 31;
 	const bool act = tid < kCols;
 	const float yi = act ? s.y[tid] : 0.f;
-	// ---- fast path: one exact sweep over the OLS pilot bracket
-	{
-		float c, sigma;
-		ols_pilot(s, tid, c, sigma);
-		const float dlt = fmaxf(3.5e-4f * sigma, fmaxf(fabsf(c) * 4e-6f, 1e-10f));
-		const float blo = c - dlt, bhi = c + dlt;
+	// ---- fast path: exact sweeps over the OLS pilot bracket; if the rank falls just outside, slide the bracket
+	float c, sigma;
+	ols_pilot(s, tid, c, sigma);
+	const float dlt = fmaxf(3.5e-4f * sigma, fmaxf(fabsf(c) * 4e-6f, 1e-10f));
+	float blo = c - dlt, bhi = c + dlt;
+	for (int attempt = 0; attempt < 5; ++attempt) {
 		// approximate slopes (diff * 1/d) are within 2 ulp of the exact quotient: anything within mg of the bracket is
 		// re-evaluated exactly, the rest is classified by the approximation
 		const float mg = 2e-6f * fmaxf(fabsf(blo), fabsf(bhi)) + 1e-30f;
@@ -195,28 +196,9 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 		__syncthreads();
 		int cb = 0, cnt = 0;
 		if (act) {
-			// phase 1: classify by the approximate slope only; remember the few pairs near/inside the bracket.
-			// Thread i owns the pairs (i, i+d), d <= min(216, 431-i), and the far pairs (j, i), i-j >= 217: every unordered
-			// pair exactly once, 215 or 216 per thread, and no wrap-around logic inside the loops.
-			const int nA = min(216, kCols - 1 - tid);
 			const float *yp = s.y + tid;
-#pragma unroll 4
-			for (int d = 1; d <= nA; ++d) {
-				const float sl = (yp[d] - yi) * s.rcp[d];
-				if (sl < blo_m) ++cb;
-				else if (sl < bhi_m) { if (cnt < kMineCap) s.mine[cnt][tid] = (unsigned short)d; ++cnt; }
-			}
-			const float *rp = s.rcp + tid;
-#pragma unroll 4
-			for (int j = 0; j <= tid - 217; ++j) {
-				const float sl = (yi - s.y[j]) * rp[-j];
-				if (sl < blo_m) ++cb;
-				else if (sl < bhi_m) { if (cnt < kMineCap) s.mine[cnt][tid] = (unsigned short)(0x8000 | j); ++cnt; }
-			}
-			// phase 2: exact quotients of the remembered pairs (dense: every lane has work)
-			const int m = min(cnt, kMineCap);
-			for (int k = 0; k < m; ++k) {
-				const int code = s.mine[k][tid];
+			// exact evaluation of one remembered pair: code = d (near pair (tid, tid+d)) or 0x8000|j (far pair (j, tid))
+			auto exact_eval = [&](int code) {
 				float diff; int dist;
 				if (code & 0x8000) { const int j = code & 0x7fff; diff = yi - s.y[j]; dist = tid - j; }
 				else { diff = yp[code] - yi; dist = code; }
@@ -226,16 +208,57 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 					const int p = atomicAdd(&s.ncand, 1);
 					if (p < kCandCap) s.cand[p] = q;
 				}
+			};
+			// phase 1: classify by the approximate slope only; remember the few pairs near/inside the bracket.
+			// Thread i owns the pairs (i, i+d), d <= min(216, 431-i), and the far pairs (j, i), i-j >= 217: every unordered
+			// pair exactly once, 215 or 216 per thread, and no wrap-around logic inside the loops.
+			const int nA = min(216, kCols - 1 - tid);
+			for (int d0 = 1; d0 <= nA; d0 += 8) { // 216 = 27 * 8; shorter rows run into the +inf padding
+				unsigned hits = 0;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const float sl = (yp[d0 + k] - yi) * s.rcp[d0 + k];
+					cb += sl < blo_m;
+					hits |= (unsigned)((sl >= blo_m) & (sl < bhi_m)) << k;
+				}
+				while (hits) {
+					const int k = __ffs(hits) - 1;
+					hits &= hits - 1;
+					if (cnt < kMineCap) s.mine[cnt++][tid] = (unsigned short)(d0 + k);
+					else exact_eval(d0 + k); // list full (far pairs cluster on high thread ids): evaluate on the spot
+				}
 			}
-			if (cnt > kMineCap) s.state = 1; // list overflow: take the general path
+			const float *rp = s.rcpfar + tid;
+			for (int j0 = 0; j0 <= tid - 217; j0 += 8) { // overshoot hits the NaN part of rcpfar: never counted
+				unsigned hits = 0;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const float sl = (yi - s.y[j0 + k]) * rp[-(j0 + k)];
+					cb += sl < blo_m;
+					hits |= (unsigned)((sl >= blo_m) & (sl < bhi_m)) << k;
+				}
+				while (hits) {
+					const int k = __ffs(hits) - 1;
+					hits &= hits - 1;
+					if (cnt < kMineCap) s.mine[cnt++][tid] = (unsigned short)(0x8000 | (j0 + k));
+					else exact_eval(0x8000 | (j0 + k));
+				}
+			}
+			// phase 2: exact quotients of the remembered pairs (dense: every lane has work)
+			for (int k = 0; k < cnt; ++k) exact_eval(s.mine[k][tid]);
 		}
 #pragma unroll
 		for (int d = 16; d; d >>= 1) cb += __shfl_xor_sync(FULL, cb, d);
 		if (lane == 0 && cb) atomicAdd(&s.below, cb);
 		__syncthreads();
-		const int kk = kRankSlope - s.below, nc = s.ncand, ovf = s.state;
+		const int kk = kRankSlope - s.below, nc = s.ncand;
 		__syncthreads();
-		if (!ovf && kk >= 0 && kk < nc && nc <= kCandCap) return select_kth(s, s.cand, nc, kk, tid);
+		if (kk >= 0 && kk < nc && nc <= kCandCap) return select_kth(s, s.cand, nc, kk, tid);
+		if (nc > kCandCap) break;
+		// the counts are exact with respect to blo/bhi, so the neighbouring bracket is the next place to look
+		const float w = (bhi - blo) * (float)(2 << attempt);
+		if (kk < 0) { bhi = blo; blo = blo - w; }
+		else { blo = bhi; bhi = bhi + w; }
 	}
 	// ---- general path (pilot missed: outliers, erased rows, very low SNR)
 	// seed bracket: quartiles of the 216 slopes with baseline 216
@@ -365,7 +388,11 @@ __global__ void __launch_bounds__(kDmThreads) k_demod(const cfx *iq, int64_t iq_
 	float *code = llr + (size_t)f * kCodeLen;
 	const int p0 = st.sc_pos + 2 * kPitch; // pilot body (decode.cc:456-459)
 	const double turns = -(double)st.cfo_rad / 6.283185307179586476925286766559;
-	if (tid < kCols) s.rcp[tid] = tid ? __frcp_rn((float)tid) : 0.f;
+	if (tid < kCols) {
+		s.rcp[tid] = tid ? __frcp_rn((float)tid) : 0.f;
+		s.rcpfar[tid] = tid >= 217 ? __frcp_rn((float)tid) : __int_as_float(0x7fc00000);
+	}
+	if (tid < 8) s.y[kCols + tid] = __int_as_float(0x7f800000);
 	float sp = 0.f, np = 0.f; // cumulative, never reset (decode.cc:507)
 	for (int sym = 0; sym <= kConsRows; ++sym) {
 		const int w0 = p0 + kPitch * sym;

@@ -10,6 +10,7 @@
 #include "frontend.cuh"
 #include "polar.cuh"
 #include "../../include/ofdmrx.h"
+#include <algorithm>
 #include <cstring>
 #include <cstdlib>
 #include <vector>
@@ -49,6 +50,8 @@ struct ofdmrx_handle {
 	int last_chunk_frames = 0;
 	cudaEvent_t ev[10] = {};
 	bool ev_valid = false;
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_slice[4] = {}, ev_in_free = nullptr;
 };
 
 namespace {
@@ -119,7 +122,11 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	h->iq_len = ((max_samples + 1 + 127) / 128) * 128; // stream steps t = 0..n, padded
 	// ---- constant tables
 	h->h_frozen = make_frozen(kCodeOrder, kConsBits, kCrcBits);
-	h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder);
+	{
+		int fuse = 2; // F/G chain fusion depth of the SCL schedule (1 = none, kernel supports <= 2); OFDMRX_SCL_FUSE overrides for A/B runs
+		if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(2, std::atoi(e)));
+		h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder, fuse);
+	}
 	std::vector<uint32_t> msg_off(2048);
 	{
 		uint32_t acc = 0;
@@ -168,6 +175,9 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_ncw, (size_t)1);
 	if (!r) r = dev_alloc(&h->d_payload, F * (size_t)(kDataBytes / 4));
 	for (int i = 0; i < 10 && !r; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) r = -12;
+	for (int i = 0; i < 4 && !r; ++i) if (cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming) != cudaSuccess) r = -12;
+	if (!r && cudaEventCreateWithFlags(&h->ev_in_free, cudaEventDisableTiming) != cudaSuccess) r = -12;
+	if (!r && cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) r = -12;
 	if (r) { ofdmrx_destroy(h); return r; }
 	h->in_bytes = F * (size_t)max_samples * 4;
 	*out = h;
@@ -183,6 +193,9 @@ void ofdmrx_destroy(ofdmrx_t *h)
 		h->d_cwlist, h->d_ncw, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+	for (int i = 0; i < 4; ++i) if (h->ev_slice[i]) cudaEventDestroy(h->ev_slice[i]);
+	if (h->ev_in_free) cudaEventDestroy(h->ev_in_free);
+	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	delete h;
 }
 
@@ -232,32 +245,36 @@ int ofdmrx_get_table(ofdmrx_t *h, int which, void *dst, size_t bytes)
 	return (int)(have / 4);
 }
 
-static int run_chunk(ofdmrx_handle *h, const void *d_samples, int format, int nf, int64_t stride, const int32_t *h_nsamp, int skip, cudaStream_t s)
+// front stages (K0..K4) for windows [f0, f0+nf) of the current chunk; d_samples points at window f0
+static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0, int nf, int64_t stride, const int32_t *d_ns, int n_default,
+	int n_max, int skip, cudaStream_t s, bool record)
 {
-	int n_default = (int)std::min<int64_t>(stride, h->max_samples), n_max = n_default;
-	const int32_t *d_ns = nullptr;
-	if (h_nsamp) {
-		n_max = 0;
-		for (int i = 0; i < nf; ++i) {
-			if (h_nsamp[i] < 0 || h_nsamp[i] > h->max_samples || h_nsamp[i] > stride) return -22;
-			n_max = std::max(n_max, (int)h_nsamp[i]);
-		}
-		OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_nsamp, h_nsamp, (size_t)nf * 4, cudaMemcpyHostToDevice, s));
-		d_ns = h->d_nsamp;
-	}
-	cudaEventRecord(h->ev[0], s);
-	OFDMRX_CUDA_TRY(launch_frontend(format, d_samples, stride, d_ns, n_default, nf, h->d_iq, h->iq_len, h->iq_len, h->fc, s));
-	cudaEventRecord(h->ev[1], s);
-	OFDMRX_CUDA_TRY(launch_sync_metric(h->d_iq, h->iq_len, h->iq_len, d_ns, n_default, n_max, nf, h->d_timing, h->iq_len, s));
-	cudaEventRecord(h->ev[2], s);
-	OFDMRX_CUDA_TRY(launch_sync_detect(h->d_timing, h->iq_len, d_ns, n_default, nf, h->d_det, h->d_detcnt, s));
-	cudaEventRecord(h->ev[3], s);
+	const size_t L = (size_t)h->iq_len;
+	cfx *iq = h->d_iq + (size_t)f0 * L;
+	float *timing = h->d_timing + (size_t)f0 * L;
+	const int32_t *ns = d_ns ? d_ns + f0 : nullptr;
+	if (record) cudaEventRecord(h->ev[0], s);
+	OFDMRX_CUDA_TRY(launch_frontend(format, d_samples, stride, ns, n_default, nf, iq, h->iq_len, h->iq_len, h->fc, s));
+	if (record) cudaEventRecord(h->ev[1], s);
+	OFDMRX_CUDA_TRY(launch_sync_metric(iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, s));
+	if (record) cudaEventRecord(h->ev[2], s);
+	OFDMRX_CUDA_TRY(launch_sync_detect(timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, s));
+	if (record) cudaEventRecord(h->ev[3], s);
 	AcquireConsts ac{h->d_tw1280, h->d_tw640, h->d_kern, h->d_mls1, h->d_bch};
-	OFDMRX_CUDA_TRY(launch_acquire(h->d_iq, h->iq_len, h->iq_len, h->d_det, h->d_detcnt, skip, nf, h->d_st, h->d_soft, ac, s));
-	cudaEventRecord(h->ev[4], s);
-	OFDMRX_CUDA_TRY(launch_demod(h->d_iq, h->iq_len, h->iq_len, h->d_st, nf, h->d_tw1280, h->keep_taps ? h->d_cons_raw : nullptr,
-		h->keep_taps ? h->d_cons : nullptr, h->keep_taps ? h->d_ts : nullptr, h->d_llr, s));
-	cudaEventRecord(h->ev[5], s);
+	OFDMRX_CUDA_TRY(launch_acquire(iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
+		h->d_soft + (size_t)f0 * 256, ac, s));
+	if (record) cudaEventRecord(h->ev[4], s);
+	OFDMRX_CUDA_TRY(launch_demod(iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280,
+		h->keep_taps ? h->d_cons_raw + (size_t)f0 * kConsCnt : nullptr, h->keep_taps ? h->d_cons + (size_t)f0 * kConsCnt : nullptr,
+		h->keep_taps ? h->d_ts + (size_t)f0 * kConsRows * 3 : nullptr, h->d_llr + (size_t)f0 * kCodeLen, s));
+	if (record) cudaEventRecord(h->ev[5], s);
+	h->launches += 5;
+	return 0;
+}
+
+// compaction of the header-ok windows + list decoding of the whole chunk
+static int run_scl(ofdmrx_handle *h, int nf, cudaStream_t s)
+{
 	OFDMRX_CUDA_TRY(launch_compact(h->d_st, nf, h->d_cwlist, h->d_ncw, s));
 	OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, s));
 	if (int r = ensure_scl_scratch(h)) return r;
@@ -268,7 +285,7 @@ static int run_chunk(ofdmrx_handle *h, const void *d_samples, int format, int nf
 	OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
 	cudaEventRecord(h->ev[7], s);
 	h->ev_valid = true;
-	h->launches += 8;
+	h->launches += 3;
 	h->last_chunk_frames = nf;
 	return 0;
 }
@@ -285,17 +302,43 @@ int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int form
 	for (int f0 = 0; f0 < n_frames; f0 += h->max_frames) {
 		const int nf = std::min(h->max_frames, n_frames - f0);
 		const char *src = (const char *)samples + (size_t)f0 * frame_bytes;
-		const void *d_src = src;
-		if (mem_kind == OFDMRX_MEM_HOST) {
-			if ((size_t)nf * frame_bytes > h->in_bytes) return -27;
-			OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_in, src, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, s));
-			d_src = h->d_in;
+		const int32_t *h_ns = n_samples ? n_samples + f0 : nullptr;
+		int n_default = (int)std::min<int64_t>(stride, h->max_samples), n_max = n_default;
+		const int32_t *d_ns = nullptr;
+		if (h_ns) {
+			n_max = 0;
+			for (int i = 0; i < nf; ++i) {
+				if (h_ns[i] < 0 || h_ns[i] > h->max_samples || h_ns[i] > stride) return -22;
+				n_max = std::max(n_max, (int)h_ns[i]);
+			}
+			OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_nsamp, h_ns, (size_t)nf * 4, cudaMemcpyHostToDevice, s));
+			d_ns = h->d_nsamp;
 		}
-		if (int r = run_chunk(h, d_src, format, nf, stride, n_samples ? n_samples + f0 : nullptr, skip, s)) return r;
+		if (mem_kind == OFDMRX_MEM_HOST) {
+			// host windows: the H2D copy of slice k+1 runs on the copy stream while slice k goes through the front stages
+			if ((size_t)nf * frame_bytes > h->in_bytes) return -27;
+			const int slices = nf >= 4096 ? 4 : nf >= 1024 ? 2 : 1;
+			const int per = (nf + slices - 1) / slices;
+			OFDMRX_CUDA_TRY(cudaEventRecord(h->ev_in_free, s)); // earlier work on `s` may still read d_in
+			OFDMRX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_in_free, 0));
+			for (int k = 0, a = 0; a < nf; ++k, a += per) {
+				const int m = std::min(per, nf - a);
+				OFDMRX_CUDA_TRY(cudaMemcpyAsync((char *)h->d_in + (size_t)a * frame_bytes, src + (size_t)a * frame_bytes, (size_t)m * frame_bytes,
+					cudaMemcpyHostToDevice, h->copy_stream));
+				OFDMRX_CUDA_TRY(cudaEventRecord(h->ev_slice[k], h->copy_stream));
+			}
+			for (int k = 0, a = 0; a < nf; ++k, a += per) {
+				const int m = std::min(per, nf - a);
+				OFDMRX_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_slice[k], 0));
+				if (int r = run_front(h, (char *)h->d_in + (size_t)a * frame_bytes, format, a, m, stride, d_ns, n_default, n_max, skip, s, a + m >= nf)) return r;
+			}
+		} else {
+			if (int r = run_front(h, src, format, 0, nf, stride, d_ns, n_default, n_max, skip, s, true)) return r;
+		}
+		if (int r = run_scl(h, nf, s)) return r;
 		const cudaMemcpyKind k = mem_kind == OFDMRX_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
 		OFDMRX_CUDA_TRY(cudaMemcpyAsync(payload_out + (size_t)f0 * kDataBytes, h->d_payload, (size_t)nf * kDataBytes, k, s));
 		if (status_out) OFDMRX_CUDA_TRY(cudaMemcpyAsync(status_out + f0, h->d_st, (size_t)nf * sizeof(FrameState), k, s));
-		// the chunk scratch is reused by the next chunk: order the copies before it (same stream) — nothing to do
 	}
 	if (mem_kind == OFDMRX_MEM_HOST) OFDMRX_CUDA_TRY(cudaStreamSynchronize(s));
 	return 0;

@@ -80,23 +80,27 @@ __device__ __noinline__ ForkResult leaf_fork(float metric, float a, int t, int g
 	return r;
 }
 
-// One node of the 32-leaf word, LVL = log2(size), BASE = first leaf.  `a` = this node's alpha values in
-// registers (unused for LVL 5, whose alphas are in the level-5 scratch buffer).
+// ---- the 32-leaf word -------------------------------------------------------------------------------------------
+// Code footprint matters more than instruction count here (the first fully unrolled version was 210 KB of SASS and
+// spent 55 % of its stall cycles waiting for instruction fetch): the word is decoded by ONE non-inlined 8-leaf routine
+// (levels 2..0 unrolled in registers, called four times) under ONE non-inlined 16-leaf routine (called twice).
+struct Sub { float metric; uint32_t W; int ret; int pad; }; // result of a sub-tree: path metric, partial sums, lane map
+
+// One node of an 8-leaf group, LVL = log2(size) <= 3, BASE = first leaf inside the group.  `a` = the node's alphas
+// (registers); c.W / c.fmask hold the group's 8 local partial-sum / frozen bits.
 template <int LVL, int BASE>
 __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 {
 	constexpr int N = 1 << LVL;
-	if constexpr (LVL < 5) {
-		constexpr uint32_t SUB = ((1u << N) - 1u) << BASE;
-		if ((c.fmask & SUB) == SUB) { // rate-0 node (also the frozen leaf)
+	constexpr uint32_t SUB = ((1u << N) - 1u) << BASE;
+	if ((c.fmask & SUB) == SUB) { // rate-0 node (also the frozen leaf)
 #pragma unroll
-			for (int k = 0; k < N; ++k) {
-				const float v = a[k];
-				if (v < 0.f) c.metric = __fsub_rn(c.metric, v);
-			}
-			c.ret = c.t;
-			return;
+		for (int k = 0; k < N; ++k) {
+			const float v = a[k];
+			if (v < 0.f) c.metric = __fsub_rn(c.metric, v);
 		}
+		c.ret = c.t;
+		return;
 	}
 	if constexpr (LVL == 0) {
 		// Fast path (exact): if every "follow the sign" fork beats every "flip" fork and the lanes are already in
@@ -120,59 +124,94 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 	} else {
 		constexpr int H = N / 2;
 		float ch[H];
-		if constexpr (LVL == 5) {
-			float4 v[8];
-			const int own = c.gbase + c.t;
 #pragma unroll
-			for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + own];
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				ch[4 * q + 0] = f_op(v[q].x, v[q + 4].x);
-				ch[4 * q + 1] = f_op(v[q].y, v[q + 4].y);
-				ch[4 * q + 2] = f_op(v[q].z, v[q + 4].z);
-				ch[4 * q + 3] = f_op(v[q].w, v[q + 4].w);
-			}
-		} else {
-#pragma unroll
-			for (int k = 0; k < H; ++k) ch[k] = f_op(a[k], a[k + H]);
-		}
+		for (int k = 0; k < H; ++k) ch[k] = f_op(a[k], a[k + H]);
 		blk_node<LVL - 1, BASE>(c, ch);
 		const int lmap = c.ret;
 		const int srcl = c.gbase + lmap;
-		if constexpr (LVL == 5) {
-			float4 v[8];
 #pragma unroll
-			for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + srcl];
-			const uint32_t wb = c.W >> BASE;
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				ch[4 * q + 0] = g_op(v[q].x, v[q + 4].x, (wb >> (4 * q + 0)) & 1u);
-				ch[4 * q + 1] = g_op(v[q].y, v[q + 4].y, (wb >> (4 * q + 1)) & 1u);
-				ch[4 * q + 2] = g_op(v[q].z, v[q + 4].z, (wb >> (4 * q + 2)) & 1u);
-				ch[4 * q + 3] = g_op(v[q].w, v[q + 4].w, (wb >> (4 * q + 3)) & 1u);
-			}
-		} else if (__all_sync(FULL, lmap == c.t)) { // no lane moved inside the left child: parents are my own registers
-#pragma unroll
-			for (int k = 0; k < H; ++k) ch[k] = g_op(a[k], a[k + H], (c.W >> (BASE + k)) & 1u);
-		} else {
-#pragma unroll
-			for (int k = 0; k < H; ++k) {
-				const float pa = __shfl_sync(FULL, a[k], srcl), pb = __shfl_sync(FULL, a[k + H], srcl);
-				ch[k] = g_op(pa, pb, (c.W >> (BASE + k)) & 1u);
-			}
+		for (int k = 0; k < H; ++k) {
+			const float pa = __shfl_sync(FULL, a[k], srcl), pb = __shfl_sync(FULL, a[k + H], srcl);
+			ch[k] = g_op(pa, pb, (c.W >> (BASE + k)) & 1u);
 		}
 		blk_node<LVL - 1, BASE + H>(c, ch);
 		constexpr uint32_t MASKL = ((1u << H) - 1u) << BASE;
-		if (__all_sync(FULL, c.ret == c.t)) {
-			c.W = (c.W & ~MASKL) | ((c.W ^ (c.W >> H)) & MASKL);
-			c.ret = lmap;
-		} else {
-			const int srcr = c.gbase + c.ret;
-			const uint32_t Wl = __shfl_sync(FULL, c.W, srcr);
-			c.W = (c.W & ~MASKL) | ((Wl ^ (c.W >> H)) & MASKL);
-			c.ret = __shfl_sync(FULL, lmap, srcr);
-		}
+		const int srcr = c.gbase + c.ret;
+		const uint32_t Wl = __shfl_sync(FULL, c.W, srcr);
+		c.W = (c.W & ~MASKL) | ((Wl ^ (c.W >> H)) & MASKL);
+		c.ret = __shfl_sync(FULL, lmap, srcr);
 	}
+}
+
+__device__ __noinline__ Sub leaf8(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
+	uint32_t fmask8, float metric, int t, int gbase)
+{
+	SclCtx c;
+	c.metric = metric; c.ret = t; c.W = 0; c.fmask = fmask8; c.t = t; c.gbase = gbase; c.A5 = nullptr;
+	const float a[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+	blk_node<3, 0>(c, a);
+	Sub r;
+	r.metric = c.metric; r.W = c.W; r.ret = c.ret; r.pad = 0;
+	return r;
+}
+
+// 16 leaves: f -> left 8 -> g (parents through the lane map) -> right 8 -> combine
+__device__ __noinline__ Sub node16(float4 x0, float4 x1, float4 x2, float4 x3, uint32_t fmask16, float metric, int t, int gbase)
+{
+	const float a[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
+	Sub r;
+	r.pad = 0;
+	if (fmask16 == 0xffffu) {
+#pragma unroll
+		for (int k = 0; k < 16; ++k) if (a[k] < 0.f) metric = __fsub_rn(metric, a[k]);
+		r.metric = metric; r.W = 0; r.ret = t;
+		return r;
+	}
+	float ch[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) ch[k] = f_op(a[k], a[k + 8]);
+	const Sub l = leaf8(ch[0], ch[1], ch[2], ch[3], ch[4], ch[5], ch[6], ch[7], fmask16 & 0xffu, metric, t, gbase);
+	const int srcl = gbase + l.ret;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const float pa = __shfl_sync(FULL, a[k], srcl), pb = __shfl_sync(FULL, a[k + 8], srcl);
+		ch[k] = g_op(pa, pb, (l.W >> k) & 1u);
+	}
+	const Sub rr = leaf8(ch[0], ch[1], ch[2], ch[3], ch[4], ch[5], ch[6], ch[7], fmask16 >> 8, l.metric, t, gbase);
+	const int srcr = gbase + rr.ret;
+	const uint32_t Wl = __shfl_sync(FULL, l.W, srcr);
+	r.metric = rr.metric;
+	r.W = ((Wl ^ rr.W) & 0xffu) | (rr.W << 8);
+	r.ret = __shfl_sync(FULL, l.ret, srcr);
+	return r;
+}
+
+// the whole word: alphas of the level-5 node are in the scratch buffer (8 quads per lane)
+__device__ __forceinline__ void word32(SclCtx &c)
+{
+	float4 v[8];
+	const int own = c.gbase + c.t;
+#pragma unroll
+	for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + own];
+	float4 x[4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q) x[q] = make_float4(f_op(v[q].x, v[q + 4].x), f_op(v[q].y, v[q + 4].y), f_op(v[q].z, v[q + 4].z), f_op(v[q].w, v[q + 4].w));
+	const Sub l = node16(x[0], x[1], x[2], x[3], c.fmask & 0xffffu, c.metric, c.t, c.gbase);
+	const int srcl = c.gbase + l.ret;
+#pragma unroll
+	for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + srcl];
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const uint32_t wb = l.W >> (4 * q);
+		x[q] = make_float4(g_op(v[q].x, v[q + 4].x, wb & 1u), g_op(v[q].y, v[q + 4].y, (wb >> 1) & 1u),
+			g_op(v[q].z, v[q + 4].z, (wb >> 2) & 1u), g_op(v[q].w, v[q + 4].w, (wb >> 3) & 1u));
+	}
+	const Sub r = node16(x[0], x[1], x[2], x[3], c.fmask >> 16, l.metric, c.t, c.gbase);
+	const int srcr = c.gbase + r.ret;
+	const uint32_t Wl = __shfl_sync(FULL, l.W, srcr);
+	c.metric = r.metric;
+	c.W = ((Wl ^ r.W) & 0xffffu) | (r.W << 16);
+	c.ret = __shfl_sync(FULL, l.ret, srcr);
 }
 
 __device__ __forceinline__ float4 f_op4(float4 a, float4 b) { return make_float4(f_op(a.x, b.x), f_op(a.y, b.y), f_op(a.z, b.z), f_op(a.w, b.w)); }
@@ -209,7 +248,7 @@ __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint
 #pragma unroll
 			for (int m = 0; m < M; ++m) bw[m] = Bw[((q0 + m * step) >> 3) * 32];
 		}
-#pragma unroll
+#pragma unroll 1
 		for (int k = 0; k < 8; k += U) {
 			float4 pa[U][M], pb[U][M];
 #pragma unroll
@@ -285,19 +324,16 @@ __global__ void __launch_bounds__(kSclThreads, 2) k_polar_scl(SclParams p)
 				const int src = op == OP_G ? c.gbase + c.ret : lane32;
 				const uint32_t *Bw = B + (size_t)iw * 32 + lane32;
 				if (op == OP_F) {
-					if (depth == 2) fused_op<3, false>(A, C4, Bw, l, src, lane32);
-					else if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32);
+					if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32);
 					else fused_op<1, false>(A, C4, Bw, l, src, lane32);
 				} else {
-					if (depth == 2) fused_op<3, true>(A, C4, Bw, l, src, lane32);
-					else if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32);
+					if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32);
 					else fused_op<1, true>(A, C4, Bw, l, src, lane32);
 				}
 				__syncwarp();
 			} else if (op == OP_WORD) {
 				c.fmask = __ldg(&p.frozen[iw]);
-				c.W = 0;
-				blk_node<5, 0>(c, nullptr);
+				word32(c);
 				B[(size_t)iw * 32 + lane32] = c.W;
 				__syncwarp();
 			} else if (op == OP_R0) {
