@@ -22,7 +22,7 @@ constexpr int kCols = kConsCols;           // 432
 constexpr int kPairs = kCols * (kCols - 1) / 2; // 93096
 constexpr int kRankSlope = kPairs / 2;      // element count/2 after nth_element
 constexpr int kRankYint = kCols / 2;
-constexpr int kBins = 256, kCandCap = 4096, kBinCap = 2048, kMineCap = 24;
+constexpr int kBins = 256, kCandCap = 4096, kBinCap = 2048, kMineCap = 40;
 
 struct DmShared {
 	cfx buf0[kSymLen];
@@ -36,6 +36,7 @@ struct DmShared {
 	float cand[kCandCap];
 	int hist[kBins];
 	float red[kDmWarps][2];
+	int wcnt[kDmWarps];
 	double redd[kDmWarps][2];
 	int sel_lo, sel_k, sel_cnt, ncand2;
 	int small[32];
@@ -194,21 +195,16 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 		const float blo_m = blo - mg, bhi_m = bhi + mg;
 		if (tid == 0) { s.below = 0; s.ncand = 0; s.state = 0; }
 		__syncthreads();
-		int cb = 0, cnt = 0;
+		int cb = 0, cnt = 0, nin = 0;
+		const float *yp = s.y + tid;
+		// exact quotient of one remembered pair: code = d (near pair (tid, tid+d)) or 0x8000|j (far pair (j, tid))
+		auto exact_q = [&](int code) {
+			float diff; int dist;
+			if (code & 0x8000) { const int j = code & 0x3fff; diff = yi - s.y[j]; dist = tid - j; }
+			else { diff = yp[code & 0x3fff] - yi; dist = code & 0x3fff; }
+			return __fdiv_rn(diff, (float)dist);
+		};
 		if (act) {
-			const float *yp = s.y + tid;
-			// exact evaluation of one remembered pair: code = d (near pair (tid, tid+d)) or 0x8000|j (far pair (j, tid))
-			auto exact_eval = [&](int code) {
-				float diff; int dist;
-				if (code & 0x8000) { const int j = code & 0x7fff; diff = yi - s.y[j]; dist = tid - j; }
-				else { diff = yp[code] - yi; dist = code; }
-				const float q = __fdiv_rn(diff, (float)dist);
-				if (q < blo) ++cb;
-				else if (q < bhi) {
-					const int p = atomicAdd(&s.ncand, 1);
-					if (p < kCandCap) s.cand[p] = q;
-				}
-			};
 			// phase 1: classify by the approximate slope only; remember the few pairs near/inside the bracket.
 			// Thread i owns the pairs (i, i+d), d <= min(216, 431-i), and the far pairs (j, i), i-j >= 217: every unordered
 			// pair exactly once, 215 or 216 per thread, and no wrap-around logic inside the loops.
@@ -224,8 +220,8 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 				while (hits) {
 					const int k = __ffs(hits) - 1;
 					hits &= hits - 1;
-					if (cnt < kMineCap) s.mine[cnt++][tid] = (unsigned short)(d0 + k);
-					else exact_eval(d0 + k); // list full (far pairs cluster on high thread ids): evaluate on the spot
+					if (cnt < kMineCap) s.mine[cnt][tid] = (unsigned short)(d0 + k);
+					++cnt;
 				}
 			}
 			const float *rp = s.rcpfar + tid;
@@ -240,19 +236,44 @@ __device__ float theil_sen_slope(DmShared &s, int tid)
 				while (hits) {
 					const int k = __ffs(hits) - 1;
 					hits &= hits - 1;
-					if (cnt < kMineCap) s.mine[cnt++][tid] = (unsigned short)(0x8000 | (j0 + k));
-					else exact_eval(0x8000 | (j0 + k));
+					if (cnt < kMineCap) s.mine[cnt][tid] = (unsigned short)(0x8000 | (j0 + k));
+					++cnt;
 				}
 			}
-			// phase 2: exact quotients of the remembered pairs (dense: every lane has work)
-			for (int k = 0; k < cnt; ++k) exact_eval(s.mine[k][tid]);
+			if (cnt > kMineCap) s.state = 1; // list overflow (not seen in practice): take the general path
+			// phase 2a: exact quotients of the remembered pairs; mark those inside the bracket (bit 14)
+			const int m = min(cnt, kMineCap);
+			for (int k = 0; k < m; ++k) {
+				const int code = s.mine[k][tid];
+				const float q = exact_q(code);
+				if (q < blo) ++cb;
+				else if (q < bhi) { s.mine[k][tid] = (unsigned short)(code | 0x4000); ++nin; }
+			}
 		}
+		// slots for the survivors: block-wide exclusive scan of the per-thread counts (no atomics on a single counter)
+		int incl = nin;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+		if (lane == 31) s.wcnt[tid >> 5] = incl;
 #pragma unroll
 		for (int d = 16; d; d >>= 1) cb += __shfl_xor_sync(FULL, cb, d);
 		if (lane == 0 && cb) atomicAdd(&s.below, cb);
 		__syncthreads();
+		int off = incl - nin, total = 0;
+		for (int w = 0; w < kDmWarps; ++w) { if (w < (tid >> 5)) off += s.wcnt[w]; total += s.wcnt[w]; }
+		if (act && total <= kCandCap) {
+			const int m = min(cnt, kMineCap);
+			for (int k = 0; k < m; ++k) {
+				const int code = s.mine[k][tid];
+				if (code & 0x4000) s.cand[off++] = exact_q(code);
+			}
+		}
+		if (tid == 0) s.ncand = total;
+		__syncthreads();
+		const int ovf = s.state;
 		const int kk = kRankSlope - s.below, nc = s.ncand;
 		__syncthreads();
+		if (ovf) break;
 		if (kk >= 0 && kk < nc && nc <= kCandCap) return select_kth(s, s.cand, nc, kk, tid);
 		if (nc > kCandCap) break;
 		// the counts are exact with respect to blo/bhi, so the neighbouring bracket is the next place to look

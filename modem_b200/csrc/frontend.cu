@@ -160,9 +160,15 @@ __global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64
 	if (t0 > n) return; // stream has n+1 steps: t = 0..n
 	const cfx *a = iq + (size_t)f * iq_stride;
 	const int base = t0 - 5918;
-	for (int j = tid; j < kMtPad; j += kMtThreads) {
-		const int idx = base + j;
-		sa[j] = (j < kMtExt && idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
+	{ // all kMtPer loads of a thread are issued before the first shared-memory store (memory-level parallelism)
+		cfx v[kMtPer];
+#pragma unroll
+		for (int k = 0; k < kMtPer; ++k) {
+			const int j = tid + k * kMtThreads, idx = base + j;
+			v[k] = (j < kMtExt && idx >= 0 && idx < iq_len) ? __ldg(&a[idx]) : make_float2(0.f, 0.f);
+		}
+#pragma unroll
+		for (int k = 0; k < kMtPer; ++k) sa[tid + k * kMtThreads] = v[k];
 	}
 	__syncthreads();
 	// per-thread chunk [j0, j0+kMtPer): local sums of c and e, then block scan
