@@ -168,7 +168,7 @@ def main():
     status = torch.empty((n, 112), dtype=torch.uint8, device="cuda")
     host_payload = torch.empty((n, M.PAYLOAD_BYTES), dtype=torch.uint8).pin_memory()
     host_status = torch.empty((n, 112), dtype=torch.uint8).pin_memory()
-    rx = M.Receiver(device=local_rank, max_frames=n, scl_ctas_per_sm=int(os.environ.get("OFDMRX_SCL_CTAS_PER_SM", "3")))
+    rx = M.Receiver(device=local_rank, max_frames=n, scl_ctas_per_sm=int(os.environ.get("OFDMRX_SCL_CTAS_PER_SM", "0")) or None)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_device():

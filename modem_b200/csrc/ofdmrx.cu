@@ -24,7 +24,7 @@ struct ofdmrx_handle {
 	int device = 0, n_sm = 0;
 	int max_frames = 0, max_samples = 0, iq_len = 0;
 	bool keep_taps = false;
-	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0;
+	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0, scl_stream_level = 17;
 	int launches = 0;
 	// constants
 	uint32_t *d_frozen = nullptr, *d_ops = nullptr, *d_msg_off = nullptr, *d_scr = nullptr, *d_bch = nullptr;
@@ -75,7 +75,7 @@ int ensure_scl_scratch(ofdmrx_handle *h)
 	if (h->d_A) return 0;
 	int occ = scl_occupancy_ctas_per_sm();
 	if (occ < 1) occ = 1;
-	int want = h->scl_ctas_per_sm > 0 ? h->scl_ctas_per_sm : 2;
+	int want = h->scl_ctas_per_sm > 0 ? h->scl_ctas_per_sm : kSclCtasPerSm;
 	if (const char *e = std::getenv("OFDMRX_SCL_CTAS_PER_SM")) want = std::atoi(e);
 	if (want > occ) want = occ;
 	if (want < 1) want = 1;
@@ -123,8 +123,10 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	// ---- constant tables
 	h->h_frozen = make_frozen(kCodeOrder, kConsBits, kCrcBits);
 	{
-		int fuse = 2; // F/G chain fusion depth of the SCL schedule (1 = none, kernel supports <= 2); OFDMRX_SCL_FUSE overrides for A/B runs
-		if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(2, std::atoi(e)));
+		int fuse = 2; // F/G chain fusion depth of the SCL schedule (1 = none); OFDMRX_SCL_FUSE overrides for A/B runs
+		if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(3, std::atoi(e)));
+		h->scl_stream_level = 17;
+		if (const char *e = std::getenv("OFDMRX_SCL_STREAM_LEVEL")) h->scl_stream_level = std::atoi(e);
 		h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder, fuse);
 	}
 	std::vector<uint32_t> msg_off(2048);
@@ -281,7 +283,7 @@ static int run_scl(ofdmrx_handle *h, int nf, cudaStream_t s)
 	cudaEventRecord(h->ev[6], s);
 	SclParams p{};
 	p.llr = h->d_llr; p.cw_list = h->d_cwlist; p.n_cw = 0; p.n_cw_ptr = h->d_ncw; p.A = h->d_A; p.B = h->d_B;
-	p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr;
+	p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr; p.stream_level = h->scl_stream_level;
 	OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
 	cudaEventRecord(h->ev[7], s);
 	h->ev_valid = true;
@@ -366,6 +368,7 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
 		p.llr = h->d_llr; p.cw_list = nullptr; p.n_cw = nf; p.n_cw_ptr = nullptr; p.A = h->d_A; p.B = h->d_B;
 		p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st;
 		p.xbits = xbits ? h->d_xbits : nullptr;
+		p.stream_level = h->scl_stream_level;
 		OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
 		h->launches += 2;
 		OFDMRX_CUDA_TRY(cudaMemcpyAsync(payload_out + (size_t)f0 * kDataBytes, h->d_payload, (size_t)nf * kDataBytes, cudaMemcpyDeviceToHost, s));

@@ -214,6 +214,26 @@ __device__ __forceinline__ void word32(SclCtx &c)
 	c.ret = __shfl_sync(FULL, l.ret, srcr);
 }
 
+// L2 cache policy per tree level: the big alpha levels stream through (evict-first) so that they do not push the small,
+// frequently re-read levels out of the 126 MB L2; the policy is a runtime operand, so the code is not duplicated.
+__device__ __forceinline__ uint64_t l2_policy(bool stream)
+{
+	uint64_t p;
+	if (stream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ float4 ld_pol(const float4 *ptr, uint64_t pol)
+{
+	float4 v;
+	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_pol(float4 *ptr, float4 v, uint64_t pol)
+{
+	asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ float4 f_op4(float4 a, float4 b) { return make_float4(f_op(a.x, b.x), f_op(a.y, b.y), f_op(a.z, b.z), f_op(a.w, b.w)); }
 __device__ __forceinline__ float4 g_op4(float4 a, float4 b, uint32_t bits)
 {
@@ -233,8 +253,9 @@ __device__ __forceinline__ float r0_acc(float m, float4 v)
 // intermediate levels are produced in registers, written once (the later G needs them) and never re-read by an F.
 // 8 x 128-bit loads are in flight per thread for every D.
 template <int D, bool IS_G>
-__device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32)
+__device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32, int stream_level)
 {
+	const uint64_t pl = l2_policy(l >= stream_level), p1 = l2_policy(l - 1 >= stream_level), p2 = l2_policy(l - 2 >= stream_level), p3 = l2_policy(l - 3 >= stream_level);
 	constexpr int M = 1 << (D - 1), U = 4 / M;
 	const int hq = 1 << (l - 3), step = hq >> (D - 1);
 	const float4 *P = A + scl_off4(l);
@@ -257,7 +278,7 @@ __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint
 				for (int m = 0; m < M; ++m) {
 					const int q = q0 + k + u + m * step;
 					if (root) { pa[u][m] = __ldg(&C4[q]); pb[u][m] = __ldg(&C4[q + hq]); }
-					else { pa[u][m] = P[q * 32 + src]; pb[u][m] = P[(q + hq) * 32 + src]; }
+					else { pa[u][m] = ld_pol(&P[q * 32 + src], pl); pb[u][m] = ld_pol(&P[(q + hq) * 32 + src], pl); }
 				}
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
@@ -267,16 +288,16 @@ __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint
 					const int q = q0 + k + u + m * step;
 					if constexpr (IS_G) v1[m] = g_op4(pa[u][m], pb[u][m], (bw[m] >> (4 * (k + u))) & 15u);
 					else v1[m] = f_op4(pa[u][m], pb[u][m]);
-					D1[q * 32 + lane32] = v1[m];
+					st_pol(&D1[q * 32 + lane32], v1[m], p1);
 				}
 				if constexpr (D >= 2) {
 					float4 v2[M / 2];
 #pragma unroll
 					for (int m = 0; m < M / 2; ++m) {
 						v2[m] = f_op4(v1[m], v1[m + M / 2]);
-						D2[(q0 + k + u + m * step) * 32 + lane32] = v2[m];
+						st_pol(&D2[(q0 + k + u + m * step) * 32 + lane32], v2[m], p2);
 					}
-					if constexpr (D >= 3) D3[(q0 + k + u) * 32 + lane32] = f_op4(v2[0], v2[1]);
+					if constexpr (D >= 3) st_pol(&D3[(q0 + k + u) * 32 + lane32], f_op4(v2[0], v2[1]), p3);
 				}
 			}
 		}
@@ -288,7 +309,7 @@ __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint
 // as far as the compiler knows, so the batching has to be explicit).
 constexpr int kU = 4;
 
-__global__ void __launch_bounds__(kSclThreads, 2) k_polar_scl(SclParams p)
+__global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclParams p)
 {
 	const int lane32 = threadIdx.x & 31;
 	const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -324,11 +345,13 @@ __global__ void __launch_bounds__(kSclThreads, 2) k_polar_scl(SclParams p)
 				const int src = op == OP_G ? c.gbase + c.ret : lane32;
 				const uint32_t *Bw = B + (size_t)iw * 32 + lane32;
 				if (op == OP_F) {
-					if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32);
-					else fused_op<1, false>(A, C4, Bw, l, src, lane32);
+					if (depth == 2) fused_op<3, false>(A, C4, Bw, l, src, lane32, p.stream_level);
+					else if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32, p.stream_level);
+					else fused_op<1, false>(A, C4, Bw, l, src, lane32, p.stream_level);
 				} else {
-					if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32);
-					else fused_op<1, true>(A, C4, Bw, l, src, lane32);
+					if (depth == 2) fused_op<3, true>(A, C4, Bw, l, src, lane32, p.stream_level);
+					else if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32, p.stream_level);
+					else fused_op<1, true>(A, C4, Bw, l, src, lane32, p.stream_level);
 				}
 				__syncwarp();
 			} else if (op == OP_WORD) {

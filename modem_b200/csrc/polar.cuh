@@ -4,7 +4,8 @@
 
 namespace ofdmrx {
 
-constexpr int kSclThreads = 256;                       // 8 warps = 32 codewords per CTA
+constexpr int kSclThreads = 32;                        // one warp = 4 codewords per CTA (no CTA-level cooperation is needed)
+constexpr int kSclCtasPerSm = 17;                      // 17 x 148 = 2516 warps: 10 000 codewords (BASELINE configs[1]) fit in one pass; needs <= 120 registers
 constexpr size_t kSclWarpFloats = (size_t)(65536 - 32) * 32; // alpha levels 5..15, [element][warp lane]
 constexpr size_t kSclWarpWords = (size_t)2048 * 32;          // beta bits, [word][warp lane]
 __host__ __device__ constexpr size_t scl_off(int l) { return (size_t)((1 << l) - 32) * 32; }
@@ -23,6 +24,7 @@ struct SclParams {
 	const uint32_t *msg_off; // number of non-frozen indices before word w
 	uint32_t *payload;       // [frames][1345] words pre-filled with the scrambler sequence
 	FrameState *st;
+	int stream_level;        // alpha levels >= this use the L2 evict-first policy (17 = none)
 	uint32_t *xbits;         // optional [n_cw][8][2048]: all candidates' codeword bits in rank order (tests)
 };
 

@@ -9,7 +9,7 @@ import oracle_lib as O
 
 n = int(os.environ.get("N_FRAMES", "9472"))
 uniq = int(os.environ.get("N_UNIQ", "592"))
-ctas = int(os.environ.get("CTAS", "2"))
+ctas = int(os.environ.get("CTAS", "0")) or None
 reps = int(os.environ.get("REPS", "3"))
 t = time.time()
 pcm_u, ns, pay_u = O.encode_batch(uniq, seed0=1)
