@@ -125,7 +125,7 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	{
 		int fuse = 2; // F/G chain fusion depth of the SCL schedule (1 = none); OFDMRX_SCL_FUSE overrides for A/B runs
 		if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(3, std::atoi(e)));
-		h->scl_stream_level = 17;
+		h->scl_stream_level = 11; // alpha levels >= 11 stream through L2 (evict-first), smaller ones are kept (evict-last)
 		if (const char *e = std::getenv("OFDMRX_SCL_STREAM_LEVEL")) h->scl_stream_level = std::atoi(e);
 		h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder, fuse);
 	}

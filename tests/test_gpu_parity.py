@@ -207,3 +207,34 @@ def test_device_memory_interface(rx, oracle):
     assert (out.cpu().numpy() == sent).all()
     ms, n = rx.stage_times()
     assert n == 8 and ms["polar_scl"] > 0
+
+
+def test_decode_cli_matches_reference_contract(oracle, tmp_path):
+    """`modem_b200/decode OUTPUT INPUT [SKIP]` (C++ host driver over the C-ABI) against the oracle's decode_ref on the
+    README quick-start recipe: same bytes, exit 0, the reference's stderr lines; failure still writes 5380 bytes."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dec, ref, enc = os.path.join(root, "modem_b200", "decode"), os.path.join(root, "oracle", "build", "decode_ref"), os.path.join(root, "oracle", "build", "encode_ref")
+    data = [os.urandom(5380) for _ in range(2)]
+    for i, d in enumerate(data):
+        (tmp_path / ("in%d.dat" % i)).write_bytes(d)
+    wav = str(tmp_path / "enc.wav")
+    for ch in ("1", "2"):
+        subprocess.run([enc, wav, "8000", "16", ch, "2000", "6", "CALLSIGN", str(tmp_path / "in0.dat"), str(tmp_path / "in1.dat")], check=True)
+        for skip in (0, 1):
+            r = subprocess.run([dec, str(tmp_path / "gpu.dat"), wav, str(skip)], capture_output=True)
+            q = subprocess.run([ref, str(tmp_path / "cpu.dat"), wav, str(skip)], capture_output=True)
+            assert r.returncode == 0 and q.returncode == 0
+            assert (tmp_path / "gpu.dat").read_bytes() == (tmp_path / "cpu.dat").read_bytes() == data[skip]
+            for line in (b"symbol pos:", b"coarse cfo:", b"oper mode: 6", b"call sign:  CALLSIGN", b"bit flips: 0"):
+                assert line in r.stderr, line
+    r = subprocess.run([dec], capture_output=True)
+    assert r.returncode == 1 and b"usage:" in r.stderr
+    raw = bytearray(open(wav, "rb").read())
+    raw[44:] = bytes(len(raw) - 44)
+    open(wav, "wb").write(raw)
+    r = subprocess.run([dec, str(tmp_path / "gpu.dat"), wav], capture_output=True)
+    q = subprocess.run([ref, str(tmp_path / "cpu.dat"), wav], capture_output=True)
+    assert r.returncode == 0 and (tmp_path / "gpu.dat").read_bytes() == (tmp_path / "cpu.dat").read_bytes()
+    assert len((tmp_path / "gpu.dat").read_bytes()) == 5380
