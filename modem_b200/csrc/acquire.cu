@@ -242,7 +242,7 @@ __device__ __forceinline__ cfx load_iq(const cfx *a, int idx, int iq_len)
 	return (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
 }
 
-__global__ void __launch_bounds__(kAcqThreads) k_acquire(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det,
+__global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det,
 	const int32_t *det_count, int skip, FrameState *stv, int8_t *soft_out, AcquireConsts ac)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];

@@ -248,6 +248,11 @@ __device__ __forceinline__ float r0_acc(float m, float4 v)
 	return m;
 }
 
+#ifndef OFDMRX_SCL_PAIRS
+#define OFDMRX_SCL_PAIRS 4
+#endif
+constexpr int kSclPairsInFlight = OFDMRX_SCL_PAIRS; // quad pairs loaded per thread before the first store (x2 128-bit loads in flight)
+
 // F or G at level l fused with the D-1 F steps that follow it down the left spine (host_tables.cc: depth field).
 // One iteration takes the 2^(D-1) quad pairs of the parent whose results meet again in the chained F steps, so the
 // intermediate levels are produced in registers, written once (the later G needs them) and never re-read by an F.
@@ -256,7 +261,7 @@ template <int D, bool IS_G>
 __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32, int stream_level)
 {
 	const uint64_t pl = l2_policy(l >= stream_level), p1 = l2_policy(l - 1 >= stream_level), p2 = l2_policy(l - 2 >= stream_level), p3 = l2_policy(l - 3 >= stream_level);
-	constexpr int M = 1 << (D - 1), U = 4 / M;
+	constexpr int M = 1 << (D - 1), U = kSclPairsInFlight / M;
 	const int hq = 1 << (l - 3), step = hq >> (D - 1);
 	const float4 *P = A + scl_off4(l);
 	float4 *D1 = A + scl_off4(l - 1);
