@@ -68,6 +68,7 @@ typedef struct ofdmrx_frame_status {
 #define OFDMRX_TAP_CONS 4     /* float2[50*432]           cons after Theil-Sen derotation (decode.cc:494) */
 #define OFDMRX_TAP_TS 5       /* float[50*3]              slope, yint, precision per row (decode.cc:488-492,517) */
 #define OFDMRX_TAP_LLR 6      /* float[65536]             code[] after lengthen() (decode.cc:529) */
+#define OFDMRX_TAP_PHASE 7    /* float[50*432]            decision-directed phase errors fed to Theil-Sen (decode.cc:483-486) */
 
 /* Replaces: `new Decoder<float, Complex<float>, 8000>` set-up work (decode.cc:375-387,590-606): constant tables,
  * BCH generator, correlator kernel — plus device scratch for up to max_frames windows of max_samples sample frames
@@ -94,7 +95,11 @@ int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int samp
 int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_out, ofdmrx_frame_status *status_out,
 	uint32_t *xbits);
 
-/* Copies stage outputs of the LAST decode_batch chunk (needs option keep_taps=1 for CONS_RAW/CONS/TS) to host memory. */
+/* Replaces: DSP::TheilSenEstimator<float,512>::compute over x = -216..215 (decode.cc:488) for n_rows (a multiple of 50)
+ * host-resident rows of 432 phase values; out3 receives (slope, yint, pair sweeps the search took) per row. */
+int ofdmrx_theil_sen(ofdmrx_t *h, const float *y, int n_rows, float *out3);
+
+/* Copies stage outputs of the LAST decode_batch chunk (needs option keep_taps=1 for CONS) to host memory. */
 int ofdmrx_get_taps(ofdmrx_t *h, int stage, int frame_first, int frame_count, void *dst, size_t bytes);
 /* elements per window of a tap (in units of the tap's element type) */
 int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage);

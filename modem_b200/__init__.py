@@ -31,9 +31,9 @@ STATUS_TEXT = {  # the reference's stderr strings (decode.cc:419,430,435,440,543
     ST_BAD_MODE: "operation mode unsupported.", ST_BAD_CALL: "call sign unsupported.",
     ST_PAYLOAD_CRC: "payload decoding error.", ST_UNSUPPORTED_MODE: "operation mode not built (7..13).",
 }
-TAP_IQ, TAP_TIMING, TAP_SOFT, TAP_CONS_RAW, TAP_CONS, TAP_TS, TAP_LLR = range(7)
+TAP_IQ, TAP_TIMING, TAP_SOFT, TAP_CONS_RAW, TAP_CONS, TAP_TS, TAP_LLR, TAP_PHASE = range(8)
 _TAP_DTYPE = {TAP_IQ: np.complex64, TAP_TIMING: np.float32, TAP_SOFT: np.int8, TAP_CONS_RAW: np.complex64,
-              TAP_CONS: np.complex64, TAP_TS: np.float32, TAP_LLR: np.float32}
+              TAP_CONS: np.complex64, TAP_TS: np.float32, TAP_LLR: np.float32, TAP_PHASE: np.float32}
 
 STATUS_DTYPE = np.dtype([
     ("status", "<i4"), ("detections", "<i4"), ("t_fire", "<i4"), ("symbol_pos", "<i4"), ("sc_pos", "<i4"),
@@ -45,7 +45,7 @@ assert STATUS_DTYPE.itemsize == 112
 
 EXPORTS = ["ofdmrx_create", "ofdmrx_destroy", "ofdmrx_set_option", "ofdmrx_decode_batch", "ofdmrx_polar_decode",
            "ofdmrx_get_taps", "ofdmrx_tap_elems", "ofdmrx_last_launches", "ofdmrx_stage_times", "ofdmrx_get_table",
-           "ofdmrx_version"]
+           "ofdmrx_version", "ofdmrx_theil_sen"]
 STAGES = ["frontend", "sync_metric", "sync_detect", "acquire", "demod", "compact_init", "polar_scl"]
 
 _lib = None
@@ -70,6 +70,7 @@ def load():
     L.ofdmrx_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
     L.ofdmrx_polar_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ofdmrx_theil_sen.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.ofdmrx_get_taps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.ofdmrx_tap_elems.argtypes = [C.c_void_p, C.c_int]
     L.ofdmrx_tap_elems.restype = C.c_int64
@@ -153,11 +154,25 @@ class Receiver:
                                              xb.ctypes.data if xb is not None else None), "ofdmrx_polar_decode")
         return (payload, status, xb) if want_xbits else (payload, status)
 
+    def theil_sen(self, y):
+        """DSP::TheilSenEstimator over rows of 432 phase values (decode.cc:488): y [n, 432] -> (slope [n], yint [n]).
+        The device works on groups of 50 rows (one window); the input is padded to a multiple of 50."""
+        y = np.ascontiguousarray(y, np.float32)
+        n = y.shape[0]
+        assert y.ndim == 2 and y.shape[1] == 432
+        m = -(-n // 50) * 50
+        yp = np.zeros((m, 432), np.float32)
+        yp[:n] = y
+        out = np.zeros((m, 3), np.float32)
+        _check(self._lib.ofdmrx_theil_sen(self._h, yp.ctypes.data, m, out.ctypes.data), "ofdmrx_theil_sen")
+        self.last_sweeps = out[:n, 2].astype(int)   # pair sweeps per row (>= 100: the bisection fallback ran)
+        return out[:n, 0].copy(), out[:n, 1].copy()
+
     def taps(self, stage, first=0, count=1):
         per = int(self._lib.ofdmrx_tap_elems(self._h, stage))
         out = np.empty((count, per), _TAP_DTYPE[stage])
         _check(self._lib.ofdmrx_get_taps(self._h, stage, first, count, out.ctypes.data, out.nbytes), "ofdmrx_get_taps")
-        if stage in (TAP_CONS_RAW, TAP_CONS):
+        if stage in (TAP_CONS_RAW, TAP_CONS, TAP_PHASE):
             return out.reshape(count, 50, 432)
         if stage == TAP_TS:
             return out.reshape(count, 50, 3)

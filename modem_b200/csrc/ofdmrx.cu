@@ -42,7 +42,7 @@ struct ofdmrx_handle {
 	FrameState *d_st = nullptr;
 	int8_t *d_soft = nullptr;
 	cfx *d_cons_raw = nullptr, *d_cons = nullptr;
-	float *d_ts = nullptr, *d_llr = nullptr;
+	float *d_ts = nullptr, *d_llr = nullptr, *d_y = nullptr;
 	int *d_cwlist = nullptr, *d_ncw = nullptr;
 	uint32_t *d_payload = nullptr;
 	float *d_A = nullptr; uint32_t *d_B = nullptr;
@@ -173,6 +173,9 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_st, F);
 	if (!r) r = dev_alloc(&h->d_soft, F * 256);
 	if (!r) r = dev_alloc(&h->d_llr, F * (size_t)kCodeLen);
+	if (!r) r = dev_alloc(&h->d_cons_raw, F * kConsCnt);
+	if (!r) r = dev_alloc(&h->d_y, F * kConsCnt);
+	if (!r) r = dev_alloc(&h->d_ts, F * kConsRows * 3);
 	if (!r) r = dev_alloc(&h->d_cwlist, F);
 	if (!r) r = dev_alloc(&h->d_ncw, (size_t)1);
 	if (!r) r = dev_alloc(&h->d_payload, F * (size_t)(kDataBytes / 4));
@@ -191,7 +194,7 @@ void ofdmrx_destroy(ofdmrx_t *h)
 	if (!h) return;
 	cudaSetDevice(h->device);
 	void *ptrs[] = {h->d_frozen, h->d_ops, h->d_msg_off, h->d_scr, h->d_bch, h->d_mls1, h->d_tw1280, h->d_tw640, h->d_kern, h->d_in,
-		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr,
+		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr, h->d_y,
 		h->d_cwlist, h->d_ncw, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -209,10 +212,7 @@ int ofdmrx_set_option(ofdmrx_t *h, const char *key, int value)
 		if (h->keep_taps && !h->d_cons) {
 			cudaSetDevice(h->device);
 			const size_t F = (size_t)h->max_frames;
-			int r = dev_alloc(&h->d_cons_raw, F * kConsCnt);
-			if (!r) r = dev_alloc(&h->d_cons, F * kConsCnt);
-			if (!r) r = dev_alloc(&h->d_ts, F * kConsRows * 3);
-			return r;
+			return dev_alloc(&h->d_cons, F * kConsCnt);
 		}
 		return 0;
 	}
@@ -266,11 +266,11 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 	OFDMRX_CUDA_TRY(launch_acquire(iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
 		h->d_soft + (size_t)f0 * 256, ac, s));
 	if (record) cudaEventRecord(h->ev[4], s);
-	OFDMRX_CUDA_TRY(launch_demod(iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280,
-		h->keep_taps ? h->d_cons_raw + (size_t)f0 * kConsCnt : nullptr, h->keep_taps ? h->d_cons + (size_t)f0 * kConsCnt : nullptr,
-		h->keep_taps ? h->d_ts + (size_t)f0 * kConsRows * 3 : nullptr, h->d_llr + (size_t)f0 * kCodeLen, s));
+	OFDMRX_CUDA_TRY(launch_demod(iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kConsCnt,
+		h->d_y + (size_t)f0 * kConsCnt, h->keep_taps ? h->d_cons + (size_t)f0 * kConsCnt : nullptr, h->d_ts + (size_t)f0 * kConsRows * 3,
+		h->d_llr + (size_t)f0 * kCodeLen, h->n_sm, s));
 	if (record) cudaEventRecord(h->ev[5], s);
-	h->launches += 5;
+	h->launches += 7;
 	return 0;
 }
 
@@ -379,6 +379,21 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
 	return 0;
 }
 
+int ofdmrx_theil_sen(ofdmrx_t *h, const float *y, int n_rows, float *out3)
+{
+	if (!h || !y || !out3 || n_rows < 0 || n_rows % kConsRows) return -22;
+	if (n_rows > h->max_frames * kConsRows) return -27;
+	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
+	cudaStream_t s = nullptr;
+	OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_y, y, (size_t)n_rows * kConsCols * 4, cudaMemcpyHostToDevice, s));
+	OFDMRX_CUDA_TRY(cudaMemsetAsync(h->d_ts, 0, (size_t)n_rows * 3 * 4, s));
+	OFDMRX_CUDA_TRY(launch_theil_sen_rows(h->d_y, n_rows, h->d_ts, h->n_sm, s));
+	OFDMRX_CUDA_TRY(cudaMemcpyAsync(out3, h->d_ts, (size_t)n_rows * 3 * 4, cudaMemcpyDeviceToHost, s));
+	OFDMRX_CUDA_TRY(cudaStreamSynchronize(s));
+	h->launches = 1;
+	return 0;
+}
+
 int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage)
 {
 	if (!h) return -22;
@@ -388,6 +403,7 @@ int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage)
 	case OFDMRX_TAP_CONS_RAW: case OFDMRX_TAP_CONS: return kConsCnt;
 	case OFDMRX_TAP_TS: return kConsRows * 3;
 	case OFDMRX_TAP_LLR: return kCodeLen;
+	case OFDMRX_TAP_PHASE: return kConsCnt;
 	}
 	return -22;
 }
@@ -406,6 +422,7 @@ int ofdmrx_get_taps(ofdmrx_t *h, int stage, int first, int count, void *dst, siz
 	case OFDMRX_TAP_CONS: src = h->d_cons; esz = sizeof(cfx); break;
 	case OFDMRX_TAP_TS: src = h->d_ts; esz = 4; break;
 	case OFDMRX_TAP_LLR: src = h->d_llr; esz = 4; break;
+	case OFDMRX_TAP_PHASE: src = h->d_y; esz = 4; break;
 	default: return -22;
 	}
 	if (!src) return -61; // keep_taps was off

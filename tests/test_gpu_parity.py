@@ -73,6 +73,56 @@ def test_polar_degenerate_inputs(rx, oracle):
         assert (payload[i] == opay).all()
 
 
+def _theil_sen_exact(y):
+    """What DSP::TheilSenEstimator computes, restated with numpy fp32 (IEEE) arithmetic: the element of rank count/2 of
+    all pairwise quotients (y_j - y_i) / (x_j - x_i), then of y_i - slope * x_i (decode.cc:488; oracle/ref_dsp.hh)."""
+    y = np.asarray(y, np.float32)
+    i, j = np.triu_indices(432, 1)
+    q = ((y[j] - y[i]).astype(np.float32) / (j - i).astype(np.float32)).astype(np.float32)
+    slope = np.partition(q, q.size // 2)[q.size // 2]
+    x = (np.arange(432) - 216).astype(np.float32)
+    z = (y - (slope * x).astype(np.float32)).astype(np.float32)
+    return slope, np.partition(z, 216)[216]
+
+
+def test_theil_sen_is_the_exact_order_statistic(rx):
+    """Bit-exact against the brute-force order statistic on synthetic rows: Gaussian phase noise at several levels,
+    lines with outliers, heavy ties (quantised phases, erased carriers), constant and exactly linear rows."""
+    rng = np.random.default_rng(11)
+    x = np.arange(432) - 216
+    rows = []
+    for sigma in (1e-4, 3e-3, 0.03, 0.1, 0.25):
+        for slope in (0.0, 1.3e-4, -9e-4):
+            rows.append(np.clip(0.05 + slope * x + sigma * rng.standard_normal(432), -np.pi / 8, np.pi / 8))
+    r = 0.02 * rng.standard_normal(432); r[::9] = rng.uniform(-0.39, 0.39, 48); rows.append(r)          # outliers
+    r = 0.02 * rng.standard_normal(432); r[rng.random(432) < 0.4] = 0.0; rows.append(r)                 # erased carriers
+    rows.append(np.round(0.05 * rng.standard_normal(432) * 16) / 16)                                    # few distinct values
+    rows.append(np.round(rng.uniform(-0.39, 0.39, 432) * 4) / 4)
+    rows.append(np.zeros(432)); rows.append(np.full(432, 0.125)); rows.append(x / 1024.0)               # constant, linear
+    rows.append(rng.uniform(-0.39, 0.39, 432))                                                          # no line at all
+    r = np.zeros(432); r[200:] = 0.3; rows.append(r)                                                    # step
+    y = np.stack(rows).astype(np.float32)
+    slope, yint = rx.theil_sen(y)
+    for k in range(y.shape[0]):
+        es, ey = _theil_sen_exact(y[k])
+        assert slope[k] == es and yint[k] == ey, (k, slope[k], es, yint[k], ey)
+
+
+def test_theil_sen_exact_on_pipeline_rows(rx, oracle):
+    """The same check on the phase errors the device itself produced for noisy frames (tap PHASE -> tap TS)."""
+    import modem_b200 as M
+    imp = oracle.impair(multipath=True, cfo_hz=234.567, sfo_ppm=147, awgn_db=-20, seed=5)
+    pcm, ns, sent = oracle.encode_batch(3, seed0=7100, channels=2, imp=imp)
+    payload, st = rx.decode(pcm, channels=2)
+    assert (st["status"] == 0).all()
+    for f in range(3):
+        y = rx.taps(M.TAP_PHASE, f, 1)[0]
+        ts = rx.taps(M.TAP_TS, f, 1)[0]
+        for row in range(0, 50, 7):
+            es, ey = _theil_sen_exact(y[row])
+            assert ts[row, 0] == es and ts[row, 1] == ey, (f, row)
+
+
 def _compare_frames(rx, oracle, pcm, channels, sent, strict_payload=True):
     import modem_b200 as M
     payload, st = rx.decode(pcm, channels=channels)
