@@ -89,35 +89,33 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 
 // ================================================================================================ k_theil_sen
 constexpr int kTsWarps = 4;            // rows in flight per CTA (one per warp)
-constexpr int kTsCap = 2048;           // in-bracket pairs a warp can queue
+constexpr int kTsCap = 2048;           // in-bracket pairs a warp can queue ...
+constexpr int kTsLaneCap = kTsCap / 32; // ... as 32 private sub-queues
 constexpr int kTsPad = 448;            // 14 x 32 columns, the tail holds +inf
 constexpr int kTsRows = kTsPad / 32;   // 14 row blocks: lane L owns carriers i = 32 R + L
-constexpr int kTsUnroll = 4;           // columns per unrolled step of the sweep (the hit masks shift by this much)
 
 struct TsShared {
 	float y[kTsPad];
 	float2 uv[kTsPad];                 // (y_k - blo x_k, y_k - bhi x_k); later scratch of the selects
 	uint32_t q[kTsCap];                // queued pair codes (i << 16 | j), then their exact quotients
-	int cnt;
-	int pad[3];
 };
 
-// k-th smallest (0-based) of the n floats in v[] (shared memory of this warp), exact: radix select on the
-// order-preserving integer image, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
-__device__ __noinline__ float warp_select_kth(const float *v, int n, int k, int *hist, int lane)
+// k-th smallest (0-based) of the n values v[] (shared memory of this warp; order-preserving integer images of
+// floats, see f2ord), exact: radix select, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
+__device__ __noinline__ int warp_select_kth(const int *v, int n, int k, int *hist, int lane)
 {
 	int mn = 0x7fffffff, mx = (int)0x80000000;
-	for (int i = lane; i < n; i += 32) { const int o = f2ord(v[i]); mn = min(mn, o); mx = max(mx, o); }
+	for (int i = lane; i < n; i += 32) { const int o = v[i]; mn = min(mn, o); mx = max(mx, o); }
 	mn = __reduce_min_sync(FULL, mn);
 	mx = __reduce_max_sync(FULL, mx);
 	int lo = mn;
 	int sh = max(0, 32 - __clz(((unsigned)mx - (unsigned)mn) | 1u) - 8);
 	for (int level = 0; level < 5; ++level) {
 #pragma unroll
-		for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+		for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0;
 		__syncwarp();
 		for (int i = lane; i < n; i += 32) {
-			const unsigned b = ((unsigned)f2ord(v[i]) - (unsigned)lo) >> sh; // values below lo wrap to huge bins
+			const unsigned b = ((unsigned)v[i] - (unsigned)lo) >> sh; // values below lo wrap to huge bins
 			if (b < 256u) atomicAdd(&hist[b], 1);
 		}
 		__syncwarp();
@@ -137,7 +135,7 @@ __device__ __noinline__ float warp_select_kth(const float *v, int n, int k, int 
 			bin += lane * 8;
 		}
 		const unsigned bal = __ballot_sync(FULL, mine);
-		if (bal == 0u) return ord2f(mx); // k out of range (callers never ask for it): keep the function total
+		if (bal == 0u) return mx; // k out of range (callers never ask for it): keep the function total
 		const int src = __ffs(bal) - 1;
 		bin = __shfl_sync(FULL, bin, src);
 		k = __shfl_sync(FULL, kk, src);
@@ -146,27 +144,34 @@ __device__ __noinline__ float warp_select_kth(const float *v, int n, int k, int 
 		if (sh == 0) break;
 		sh = max(0, sh - 8);
 	}
-	return ord2f(lo);
+	return lo;
 }
 
-// One chunk of the pair sweep: columns j = 32 K .. 32 K + 31 against the row blocks R < K (every lane's carrier
-// i = 32 R + L is below every j of the chunk) and the diagonal block R = K (only j > i).  a[R] = u_i - eps and
-// c[R] = v_i + eps live in registers; (u_j, v_j) is one broadcast 64-bit shared load per column.
+// ---- the pair sweep ---------------------------------------------------------------------------------------------
+// Lane L owns the carriers i = 32 R + L of the 14 row blocks R; the columns j come in 14 chunks of 32.  Row block R
+// meets chunk K > R in full (every i is below every j) and chunk K = R on the diagonal (only j > i).  (u_j, v_j) are
+// broadcast shared loads; a = u_i - eps and c = v_i + eps sit in registers:
 //   u_j < a  -> quotient definitely below blo (counted);  else v_j < c -> inside the bracket or within the rounding
-//   margin of an edge: remembered in a per-(R, chunk) bit mask and queued for exact evaluation afterwards.
-// bit b of a hit mask <-> column offset (n_it - 1 - b / U) * U + b % U of its chunk (the masks shift left by U per step)
-__device__ __noinline__ void push_hits(uint32_t m, int i, int col0, TsShared &s)
+//   margin of an edge: remembered in a per-(row block, chunk) bit mask and queued for exact evaluation afterwards.
+// The code is kept small on purpose (two row blocks per pass, run-time loops over the chunks): a first version that
+// unrolled all 105 (R, K) combinations was 100 KB of SASS and spent 40 % of its cycles waiting for instruction fetch.
+constexpr int kTsUnroll = 8;           // columns per unrolled step (the hit masks shift left by this much per step)
+
+// Queue the pairs of one hit mask for exact evaluation.  Every lane owns a private, interleaved sub-queue
+// (s.q[32 n + lane], n < kTsLaneCap) and counts in a register: no atomics, no cross-lane traffic.
+// bit b of a hit mask <-> column offset (n_it - 1 - b / U) * U + b % U of its chunk
+__device__ __forceinline__ void push_hits(uint32_t m, int i, int col0, TsShared &s, int lane, int &nq)
 {
 	while (m) {
 		const int b = __ffs(m) - 1;
 		m &= m - 1;
 		const int joff = (32 / kTsUnroll - 1 - b / kTsUnroll) * kTsUnroll + (b % kTsUnroll);
-		const int pos = atomicAdd(&s.cnt, 1);
-		if (pos < kTsCap) s.q[pos] = ((uint32_t)i << 16) | (uint32_t)(col0 + joff);
+		if (nq < kTsLaneCap) s.q[32 * nq + lane] = ((uint32_t)i << 16) | (uint32_t)(col0 + joff);
+		++nq;
 	}
 }
 
-// one (row, column) slot of the sweep in exactly four instructions: FSETP, @p IADD, FSETP.AND !p, @q LOP3
+// one (row, column) slot in exactly four instructions: FSETP, @p IADD, FSETP.AND !p, @q LOP3
 __device__ __forceinline__ void sweep_slot(float u, float v, float a, float c, int &cb, uint32_t &mask, uint32_t bit)
 {
 	asm("{\n\t.reg .pred p, q;\n\t"
@@ -177,46 +182,68 @@ __device__ __forceinline__ void sweep_slot(float u, float v, float a, float c, i
 		: "+r"(cb), "+r"(mask) : "f"(u), "f"(a), "f"(v), "f"(c), "r"(bit));
 }
 
-template <int K>
-__device__ __forceinline__ void sweep_chunk(const float (&a)[kTsRows], const float (&c)[kTsRows], TsShared &s, int lane, int &cb0, int &cb1)
+// chunk K in full against the row blocks r0 and r0 + 1 (both below K)
+__device__ __forceinline__ void sweep_full2(float a0, float c0, float a1, float c1, int r0, int K, TsShared &s, int lane, int &cb0, int &cb1, int &nq)
 {
-	uint32_t mask[K + 1];
+	uint32_t m0 = 0u, m1 = 0u;
+	const float4 *col = reinterpret_cast<const float4 *>(s.uv + 32 * K);
+#pragma unroll 1
+	for (int it = 0; it < 32 / kTsUnroll; ++it) {
+		m0 <<= kTsUnroll;
+		m1 <<= kTsUnroll;
+		float4 w[kTsUnroll / 2];
 #pragma unroll
-	for (int r = 0; r <= K; ++r) mask[r] = 0u;
-	const float2 *col = s.uv + 32 * K;
-	// diagonal block (row block K): only columns j > i count; below the lane's own offset the thresholds are -inf
+		for (int h = 0; h < kTsUnroll / 2; ++h) w[h] = col[it * (kTsUnroll / 2) + h];
+#pragma unroll
+		for (int h = 0; h < kTsUnroll / 2; ++h) {
+			sweep_slot(w[h].x, w[h].y, a0, c0, cb0, m0, 1u << (2 * h));
+			sweep_slot(w[h].x, w[h].y, a1, c1, cb1, m1, 1u << (2 * h));
+			sweep_slot(w[h].z, w[h].w, a0, c0, cb0, m0, 2u << (2 * h));
+			sweep_slot(w[h].z, w[h].w, a1, c1, cb1, m1, 2u << (2 * h));
+		}
+	}
+	push_hits(m0, 32 * r0 + lane, 32 * K, s, lane, nq);
+	push_hits(m1, 32 * r0 + 32 + lane, 32 * K, s, lane, nq);
+}
+
+// chunk R against its own row block: only the columns whose offset exceeds the lane's count
+__device__ __forceinline__ void sweep_diag(float a, float c, int R, TsShared &s, int lane, int &cb, int &nq)
+{
+	uint32_t m = 0u;
+	const float2 *col = s.uv + 32 * R;
 	const float ninf = __int_as_float(0xff800000);
 #pragma unroll 1
 	for (int it = 0; it < 32 / kTsUnroll; ++it) {
-#pragma unroll
-		for (int r = 0; r <= K; ++r) mask[r] <<= kTsUnroll;
+		m <<= kTsUnroll;
 #pragma unroll
 		for (int jj = 0; jj < kTsUnroll; ++jj) {
 			const float2 w = col[it * kTsUnroll + jj];
-#pragma unroll
-			for (int r = 0; r < K; ++r) sweep_slot(w.x, w.y, a[r], c[r], (r & 1) ? cb1 : cb0, mask[r], 1u << jj);
 			const bool up = it * kTsUnroll + jj > lane;
-			sweep_slot(w.x, w.y, up ? a[K] : ninf, up ? c[K] : ninf, (K & 1) ? cb1 : cb0, mask[K], 1u << jj);
+			sweep_slot(w.x, w.y, up ? a : ninf, up ? c : ninf, cb, m, 1u << jj);
 		}
 	}
-	// queue the remembered pairs for exact evaluation
-#pragma unroll
-	for (int r = 0; r <= K; ++r)
-		if (mask[r]) push_hits(mask[r], 32 * r + lane, 32 * K, s);
+	push_hits(m, 32 * R + lane, 32 * R, s, lane, nq);
 }
 
-template <int K>
-struct SweepAll {
-	static __device__ __forceinline__ void run(const float (&a)[kTsRows], const float (&c)[kTsRows], TsShared &s, int lane, int &cb0, int &cb1)
-	{
-		SweepAll<K - 1>::run(a, c, s, lane, cb0, cb1);
-		sweep_chunk<K>(a, c, s, lane, cb0, cb1);
+// all pairs: returns this lane's count of pairs definitely below the bracket; in-bracket pairs are queued in s.q
+__device__ __forceinline__ int sweep_pairs(TsShared &s, int lane, float eps, int &nq)
+{
+	const float ninf = __int_as_float(0xff800000);
+	int cb0 = 0, cb1 = 0;
+#pragma unroll 1
+	for (int r0 = 0; r0 < kTsRows; r0 += 2) {
+		const int i0 = 32 * r0 + lane, i1 = i0 + 32;
+		const float2 w0 = s.uv[i0], w1 = s.uv[i1];
+		const float a0 = i0 < kCols ? w0.x - eps : ninf, c0 = i0 < kCols ? w0.y + eps : ninf;
+		const float a1 = i1 < kCols ? w1.x - eps : ninf, c1 = i1 < kCols ? w1.y + eps : ninf;
+		sweep_diag(a0, c0, r0, s, lane, cb0, nq);
+		sweep_full2(a0, c0, ninf, ninf, r0, r0 + 1, s, lane, cb0, cb1, nq); // row block r0 + 1 has nothing below chunk r0 + 1
+		sweep_diag(a1, c1, r0 + 1, s, lane, cb1, nq);
+#pragma unroll 1
+		for (int K = r0 + 2; K < kTsRows; ++K) sweep_full2(a0, c0, a1, c1, r0, K, s, lane, cb0, cb1, nq);
 	}
-};
-template <>
-struct SweepAll<-1> {
-	static __device__ __forceinline__ void run(const float (&)[kTsRows], const float (&)[kTsRows], TsShared &, int, int &, int &) {}
-};
+	return cb0 + cb1;
+}
 
 // fallback for rows that defeat the bracket search: smallest value T with #(quotient <= T) > rank, by a binary
 // search over the ordered-int image of the floats with an exact count (one IEEE division per pair) per step.
@@ -240,9 +267,9 @@ __device__ __noinline__ float ts_slope_bisect(const float *y, int lane)
 // exact upper median of the pairwise slopes of (x = i - 216, y[i]); one warp, y in s.y (tail padded)
 __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 {
-	// ---- pilot: least-squares line and residual spread (double accumulation; only steers the bracket)
+	// ---- pilot: least-squares line and residual spread (only steers the bracket, so fp32 sums are good enough)
 	float yv[kTsRows];
-	double a0 = 0.0, a1 = 0.0;
+	float a0 = 0.f, a1 = 0.f;
 	float ymin = __int_as_float(0x7f800000), ymax = -ymin;
 #pragma unroll
 	for (int r = 0; r < kTsRows; ++r) {
@@ -250,9 +277,8 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 		const bool ok = i < kCols;
 		yv[r] = ok ? s.y[i] : 0.f;
 		if (ok) {
-			const double x = (double)(i - kCols / 2) + 0.5;
-			a0 += (double)yv[r];
-			a1 += x * (double)yv[r];
+			a0 += yv[r];
+			a1 = fmaf((float)(i - kCols / 2) + 0.5f, yv[r], a1);
 			ymin = fminf(ymin, yv[r]);
 			ymax = fmaxf(ymax, yv[r]);
 		}
@@ -266,24 +292,24 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 	}
 	if (ymin == ymax) return 0.f; // erased row: every difference is 0, every quotient +0
 	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(s.y, lane); // non-finite input: stay total
-	const double sxx = (double)kCols * ((double)kCols * kCols - 1.0) / 12.0;
-	const double slope = a1 / sxx, mean = a0 / kCols;
-	double r2 = 0.0;
+	const float sxx = (float)((double)kCols * ((double)kCols * kCols - 1.0) / 12.0);
+	const float c0 = a1 / sxx, mean = a0 / (float)kCols;
+	float r2 = 0.f;
 #pragma unroll
 	for (int r = 0; r < kTsRows; ++r) {
 		const int i = 32 * r + lane;
 		if (i < kCols) {
-			const double e = (double)yv[r] - mean - slope * ((double)(i - kCols / 2) + 0.5);
-			r2 += e * e;
+			const float e = yv[r] - mean - c0 * ((float)(i - kCols / 2) + 0.5f);
+			r2 = fmaf(e, e, r2);
 		}
 	}
 #pragma unroll
 	for (int d = 16; d; d >>= 1) r2 += __shfl_xor_sync(FULL, r2, d);
-	const float c0 = (float)slope, sigma = (float)sqrt(r2 / (kCols - 2));
+	const float sigma = sqrtf(r2 / (float)(kCols - 2));
 	const float yabs = fmaxf(fabsf(ymin), fabsf(ymax));
 	// The Theil–Sen median differs from the OLS slope by about 0.84e-4 sigma (its efficiency relative to OLS is 0.955);
-	// +-1.7e-4 sigma holds rank 46 548 in ~95 % of the rows and ~1300 of the 93 096 quotients.
-	float half = fmaxf(1.7e-4f * sigma, fmaxf(fabsf(c0) * 4e-6f, 1e-12f));
+	// +-1.35e-4 sigma holds rank 46 548 in ~90 % of the rows and ~1000 of the 93 096 quotients (~32 per lane's sub-queue).
+	float half = fmaxf(1.35e-4f * sigma, fmaxf(fabsf(c0) * 4e-6f, 1e-12f));
 	float blo = c0 - half, bhi = c0 + half;
 	// enclosure of the answer established so far: #(q < L) = cL <= rank < cU = #(q < U)  (exact counts; +-inf = unknown)
 	const float inf = __int_as_float(0x7f800000);
@@ -295,29 +321,21 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 		// |u_k| rounding (fma, <= 2^-24 |u|) on both sides plus the two roundings of the reference's quotient
 		const float eps = 6e-7f * (yabs + 432.f * bmax) + 1e-30f;
 		__syncwarp();
-		if (lane == 0) s.cnt = 0;
-		float a[kTsRows], c[kTsRows];
 #pragma unroll
 		for (int r = 0; r < kTsRows; ++r) {
 			const int i = 32 * r + lane;
 			const float x = (float)(i - kCols / 2);
-			const bool ok = i < kCols;
 			const float yr = s.y[i]; // +inf in the padded tail
-			const float u = ok ? fmaf(-blo, x, yr) : yr;
-			const float v = ok ? fmaf(-bhi, x, yr) : yr;
-			s.uv[i] = make_float2(u, v);
-			a[r] = ok ? u - eps : -inf;
-			c[r] = ok ? v + eps : -inf;
+			s.uv[i] = i < kCols ? make_float2(fmaf(-blo, x, yr), fmaf(-bhi, x, yr)) : make_float2(yr, yr);
 		}
 		__syncwarp();
-		int cb = 0, cb1 = 0;
-		SweepAll<kTsRows - 1>::run(a, c, s, lane, cb, cb1);
-		cb += cb1;
+		int nql = 0; // pairs this lane queued
+		int cb = sweep_pairs(s, lane, eps, nql);
 		__syncwarp();
-		const int nq = s.cnt;
+		const int nq = __reduce_add_sync(FULL, nql), nqmax = __reduce_max_sync(FULL, nql);
 		const float width = bhi - blo;
-		if (nq > kTsCap) {
-			// more in-bracket pairs than the queue holds.  The definite counts are still complete: cd pairs lie below blo
+		if (nqmax > kTsLaneCap) {
+			// more in-bracket pairs than a sub-queue holds.  The definite counts are still complete: cd pairs lie below blo
 			// for certain and at most cd + nq lie below bhi, which tells where inside the bracket the rank sits.
 			const int cd = __reduce_add_sync(FULL, cb);
 			const int kd = kRankSlope - cd;
@@ -325,7 +343,7 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 			else if (kd >= nq) { L = bhi; cL = cd + nq; }
 			else {
 				const float centre = blo + width * (((float)kd + 0.5f) / (float)nq);
-				const float hw = width * ((float)kTsCap / (5.f * (float)nq));
+				const float hw = width * ((float)kTsCap / (6.f * (float)nq));
 				blo = fmaxf(centre - hw, blo);
 				bhi = fminf(centre + hw, bhi);
 				if (!(blo < bhi)) break;
@@ -333,13 +351,13 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 			}
 		} else {
 			// exact quotients of the queued pairs, as the reference forms them; survivors are compacted in place
+			// (write index <= 32 n never overtakes the entries 32 n + lane still to be read)
 			int nin = 0;
-			for (int e0 = 0; e0 < nq; e0 += 32) {
-				const int e = e0 + lane;
+			for (int n = 0; n < nqmax; ++n) {
 				bool in = false;
 				float q = 0.f;
-				if (e < nq) {
-					const uint32_t code = s.q[e];
+				if (n < nql) {
+					const uint32_t code = s.q[32 * n + lane];
 					const int i = (int)(code >> 16), j = (int)(code & 0xffffu);
 					q = __fdiv_rn(s.y[j] - s.y[i], (float)(j - i));
 					if (q < blo) ++cb;
@@ -347,20 +365,20 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 				}
 				const unsigned bal = __ballot_sync(FULL, in);
 				__syncwarp();
-				if (in) s.q[nin + __popc(bal & ((1u << lane) - 1u))] = __float_as_uint(q);
+				if (in) s.q[nin + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)f2ord(q);
 				nin += __popc(bal);
 			}
 			cb = __reduce_add_sync(FULL, cb);
 			__syncwarp();
 			const int kk = kRankSlope - cb;
-			if (kk >= 0 && kk < nin) return warp_select_kth(reinterpret_cast<const float *>(s.q), nin, kk, reinterpret_cast<int *>(s.uv), lane);
+			if (kk >= 0 && kk < nin) return ord2f(warp_select_kth(reinterpret_cast<const int *>(s.q), nin, kk, reinterpret_cast<int *>(s.uv), lane));
 			// the counts are exact with respect to blo/bhi: tighten the enclosure, then extrapolate with the local density
 			if (kk < 0) { U = blo; cU = cb; }
 			else { L = bhi; cL = cb + nin; }
 			if (nin >= 64 && !(L > -inf && U < inf)) {
 				const float per = width / (float)nin; // slope distance per quotient around here
 				const float centre = kk < 0 ? blo + ((float)kk - 0.5f) * per : bhi + ((float)(kk - nin) + 0.5f) * per;
-				const float hw = 0.5f * width * fminf(1.5f, (float)(kTsCap / 2) / (float)nin);
+				const float hw = 0.5f * width * fminf(1.5f, (float)(kTsCap / 3) / (float)nin);
 				blo = fmaxf(centre - hw, L);
 				bhi = fminf(centre + hw, U);
 				if (!(blo < bhi)) break;
@@ -404,14 +422,14 @@ __global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, c
 		const float slope = ts_slope(s, lane, sweeps);
 		// intercept: upper median of y_i - slope * x_i
 		__syncwarp();
-		float *z = reinterpret_cast<float *>(s.q);
+		int *z = reinterpret_cast<int *>(s.q);
 #pragma unroll
 		for (int r = 0; r < kTsRows; ++r) {
 			const int i = 32 * r + lane;
-			if (i < kCols) z[i] = __fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - kCols / 2)));
+			if (i < kCols) z[i] = f2ord(__fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - kCols / 2))));
 		}
 		__syncwarp();
-		const float yint = warp_select_kth(z, kCols, kRankYint, reinterpret_cast<int *>(s.uv), lane);
+		const float yint = ord2f(warp_select_kth(z, kCols, kRankYint, reinterpret_cast<int *>(s.uv), lane));
 		if (lane == 0) {
 			ts_out[(size_t)row * 3 + 0] = slope;
 			ts_out[(size_t)row * 3 + 1] = yint;
