@@ -107,11 +107,12 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 		// (metric, lane) order, the 8 survivors are the 8 keeps in place — no ranking, no permutation.  Metrics are
 		// non-negative, so their bit patterns order like unsigned integers (REDUX instead of shuffle trees).
 		const float a0 = a[0];
-		const unsigned gmask = 0xffu << c.gbase;
-		const uint32_t maxk = __reduce_max_sync(gmask, __float_as_uint(c.metric));
-		const uint32_t minf = __reduce_min_sync(gmask, __float_as_uint(__fadd_rn(c.metric, fabsf(a0))));
+		// (no 8-lane REDUX here: a __reduce_*_sync whose mask differs between the four codewords of the warp is compiled
+		// into one serialised WARPSYNC.COLLECTIVE pass per group.)  If the lanes are in order, the largest keep metric is
+		// lane 7's, and "it is below every flip metric" can be tested per lane.
+		const float m7 = __shfl_sync(FULL, c.metric, c.gbase | 7);
 		const float prev = __shfl_up_sync(FULL, c.metric, 1);
-		const bool easy = maxk < minf && (c.t == 0 || prev <= c.metric);
+		const bool easy = m7 < __fadd_rn(c.metric, fabsf(a0)) && (c.t == 0 || prev <= c.metric);
 		if (__all_sync(FULL, easy)) {
 			c.ret = c.t;
 			c.W |= (a0 < 0.f ? 1u : 0u) << BASE;
