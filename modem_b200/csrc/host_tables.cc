@@ -47,9 +47,23 @@ static int chain_len(const std::vector<uint32_t> &fr, int level, int index, int 
 	return n;
 }
 // skip_f: this node's own F step was already performed by a fused op of an ancestor (skip_f - 1 more follow)
-static void gen(std::vector<uint32_t> &ops, const std::vector<uint32_t> &fr, int level, int index, int skip_f, int max_depth)
+static void gen(std::vector<uint32_t> &ops, const std::vector<uint32_t> &fr, int level, int index, int skip_f, int max_depth, bool top)
 {
 	const int n = 1 << level;
+	if (top && level > kSclTopLevel) { // virtual node: its children are produced from the channel values by TOP ops
+		for (int half = 0; half < 2; ++half) {
+			const int ci = index + half * (n / 2);
+			if (level - 1 == kSclTopLevel) {
+				const int more = 1; // the kernel's TOP op always produces the left child too (no rate-0 node up here)
+				ops.push_back(scl_pack(OP_TOP, kSclTopLevel, ci, 1 + more));
+				gen(ops, fr, kSclTopLevel, ci, more, max_depth, top);
+			} else {
+				gen(ops, fr, level - 1, ci, 0, max_depth, top);
+			}
+		}
+		ops.push_back(scl_pack(OP_C, level, index));
+		return;
+	}
 	if (all_frozen(fr, index, n)) { ops.push_back(scl_pack(OP_R0, level, index)); return; }
 	if (level == 5) { ops.push_back(scl_pack(OP_WORD, level, index)); return; }
 	int pass_down = 0;
@@ -59,16 +73,20 @@ static void gen(std::vector<uint32_t> &ops, const std::vector<uint32_t> &fr, int
 		ops.push_back(scl_pack(OP_F, level, index, 1 + more));
 		pass_down = more;
 	}
-	gen(ops, fr, level - 1, index, pass_down, max_depth);
+	gen(ops, fr, level - 1, index, pass_down, max_depth, top);
 	const int more = chain_len(fr, level - 1, index + n / 2, max_depth - 1);
 	ops.push_back(scl_pack(OP_G, level, index, 1 + more));
-	gen(ops, fr, level - 1, index + n / 2, more, max_depth);
+	gen(ops, fr, level - 1, index + n / 2, more, max_depth, top);
 	ops.push_back(scl_pack(OP_C, level, index));
 }
-std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth)
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth, bool top_ops)
 {
 	std::vector<uint32_t> ops;
-	gen(ops, frozen, order, 0, 0, max_depth);
+	max_depth = std::max(1, std::min(max_depth, kSclMaxFuse));
+	// TOP ops need no rate-0 node at or above the top level (true for both tables of the reference: the largest is R0-2048)
+	for (int i = 0; top_ops && i < (1 << order); i += 1 << kSclTopLevel)
+		if (all_frozen(frozen, i, 1 << kSclTopLevel)) top_ops = false;
+	gen(ops, frozen, order, 0, 0, max_depth, top_ops && order > kSclTopLevel);
 	ops.push_back(scl_pack(OP_END, 0, 0));
 	return ops;
 }

@@ -34,7 +34,12 @@ std::vector<uint32_t> make_frozen(int order, int n_tx, int k_info);
 //   WORD(idx)    decode the 32 leaves idx..idx+31 (frozen mask word idx/32)
 //   R0(l, idx)   maximal all-frozen node: metric += sum of negative alpha_l, beta = 0
 //   C(l, idx)    beta[idx..idx+h) = perm(beta[idx..idx+h)) ^ beta[idx+h..idx+2h), compose lane maps
-enum SclOp : uint32_t { OP_F = 0, OP_G = 1, OP_WORD = 2, OP_R0 = 3, OP_C = 4, OP_END = 7 };
+//   TOP(13, idx) alpha_13 of the level-13 node at idx recomputed straight from the channel LLRs and the partial sums of its
+//                left-hand relatives (levels 16..14 are then never materialised: their alphas are functions of the
+//                lane-shared channel values and a few beta bits)
+enum SclOp : uint32_t { OP_F = 0, OP_G = 1, OP_WORD = 2, OP_R0 = 3, OP_C = 4, OP_TOP = 5, OP_END = 7 };
+constexpr int kSclTopLevel = 13;
+constexpr int kSclMaxFuse = 2; // longest op chain the kernel instantiates: the op itself + one F step
 // F and G carry a fusion depth d = 1..3 in bits 30..31 (stored as d-1): the op also performs the d-1 F steps that always
 // follow it on the way down the left spine (F(l-1), F(l-2)), so those levels are produced in registers and written once.
 static inline uint32_t scl_pack(uint32_t op, uint32_t level, uint32_t index, uint32_t depth = 1) { return op | (level << 3) | ((index / 32) << 8) | ((depth - 1) << 30); }
@@ -42,7 +47,7 @@ static inline uint32_t scl_op(uint32_t w) { return w & 7; }
 static inline uint32_t scl_level(uint32_t w) { return (w >> 3) & 31; }
 static inline uint32_t scl_index(uint32_t w) { return ((w >> 8) & 0x3fffffu) * 32; }
 static inline uint32_t scl_depth(uint32_t w) { return (w >> 30) + 1; }
-std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth = 3);
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth = kSclMaxFuse, bool top_ops = true);
 
 // ---- misc sequences / codes -----------------------------------------------------------------------------------
 std::vector<uint8_t> mls_bits(int poly, int n);              // first n outputs of the Galois LFSR (reg = 1)

@@ -124,10 +124,12 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	h->h_frozen = make_frozen(kCodeOrder, kConsBits, kCrcBits);
 	{
 		int fuse = 2; // F/G chain fusion depth of the SCL schedule (1 = none); OFDMRX_SCL_FUSE overrides for A/B runs
-		if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(3, std::atoi(e)));
+		if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(kSclMaxFuse, std::atoi(e)));
 		h->scl_stream_level = 11; // alpha levels >= 11 stream through L2 (evict-first), smaller ones are kept (evict-last)
 		if (const char *e = std::getenv("OFDMRX_SCL_STREAM_LEVEL")) h->scl_stream_level = std::atoi(e);
-		h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder, fuse);
+		bool top = true; // levels 16..14 recomputed from the channel LLRs (OP_TOP); OFDMRX_SCL_TOP=0 stores them instead
+		if (const char *e = std::getenv("OFDMRX_SCL_TOP")) top = std::atoi(e) != 0;
+		h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder, fuse, top);
 	}
 	std::vector<uint32_t> msg_off(2048);
 	{

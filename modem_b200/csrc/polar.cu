@@ -310,6 +310,64 @@ __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint
 	}
 }
 
+// TOP(j): alpha of the level-13 node j (8192 positions) straight from the channel LLRs: three f/g steps per value whose
+// operands are 8 lane-shared channel values and up to 7 partial-sum bits of the node's left-hand relatives at levels
+// 15, 14 and 13 (read from the lanes this path descends from: s15, s14, own).  Levels 16..14 are never stored — they
+// were 2 x 2.1 MB of writes plus as much again in reads per codeword, all of it DRAM traffic.  D = 2 also produces
+// the left child at level 12 (the F step that always follows).
+template <int D>
+__device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32_t *B, int j, int s15, int s14, int lane32, int stream_level)
+{
+	const bool j2 = j & 4, j1 = j & 2, j0 = j & 1;
+	const uint32_t *B15 = B + s15;                                           // beta of node (15, 0): words 0..1023
+	const uint32_t *B14 = B + (size_t)(j2 ? 1024 : 0) * 32 + s14;            // beta of node (14, 2 j2)
+	const uint32_t *B13 = B + (size_t)(j0 ? (j - 1) * 256 : 0) * 32 + lane32; // beta of node (13, j - 1)
+	float4 *D13 = A + scl_off4(13), *D12 = A + scl_off4(12);
+	const uint64_t p13 = l2_policy(13 >= stream_level), p12 = l2_policy(12 >= stream_level);
+	constexpr int NQ = D == 2 ? 1024 : 2048;
+	for (int q0 = 0; q0 < NQ; q0 += 8) {
+		uint32_t w15[D][4], w14[D][2], w13[D];
+#pragma unroll
+		for (int h = 0; h < D; ++h) {
+			const int wq = (q0 + 1024 * h) >> 3;
+#pragma unroll
+			for (int m = 0; m < 4; ++m) w15[h][m] = j2 ? B15[(size_t)(wq + 256 * m) * 32] : 0u;
+#pragma unroll
+			for (int m = 0; m < 2; ++m) w14[h][m] = j1 ? B14[(size_t)(wq + 256 * m) * 32] : 0u;
+			w13[h] = j0 ? B13[(size_t)wq * 32] : 0u;
+		}
+#pragma unroll 1
+		for (int k = 0; k < 8; ++k) {
+			const int sh = 4 * k;
+			float4 z[D];
+#pragma unroll
+			for (int h = 0; h < D; ++h) {
+				float4 c[8];
+#pragma unroll
+				for (int kk = 0; kk < 8; ++kk) c[kk] = __ldg(&C4[q0 + k + 1024 * h + 2048 * kk]);
+				float4 x[4], y[2];
+				if (j2) {
+#pragma unroll
+					for (int m = 0; m < 4; ++m) x[m] = g_op4(c[m], c[m + 4], (w15[h][m] >> sh) & 15u);
+				} else {
+#pragma unroll
+					for (int m = 0; m < 4; ++m) x[m] = f_op4(c[m], c[m + 4]);
+				}
+				if (j1) {
+#pragma unroll
+					for (int m = 0; m < 2; ++m) y[m] = g_op4(x[m], x[m + 2], (w14[h][m] >> sh) & 15u);
+				} else {
+#pragma unroll
+					for (int m = 0; m < 2; ++m) y[m] = f_op4(x[m], x[m + 2]);
+				}
+				z[h] = j0 ? g_op4(y[0], y[1], (w13[h] >> sh) & 15u) : f_op4(y[0], y[1]);
+				st_pol(&D13[(size_t)(q0 + k + 1024 * h) * 32 + lane32], z[h], p13);
+			}
+			if constexpr (D == 2) st_pol(&D12[(size_t)(q0 + k) * 32 + lane32], f_op4(z[0], z[1]), p12);
+		}
+	}
+}
+
 // Upper-level ops work on quads (float4 = 4 consecutive tree positions of one lane); loads of a batch of U quads are
 // issued before anything is stored so that U*2 128-bit loads are in flight per thread (the stores may alias the loads
 // as far as the compiler knows, so the batching has to be explicit).
@@ -350,15 +408,27 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 				if (op == OP_G) lmstack = (lmstack & ~(7ull << (3 * l))) | ((uint64_t)c.ret << (3 * l));
 				const int src = op == OP_G ? c.gbase + c.ret : lane32;
 				const uint32_t *Bw = B + (size_t)iw * 32 + lane32;
+				// chains of at most kSclMaxFuse - 1 F steps (host_tables.h); deeper fusion measured slower (registers) and
+				// every instantiation costs instruction-cache footprint, which this kernel is short of
 				if (op == OP_F) {
-					if (depth == 2) fused_op<3, false>(A, C4, Bw, l, src, lane32, p.stream_level);
-					else if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32, p.stream_level);
+					if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32, p.stream_level);
 					else fused_op<1, false>(A, C4, Bw, l, src, lane32, p.stream_level);
 				} else {
-					if (depth == 2) fused_op<3, true>(A, C4, Bw, l, src, lane32, p.stream_level);
-					else if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32, p.stream_level);
+					if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32, p.stream_level);
 					else fused_op<1, true>(A, C4, Bw, l, src, lane32, p.stream_level);
 				}
+				__syncwarp();
+			} else if (op == OP_TOP) {
+				const int j = (int)(iw >> 8); // node index at level 13
+				if (j > 0) { // the left-hand relative at level 13 + ctz(j) has just completed: keep its lane map (as a G would)
+					const int lv = 14 + (__ffs(j) - 1);
+					lmstack = (lmstack & ~(7ull << (3 * lv))) | ((uint64_t)c.ret << (3 * lv));
+				}
+				const int lm14 = (int)((lmstack >> 42) & 7ull), lm15 = (int)((lmstack >> 45) & 7ull);
+				const int u = (j & 1) ? lm14 : c.t;                  // my lane when node (14, 2 j2) completed
+				const int a15 = __shfl_sync(FULL, lm15, c.gbase + u); // ... and when node (15, 0) completed
+				const int s14 = c.gbase + u, s15 = c.gbase + ((j & 2) ? a15 : u);
+				top_op<2>(A, C4, B, j, s15, s14, lane32, p.stream_level); // always chained with the F step below (host_tables.cc)
 				__syncwarp();
 			} else if (op == OP_WORD) {
 				c.fmask = __ldg(&p.frozen[iw]);

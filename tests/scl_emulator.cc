@@ -173,6 +173,28 @@ struct Emu {
 				}
 				break;
 			}
+			case OP_TOP: { // level-13 node j from the channel LLRs and the betas of its left-hand relatives
+				const int j = index >> 13, j2 = (j >> 2) & 1, j1 = (j >> 1) & 1, j0 = j & 1;
+				if (j > 0) { const int lv = 14 + __builtin_ctz(j); for (int t = 0; t < L; ++t) lm[lv][t] = ret[t]; }
+				int s14[L], s15[L];
+				for (int t = 0; t < L; ++t) { int u = j0 ? lm[14][t] : t; s14[t] = u; s15[t] = j1 ? lm[15][u] : u; }
+				auto bit = [&](int base, int p, int lane) { return (B[(size_t)((base + p) / 32) * L + lane] >> ((base + p) % 32)) & 1u; };
+				for (int i = 0; i < 8192; ++i)
+					for (int t = 0; t < L; ++t) {
+						float cc[8], x[4], y[2];
+						for (int k = 0; k < 8; ++k) cc[k] = llr[i + 8192 * k];
+						for (int m = 0; m < 4; ++m) x[m] = j2 ? gg(cc[m], cc[m + 4], bit(0, i + 8192 * m, s15[t])) : ff(cc[m], cc[m + 4]);
+						for (int m = 0; m < 2; ++m) y[m] = j1 ? gg(x[m], x[m + 2], bit(j2 * 32768, i + 8192 * m, s14[t])) : ff(x[m], x[m + 2]);
+						A[13][(size_t)i * L + t] = j0 ? gg(y[0], y[1], bit((j - 1) * 8192, i, t)) : ff(y[0], y[1]);
+					}
+				for (uint32_t d = 1; d < scl_depth(w); ++d) {
+					int ll = 13 - (d - 1), hh = 1 << (ll - 1);
+					for (int i = 0; i < hh; ++i)
+						for (int t = 0; t < L; ++t)
+							A[ll - 1][(size_t)i * L + t] = ff(A[ll][(size_t)i * L + t], A[ll][(size_t)(i + hh) * L + t]);
+				}
+				break;
+			}
 			case OP_WORD:
 				word_block(index);
 				break;

@@ -32,11 +32,15 @@ def test_schedule_structure(hostlib):
     for l, i in zip(lvl[op == 3], idx[op == 3]):
         covered[i // 32:(i + (1 << l)) // 32] = True
     assert (covered == (fr == 0xFFFFFFFF)).all()
-    # every internal node has one F step, one G and one C; F steps are either explicit or fused into the F/G above them
-    f_steps = depth[op == 0].sum() + (depth[op == 1] - 1).sum()
-    assert f_steps == (op == 1).sum() == (op == 4).sum()
-    assert lvl[op == 0].max() == 16 and (lvl[op == 1] - depth[op == 1] + 1).min() >= 6 and depth.max() == 3
-    assert (depth[(op != 0) & (op != 1)] == 1).all()
+    # levels 16..14 are virtual: their 7 nodes only combine (C); the 8 level-13 nodes are produced by TOP ops
+    top = op == 5
+    assert top.sum() == 8 and (lvl[top] == 13).all() and (idx[top] == np.arange(8) * 8192).all()
+    assert lvl[(op == 0) | (op == 1)].max() == 13 and (lvl[op == 4] >= 14).sum() == 7
+    # every internal node below has one F step, one G and one C; F steps are explicit or fused into the op above them
+    f_steps = depth[op == 0].sum() + (depth[op == 1] - 1).sum() + (depth[top] - 1).sum()
+    assert f_steps == (op == 1).sum() == (op == 4).sum() - 7
+    assert (lvl[op == 1] - depth[op == 1] + 1).min() >= 6 and depth.max() == 2 and (depth[top] == 2).all()
+    assert (depth[(op != 0) & (op != 1) & ~top] == 1).all()
 
 
 def test_tables_match_oracle(oracle, hostlib):
