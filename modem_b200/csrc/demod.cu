@@ -94,11 +94,25 @@ constexpr int kTsLaneCap = kTsCap / 32; // ... as 32 private sub-queues
 constexpr int kTsPad = 448;            // 14 x 32 columns, the tail holds +inf
 constexpr int kTsRows = kTsPad / 32;   // 14 row blocks: lane L owns carriers i = 32 R + L
 
+constexpr int kTsCandCap = 1536;       // in-bracket quotients kept for the final select
+
+struct TsSweep {                       // per sweep: every 32-column chunk sorted by u
+	float2 suv[kTsPad];                // (u, v) of the chunk's columns in ascending u
+	uint32_t pm[kTsRows * 33 + 2];     // pm[33 K + p]: set of in-chunk column offsets among the first p sorted entries
+	uint16_t sj[kTsPad];               // original column of each sorted entry
+};
 struct TsShared {
 	float y[kTsPad];
-	float2 uv[kTsPad];                 // (y_k - blo x_k, y_k - bhi x_k); later scratch of the selects
-	uint32_t q[kTsCap];                // queued pair codes (i << 16 | j), then their exact quotients
+	union {
+		TsSweep sw;
+		int cand[kTsCandCap];          // after the sweep: ordered-int images of the exact in-bracket quotients
+	};
+	union {
+		uint16_t q[kTsCap];            // queued pairs (row block << 9 | column), one private sub-queue per lane
+		int hist[256];                 // after their evaluation: scratch of the radix selects
+	};
 };
+static_assert(sizeof(TsSweep) >= kTsCandCap * sizeof(int) && sizeof(TsSweep) >= kTsPad * sizeof(int), "candidate / intercept scratch");
 
 // k-th smallest (0-based) of the n values v[] (shared memory of this warp; order-preserving integer images of
 // floats, see f2ord), exact: radix select, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
@@ -148,101 +162,91 @@ __device__ __noinline__ int warp_select_kth(const int *v, int n, int k, int *his
 }
 
 // ---- the pair sweep ---------------------------------------------------------------------------------------------
-// Lane L owns the carriers i = 32 R + L of the 14 row blocks R; the columns j come in 14 chunks of 32.  Row block R
-// meets chunk K > R in full (every i is below every j) and chunk K = R on the diagonal (only j > i).  (u_j, v_j) are
-// broadcast shared loads; a = u_i - eps and c = v_i + eps sit in registers:
-//   u_j < a  -> quotient definitely below blo (counted);  else v_j < c -> inside the bracket or within the rounding
-//   margin of an edge: remembered in a per-(row block, chunk) bit mask and queued for exact evaluation afterwards.
-// The code is kept small on purpose (two row blocks per pass, run-time loops over the chunks): a first version that
-// unrolled all 105 (R, K) combinations was 100 KB of SASS and spent 40 % of its cycles waiting for instruction fetch.
-constexpr int kTsUnroll = 8;           // columns per unrolled step (the hit masks shift left by this much per step)
-
-// Queue the pairs of one hit mask for exact evaluation.  Every lane owns a private, interleaved sub-queue
-// (s.q[32 n + lane], n < kTsLaneCap) and counts in a register: no atomics, no cross-lane traffic.
-// bit b of a hit mask <-> column offset (n_it - 1 - b / U) * U + b % U of its chunk
-__device__ __forceinline__ void push_hits(uint32_t m, int i, int col0, TsShared &s, int lane, int &nq)
+// With u_k = y_k - blo x_k and v_k = y_k - bhi x_k a pair (i < j) lies below the bracket iff u_j < a_i = u_i - eps and
+// inside it (or within the rounding margin eps of an edge) iff additionally v_j < c_i = v_i + eps.  The columns are
+// sorted by u inside every chunk of 32 (one warp bitonic sort per chunk), so for a row i and a chunk the count below
+// is a 6-step binary search instead of 32 compares, and the in-bracket columns are the few sorted entries that follow:
+// v_j < c_i needs u_j < c_i + w x_j <= c_i + w x_max(chunk), w = bhi - blo >= 0, which bounds the scan.  The chunk
+// holding i itself only counts columns j > i: the prefix sets pm[] turn that into one popcount.
+// Lane L owns the rows i = 32 R + L; in-bracket pairs go to the lane's private sub-queue s.q[32 n + L].
+__device__ __forceinline__ void ts_sort_chunks(TsShared &s, int lane, float blo, float bhi)
 {
-	while (m) {
-		const int b = __ffs(m) - 1;
-		m &= m - 1;
-		const int joff = (32 / kTsUnroll - 1 - b / kTsUnroll) * kTsUnroll + (b % kTsUnroll);
-		if (nq < kTsLaneCap) s.q[32 * nq + lane] = ((uint32_t)i << 16) | (uint32_t)(col0 + joff);
-		++nq;
-	}
-}
-
-// one (row, column) slot in exactly four instructions: FSETP, @p IADD, FSETP.AND !p, @q LOP3
-__device__ __forceinline__ void sweep_slot(float u, float v, float a, float c, int &cb, uint32_t &mask, uint32_t bit)
-{
-	asm("{\n\t.reg .pred p, q;\n\t"
-		"setp.lt.f32 p, %2, %3;\n\t"
-		"@p add.s32 %0, %0, 1;\n\t"
-		"setp.lt.and.f32 q, %4, %5, !p;\n\t"
-		"@q or.b32 %1, %1, %6;\n\t}"
-		: "+r"(cb), "+r"(mask) : "f"(u), "f"(a), "f"(v), "f"(c), "r"(bit));
-}
-
-// chunk K in full against the row blocks r0 and r0 + 1 (both below K)
-__device__ __forceinline__ void sweep_full2(float a0, float c0, float a1, float c1, int r0, int K, TsShared &s, int lane, int &cb0, int &cb1, int &nq)
-{
-	uint32_t m0 = 0u, m1 = 0u;
-	const float4 *col = reinterpret_cast<const float4 *>(s.uv + 32 * K);
+	const float inf = __int_as_float(0x7f800000);
 #pragma unroll 1
-	for (int it = 0; it < 32 / kTsUnroll; ++it) {
-		m0 <<= kTsUnroll;
-		m1 <<= kTsUnroll;
-		float4 w[kTsUnroll / 2];
+	for (int K = 0; K < kTsRows; ++K) {
+		const int j = 32 * K + lane;
+		const float yj = s.y[j], x = (float)(j - kCols / 2);
+		float key = j < kCols ? fmaf(-blo, x, yj) : inf;
+		const float v = j < kCols ? fmaf(-bhi, x, yj) : inf;
+		int idx = lane;
+		// bitonic sort of (key, idx) across the warp, ascending
 #pragma unroll
-		for (int h = 0; h < kTsUnroll / 2; ++h) w[h] = col[it * (kTsUnroll / 2) + h];
+		for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-		for (int h = 0; h < kTsUnroll / 2; ++h) {
-			sweep_slot(w[h].x, w[h].y, a0, c0, cb0, m0, 1u << (2 * h));
-			sweep_slot(w[h].x, w[h].y, a1, c1, cb1, m1, 1u << (2 * h));
-			sweep_slot(w[h].z, w[h].w, a0, c0, cb0, m0, 2u << (2 * h));
-			sweep_slot(w[h].z, w[h].w, a1, c1, cb1, m1, 2u << (2 * h));
+			for (int d = k >> 1; d > 0; d >>= 1) {
+				const float ok = __shfl_xor_sync(FULL, key, d);
+				const int oi = __shfl_xor_sync(FULL, idx, d);
+				const bool keep_min = ((lane & d) == 0) == ((lane & k) == 0);
+				const bool other_less = ok < key || (ok == key && oi < idx);
+				if (keep_min == other_less) { key = ok; idx = oi; }
+			}
 		}
+		const float vs = __shfl_sync(FULL, v, idx);
+		s.sw.suv[j] = make_float2(key, vs);
+		s.sw.sj[j] = (uint16_t)(32 * K + idx);
+		uint32_t m = 1u << idx; // inclusive prefix union over the sorted order
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, m, d); if (lane >= d) m |= o; }
+		s.sw.pm[33 * K + lane + 1] = m;
+		if (lane == 0) s.sw.pm[33 * K] = 0u;
 	}
-	push_hits(m0, 32 * r0 + lane, 32 * K, s, lane, nq);
-	push_hits(m1, 32 * r0 + 32 + lane, 32 * K, s, lane, nq);
+	__syncwarp();
 }
 
-// chunk R against its own row block: only the columns whose offset exceeds the lane's count
-__device__ __forceinline__ void sweep_diag(float a, float c, int R, TsShared &s, int lane, int &cb, int &nq)
+// number of entries of the sorted chunk with u < a (0..32)
+__device__ __forceinline__ int ts_lower_bound(const float2 *chunk, float a)
 {
-	uint32_t m = 0u;
-	const float2 *col = s.uv + 32 * R;
-	const float ninf = __int_as_float(0xff800000);
-#pragma unroll 1
-	for (int it = 0; it < 32 / kTsUnroll; ++it) {
-		m <<= kTsUnroll;
+	int p = 0;
 #pragma unroll
-		for (int jj = 0; jj < kTsUnroll; ++jj) {
-			const float2 w = col[it * kTsUnroll + jj];
-			const bool up = it * kTsUnroll + jj > lane;
-			sweep_slot(w.x, w.y, up ? a : ninf, up ? c : ninf, cb, m, 1u << jj);
-		}
-	}
-	push_hits(m, 32 * R + lane, 32 * R, s, lane, nq);
+	for (int st = 16; st > 0; st >>= 1) p += chunk[p + st - 1].x < a ? st : 0;
+	p += chunk[p].x < a ? 1 : 0; // p <= 31 here
+	return p;
 }
 
-// all pairs: returns this lane's count of pairs definitely below the bracket; in-bracket pairs are queued in s.q
-__device__ __forceinline__ int sweep_pairs(TsShared &s, int lane, float eps, int &nq)
+// all pairs: returns this lane's count of pairs definitely below the bracket; nq = pairs this lane queued
+// (searching several chunks at once for more loads in flight was tried and measured slower)
+__device__ __forceinline__ int sweep_pairs(TsShared &s, int lane, float blo, float bhi, float eps, int &nq)
 {
 	const float ninf = __int_as_float(0xff800000);
-	int cb0 = 0, cb1 = 0;
+	const float w = bhi - blo;
+	const uint32_t above = lane == 31 ? 0u : 0xfffffffeu << lane; // column offsets beyond the lane's own
+	int cb = 0;
 #pragma unroll 1
-	for (int r0 = 0; r0 < kTsRows; r0 += 2) {
-		const int i0 = 32 * r0 + lane, i1 = i0 + 32;
-		const float2 w0 = s.uv[i0], w1 = s.uv[i1];
-		const float a0 = i0 < kCols ? w0.x - eps : ninf, c0 = i0 < kCols ? w0.y + eps : ninf;
-		const float a1 = i1 < kCols ? w1.x - eps : ninf, c1 = i1 < kCols ? w1.y + eps : ninf;
-		sweep_diag(a0, c0, r0, s, lane, cb0, nq);
-		sweep_full2(a0, c0, ninf, ninf, r0, r0 + 1, s, lane, cb0, cb1, nq); // row block r0 + 1 has nothing below chunk r0 + 1
-		sweep_diag(a1, c1, r0 + 1, s, lane, cb1, nq);
+	for (int R = 0; R < kTsRows; ++R) {
+		const int i = 32 * R + lane;
+		const float yi = s.y[i], x = (float)(i - kCols / 2);
+		const float a = i < kCols ? fmaf(-blo, x, yi) - eps : ninf;
+		const float c = i < kCols ? fmaf(-bhi, x, yi) + eps : ninf;
 #pragma unroll 1
-		for (int K = r0 + 2; K < kTsRows; ++K) sweep_full2(a0, c0, a1, c1, r0, K, s, lane, cb0, cb1, nq);
+		for (int K = R; K < kTsRows; ++K) {
+			const float2 *chunk = s.sw.suv + 32 * K;
+			int p = ts_lower_bound(chunk, a);
+			cb += K == R ? __popc(s.sw.pm[33 * K + p] & above) : p;
+			// in-bracket candidates: sorted entries from p on while u < c + w x_max(K) (+ eps for the roundings of u and v)
+			const float t = c + fmaf(w, (float)(32 * K + 31 - kCols / 2), eps);
+			while (p < 32) {
+				const float2 e = chunk[p];
+				if (!(e.x < t)) break;
+				const int j = s.sw.sj[32 * K + p];
+				if (e.y < c && (K != R || j > i)) {
+					if (nq < kTsLaneCap) s.q[32 * nq + lane] = (uint16_t)((R << 9) | j);
+					++nq;
+				}
+				++p;
+			}
+		}
 	}
-	return cb0 + cb1;
+	return cb;
 }
 
 // fallback for rows that defeat the bracket search: smallest value T with #(quotient <= T) > rank, by a binary
@@ -321,16 +325,9 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 		// |u_k| rounding (fma, <= 2^-24 |u|) on both sides plus the two roundings of the reference's quotient
 		const float eps = 6e-7f * (yabs + 432.f * bmax) + 1e-30f;
 		__syncwarp();
-#pragma unroll
-		for (int r = 0; r < kTsRows; ++r) {
-			const int i = 32 * r + lane;
-			const float x = (float)(i - kCols / 2);
-			const float yr = s.y[i]; // +inf in the padded tail
-			s.uv[i] = i < kCols ? make_float2(fmaf(-blo, x, yr), fmaf(-bhi, x, yr)) : make_float2(yr, yr);
-		}
-		__syncwarp();
+		ts_sort_chunks(s, lane, blo, bhi);
 		int nql = 0; // pairs this lane queued
-		int cb = sweep_pairs(s, lane, eps, nql);
+		int cb = sweep_pairs(s, lane, blo, bhi, eps, nql);
 		__syncwarp();
 		const int nq = __reduce_add_sync(FULL, nql), nqmax = __reduce_max_sync(FULL, nql);
 		const float width = bhi - blo;
@@ -350,28 +347,38 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 				continue;
 			}
 		} else {
-			// exact quotients of the queued pairs, as the reference forms them; survivors are compacted in place
-			// (write index <= 32 n never overtakes the entries 32 n + lane still to be read)
+			// exact quotients of the queued pairs, as the reference forms them; the in-bracket ones are compacted into s.cand
 			int nin = 0;
 			for (int n = 0; n < nqmax; ++n) {
 				bool in = false;
 				float q = 0.f;
 				if (n < nql) {
 					const uint32_t code = s.q[32 * n + lane];
-					const int i = (int)(code >> 16), j = (int)(code & 0xffffu);
+					const int i = 32 * (int)(code >> 9) + lane, j = (int)(code & 511u);
 					q = __fdiv_rn(s.y[j] - s.y[i], (float)(j - i));
 					if (q < blo) ++cb;
 					else in = q < bhi;
 				}
 				const unsigned bal = __ballot_sync(FULL, in);
 				__syncwarp();
-				if (in) s.q[nin + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)f2ord(q);
+				const int slot = nin + __popc(bal & ((1u << lane) - 1u));
+				if (in && slot < kTsCandCap) s.cand[slot] = f2ord(q);
 				nin += __popc(bal);
 			}
 			cb = __reduce_add_sync(FULL, cb);
 			__syncwarp();
 			const int kk = kRankSlope - cb;
-			if (kk >= 0 && kk < nin) return ord2f(warp_select_kth(reinterpret_cast<const int *>(s.q), nin, kk, reinterpret_cast<int *>(s.uv), lane));
+			if (kk >= 0 && kk < nin) {
+				if (nin <= kTsCandCap) return ord2f(warp_select_kth(s.cand, nin, kk, s.hist, lane));
+				// the rank is inside but the bracket holds more quotients than the select scratch: zoom in (counts are exact)
+				L = blo; cL = cb; U = bhi; cU = cb + nin;
+				const float centre = blo + width * (((float)kk + 0.5f) / (float)nin);
+				const float hw = width * ((float)kTsCandCap / (4.f * (float)nin));
+				blo = fmaxf(centre - hw, L);
+				bhi = fminf(centre + hw, U);
+				if (!(blo < bhi)) break;
+				continue;
+			}
 			// the counts are exact with respect to blo/bhi: tighten the enclosure, then extrapolate with the local density
 			if (kk < 0) { U = blo; cU = cb; }
 			else { L = bhi; cL = cb + nin; }
@@ -422,14 +429,14 @@ __global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, c
 		const float slope = ts_slope(s, lane, sweeps);
 		// intercept: upper median of y_i - slope * x_i
 		__syncwarp();
-		int *z = reinterpret_cast<int *>(s.q);
+		int *z = s.cand;
 #pragma unroll
 		for (int r = 0; r < kTsRows; ++r) {
 			const int i = 32 * r + lane;
 			if (i < kCols) z[i] = f2ord(__fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - kCols / 2))));
 		}
 		__syncwarp();
-		const float yint = ord2f(warp_select_kth(z, kCols, kRankYint, reinterpret_cast<int *>(s.uv), lane));
+		const float yint = ord2f(warp_select_kth(z, kCols, kRankYint, s.hist, lane));
 		if (lane == 0) {
 			ts_out[(size_t)row * 3 + 0] = slope;
 			ts_out[(size_t)row * 3 + 1] = yint;
