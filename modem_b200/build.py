@@ -19,7 +19,7 @@ CU = ["polar.cu", "frontend.cu", "acquire.cu", "demod.cu", "ofdmrx.cu"]
 CC = ["host_tables.cc"]
 HDRS = ["common.cuh", "polar.cuh", "frontend.cuh", "fft.cuh", "host_tables.h", os.path.join("..", "..", "include", "ofdmrx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-Xptxas", "-v"] + (["-DOFDMRX_SCL_PAIRS=" + os.environ["OFDMRX_SCL_PAIRS"]] if os.environ.get("OFDMRX_SCL_PAIRS") else [])
+              "-Xptxas", "-v"] + [("-D%s=%s" % (k, os.environ[k])) for k in ("OFDMRX_SCL_PAIRS", "OFDMRX_SCL_SMEM_LEVELS") if os.environ.get(k)]
 
 
 def _nvcc():

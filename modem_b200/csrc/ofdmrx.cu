@@ -51,7 +51,7 @@ struct ofdmrx_handle {
 	cudaEvent_t ev[10] = {};
 	bool ev_valid = false;
 	cudaStream_t copy_stream = nullptr;
-	cudaEvent_t ev_slice[4] = {}, ev_in_free = nullptr;
+	cudaEvent_t ev_slice[16] = {}, ev_in_free = nullptr;
 };
 
 namespace {
@@ -182,7 +182,7 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_ncw, (size_t)1);
 	if (!r) r = dev_alloc(&h->d_payload, F * (size_t)(kDataBytes / 4));
 	for (int i = 0; i < 10 && !r; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) r = -12;
-	for (int i = 0; i < 4 && !r; ++i) if (cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming) != cudaSuccess) r = -12;
+	for (int i = 0; i < 16 && !r; ++i) if (cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming) != cudaSuccess) r = -12;
 	if (!r && cudaEventCreateWithFlags(&h->ev_in_free, cudaEventDisableTiming) != cudaSuccess) r = -12;
 	if (!r && cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) r = -12;
 	if (r) { ofdmrx_destroy(h); return r; }
@@ -200,7 +200,7 @@ void ofdmrx_destroy(ofdmrx_t *h)
 		h->d_cwlist, h->d_ncw, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-	for (int i = 0; i < 4; ++i) if (h->ev_slice[i]) cudaEventDestroy(h->ev_slice[i]);
+	for (int i = 0; i < 16; ++i) if (h->ev_slice[i]) cudaEventDestroy(h->ev_slice[i]);
 	if (h->ev_in_free) cudaEventDestroy(h->ev_in_free);
 	if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
 	delete h;
@@ -321,7 +321,8 @@ int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int form
 		if (mem_kind == OFDMRX_MEM_HOST) {
 			// host windows: the H2D copy of slice k+1 runs on the copy stream while slice k goes through the front stages
 			if ((size_t)nf * frame_bytes > h->in_bytes) return -27;
-			const int slices = nf >= 4096 ? 4 : nf >= 1024 ? 2 : 1;
+			// (only the first slice's copy is exposed: many small slices keep that short)
+			const int slices = nf >= 8192 ? 16 : nf >= 4096 ? 8 : nf >= 1024 ? 4 : 1;
 			const int per = (nf + slices - 1) / slices;
 			OFDMRX_CUDA_TRY(cudaEventRecord(h->ev_in_free, s)); // earlier work on `s` may still read d_in
 			OFDMRX_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_in_free, 0));

@@ -249,6 +249,21 @@ __device__ __forceinline__ float r0_acc(float m, float4 v)
 	return m;
 }
 
+// Alpha level 5 (the buffer every 32-leaf word reads twice and every F6/G6 writes) lives in shared memory: 4 KB per warp,
+// [quad][lane] float4 like the global levels; accesses below use generic addressing.  Measured per 10 000 codewords:
+// none 70.2 ms, level 5 68.2 ms, levels 5 and 6 85.7 ms (204 KB of shared memory leave almost no L1 for the rest).
+#ifndef OFDMRX_SCL_SMEM_LEVELS
+#define OFDMRX_SCL_SMEM_LEVELS 1
+#endif
+constexpr int kSclSmemLevels = OFDMRX_SCL_SMEM_LEVELS; // 0: none, 1: level 5, 2: levels 5 and 6
+constexpr int kSclSmemBytes = (kSclSmemLevels >= 1 ? 8 : 0) * 32 * 16 + (kSclSmemLevels >= 2 ? 16 : 0) * 32 * 16;
+__device__ __forceinline__ float4 *lvl_ptr(float4 *A, float4 *S, int l)
+{
+	if (kSclSmemLevels >= 1 && l == 5) return S;
+	if (kSclSmemLevels >= 2 && l == 6) return S + 8 * 32;
+	return A + scl_off4(l);
+}
+
 #ifndef OFDMRX_SCL_PAIRS
 #define OFDMRX_SCL_PAIRS 4
 #endif
@@ -259,15 +274,14 @@ constexpr int kSclPairsInFlight = OFDMRX_SCL_PAIRS; // quad pairs loaded per thr
 // intermediate levels are produced in registers, written once (the later G needs them) and never re-read by an F.
 // 8 x 128-bit loads are in flight per thread for every D.
 template <int D, bool IS_G>
-__device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32, int stream_level)
+__device__ __forceinline__ void fused_op(float4 *A, float4 *S, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32)
 {
-	const uint64_t pl = l2_policy(l >= stream_level), p1 = l2_policy(l - 1 >= stream_level), p2 = l2_policy(l - 2 >= stream_level), p3 = l2_policy(l - 3 >= stream_level);
 	constexpr int M = 1 << (D - 1), U = kSclPairsInFlight / M;
 	const int hq = 1 << (l - 3), step = hq >> (D - 1);
-	const float4 *P = A + scl_off4(l);
-	float4 *D1 = A + scl_off4(l - 1);
-	float4 *D2 = A + scl_off4(D >= 2 ? l - 2 : l - 1);
-	float4 *D3 = A + scl_off4(D >= 3 ? l - 3 : l - 1);
+	const float4 *P = lvl_ptr(A, S, l > 15 ? 15 : l);
+	float4 *D1 = lvl_ptr(A, S, l - 1);
+	float4 *D2 = lvl_ptr(A, S, D >= 2 ? l - 2 : l - 1);
+	float4 *D3 = lvl_ptr(A, S, D >= 3 ? l - 3 : l - 1);
 	const bool root = l == 16;
 	for (int q0 = 0; q0 < step; q0 += 8) {
 		uint32_t bw[M];
@@ -284,7 +298,7 @@ __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint
 				for (int m = 0; m < M; ++m) {
 					const int q = q0 + k + u + m * step;
 					if (root) { pa[u][m] = __ldg(&C4[q]); pb[u][m] = __ldg(&C4[q + hq]); }
-					else { pa[u][m] = ld_pol(&P[q * 32 + src], pl); pb[u][m] = ld_pol(&P[(q + hq) * 32 + src], pl); }
+					else { pa[u][m] = P[q * 32 + src]; pb[u][m] = P[(q + hq) * 32 + src]; }
 				}
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
@@ -294,16 +308,16 @@ __device__ __forceinline__ void fused_op(float4 *A, const float4 *C4, const uint
 					const int q = q0 + k + u + m * step;
 					if constexpr (IS_G) v1[m] = g_op4(pa[u][m], pb[u][m], (bw[m] >> (4 * (k + u))) & 15u);
 					else v1[m] = f_op4(pa[u][m], pb[u][m]);
-					st_pol(&D1[q * 32 + lane32], v1[m], p1);
+					D1[q * 32 + lane32] = v1[m];
 				}
 				if constexpr (D >= 2) {
 					float4 v2[M / 2];
 #pragma unroll
 					for (int m = 0; m < M / 2; ++m) {
 						v2[m] = f_op4(v1[m], v1[m + M / 2]);
-						st_pol(&D2[(q0 + k + u + m * step) * 32 + lane32], v2[m], p2);
+						D2[(q0 + k + u + m * step) * 32 + lane32] = v2[m];
 					}
-					if constexpr (D >= 3) st_pol(&D3[(q0 + k + u) * 32 + lane32], f_op4(v2[0], v2[1]), p3);
+					if constexpr (D >= 3) D3[(q0 + k + u) * 32 + lane32] = f_op4(v2[0], v2[1]);
 				}
 			}
 		}
@@ -383,7 +397,9 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 	SclCtx c;
 	c.t = lane32 & 7;
 	c.gbase = lane32 & ~7;
-	c.A5 = A + scl_off4(5);
+	extern __shared__ __align__(16) float4 scl_smem[];
+	float4 *S = scl_smem;
+	c.A5 = lvl_ptr(A, S, 5);
 
 	const int n_cw = p.n_cw_ptr ? *p.n_cw_ptr : p.n_cw;
 	for (int g4 = warp_global; g4 * 4 < n_cw; g4 += n_warps) {
@@ -401,8 +417,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 			const uint32_t op = opw & 7u, l = (opw >> 3) & 31u, iw = (opw >> 8) & 0x3fffffu; // iw = first word of the node
 			if (op == OP_END) break;
 			const int hq = 1 << (l - 3);               // quads per half node
-			const float4 *P = A + scl_off4(l);          // parent level (valid for l <= 15)
-			float4 *D = A + scl_off4(l - 1);
+			const float4 *P = lvl_ptr(A, S, l > 15 ? 15 : (int)l); // parent level (valid for l <= 15)
 			if (op == OP_F || op == OP_G) {
 				const uint32_t depth = opw >> 30; // fused F steps that follow (0..2)
 				if (op == OP_G) lmstack = (lmstack & ~(7ull << (3 * l))) | ((uint64_t)c.ret << (3 * l));
@@ -411,11 +426,11 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 				// chains of at most kSclMaxFuse - 1 F steps (host_tables.h); deeper fusion measured slower (registers) and
 				// every instantiation costs instruction-cache footprint, which this kernel is short of
 				if (op == OP_F) {
-					if (depth == 1) fused_op<2, false>(A, C4, Bw, l, src, lane32, p.stream_level);
-					else fused_op<1, false>(A, C4, Bw, l, src, lane32, p.stream_level);
+					if (depth == 1) fused_op<2, false>(A, S, C4, Bw, l, src, lane32);
+					else fused_op<1, false>(A, S, C4, Bw, l, src, lane32);
 				} else {
-					if (depth == 1) fused_op<2, true>(A, C4, Bw, l, src, lane32, p.stream_level);
-					else fused_op<1, true>(A, C4, Bw, l, src, lane32, p.stream_level);
+					if (depth == 1) fused_op<2, true>(A, S, C4, Bw, l, src, lane32);
+					else fused_op<1, true>(A, S, C4, Bw, l, src, lane32);
 				}
 				__syncwarp();
 			} else if (op == OP_TOP) {
@@ -566,14 +581,14 @@ cudaError_t launch_payload_init(uint32_t *payload, const uint32_t *scr_words, in
 cudaError_t launch_polar_scl(const SclParams &p, int grid, cudaStream_t s)
 {
 	if (!p.n_cw_ptr && p.n_cw <= 0) return cudaSuccess;
-	k_polar_scl<<<grid, kSclThreads, 0, s>>>(p);
+	k_polar_scl<<<grid, kSclThreads, kSclSmemBytes, s>>>(p);
 	return cudaGetLastError();
 }
 
 int scl_occupancy_ctas_per_sm()
 {
 	int n = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_polar_scl, kSclThreads, 0);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_polar_scl, kSclThreads, kSclSmemBytes);
 	return n;
 }
 
