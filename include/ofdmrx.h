@@ -37,7 +37,7 @@ extern "C" {
 #define OFDMRX_ST_BAD_MODE 4         /* "operation mode N unsupported." (decode.cc:434-437) */
 #define OFDMRX_ST_BAD_CALL 5         /* "call sign unsupported." (decode.cc:439-442) */
 #define OFDMRX_ST_PAYLOAD_CRC 6      /* "payload decoding error." (decode.cc:542-545) */
-#define OFDMRX_ST_UNSUPPORTED_MODE 7 /* modes 7..13 are valid for the reference but not built here yet */
+#define OFDMRX_ST_UNSUPPORTED_MODE 7 /* (not produced any more: modes 6..13 are all decoded on the GPU) */
 
 typedef struct ofdmrx_handle ofdmrx_t;
 
@@ -64,11 +64,12 @@ typedef struct ofdmrx_frame_status {
 #define OFDMRX_TAP_IQ 0       /* float2[iq_len]           analytic stream after next_sample() (decode.cc:294-301) */
 #define OFDMRX_TAP_TIMING 1   /* float[iq_len]            box-161 timing metric per stream step (decode.cc:90) */
 #define OFDMRX_TAP_SOFT 2     /* int8[256]                header soft bits (decode.cc:410-416) */
-#define OFDMRX_TAP_CONS_RAW 3 /* float2[50*432]           cons after demod_or_erase (decode.cc:475) */
-#define OFDMRX_TAP_CONS 4     /* float2[50*432]           cons after Theil-Sen derotation (decode.cc:494) */
-#define OFDMRX_TAP_TS 5       /* float[50*3]              slope, yint, precision per row (decode.cc:488-492,517) */
+/* constellation taps hold rows x cols values of the window's mode (mode 6: 50 x 432) at the front of 32400 slots */
+#define OFDMRX_TAP_CONS_RAW 3 /* float2[32400]            cons after demod_or_erase (decode.cc:475) */
+#define OFDMRX_TAP_CONS 4     /* float2[32400]            cons after Theil-Sen derotation (decode.cc:494) */
+#define OFDMRX_TAP_TS 5       /* float[126*3]             slope, yint, precision per row (decode.cc:488-492,517) */
 #define OFDMRX_TAP_LLR 6      /* float[65536]             code[] after lengthen() (decode.cc:529) */
-#define OFDMRX_TAP_PHASE 7    /* float[50*432]            decision-directed phase errors fed to Theil-Sen (decode.cc:483-486) */
+#define OFDMRX_TAP_PHASE 7    /* float[32400]             decision-directed phase errors fed to Theil-Sen (decode.cc:483-486) */
 
 /* Replaces: `new Decoder<float, Complex<float>, 8000>` set-up work (decode.cc:375-387,590-606): constant tables,
  * BCH generator, correlator kernel — plus device scratch for up to max_frames windows of max_samples sample frames
@@ -76,7 +77,8 @@ typedef struct ofdmrx_frame_status {
 int ofdmrx_create(ofdmrx_t **h, int device, int rate_hz, int max_frames, int max_samples_per_frame);
 void ofdmrx_destroy(ofdmrx_t *h);
 
-/* Tunables / test switches: "keep_taps" (0/1, default 0), "scl_ctas_per_sm" (resident list-decoder warps per SM, 1..17, before the first decode). */
+/* Tunables / test switches: "keep_taps" (0/1, default 0), "scl_ctas_per_sm" (resident list-decoder warps per SM, 1..17,
+ * before the first decode), "polar_table" (0: modes 6..9, 1: modes 10..13 — code table used by ofdmrx_polar_decode). */
 int ofdmrx_set_option(ofdmrx_t *h, const char *key, int value);
 
 /* Replaces: one `decode OUTPUT INPUT [SKIP]` invocation per window (decode.cc:375-556 + the de-scrambling of
@@ -95,9 +97,9 @@ int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int samp
 int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_out, ofdmrx_frame_status *status_out,
 	uint32_t *xbits);
 
-/* Replaces: DSP::TheilSenEstimator<float,512>::compute over x = -216..215 (decode.cc:488) for n_rows (a multiple of 50)
- * host-resident rows of 432 phase values; out3 receives (slope, yint, pair sweeps the search took) per row. */
-int ofdmrx_theil_sen(ofdmrx_t *h, const float *y, int n_rows, float *out3);
+/* Replaces: DSP::TheilSenEstimator<float,512>::compute over x = i - cols/2 (decode.cc:452,484,488) for n_rows
+ * host-resident rows of `cols` (<= 512) phase values; out3 receives (slope, yint, pair sweeps the search took) per row. */
+int ofdmrx_theil_sen(ofdmrx_t *h, const float *y, int n_rows, int cols, float *out3);
 
 /* Copies stage outputs of the LAST decode_batch chunk (needs option keep_taps=1 for CONS) to host memory. */
 int ofdmrx_get_taps(ofdmrx_t *h, int stage, int frame_first, int frame_count, void *dst, size_t bytes);
@@ -110,7 +112,8 @@ int ofdmrx_last_launches(ofdmrx_t *h);
  * ms[0] frontend, [1] timing metric, [2] detection, [3] acquire (fine sync + header), [4] demod (FFT/Theil-Sen/LLR),
  * [5] compaction + payload init, [6] polar list decoder.  Returns the number of windows in that chunk (<0 on error). */
 int ofdmrx_stage_times(ofdmrx_t *h, float *ms, int n);
-/* device-side copies of the constant tables, for tests: which = 0 frozen set (2048 u32), 1 SCL schedule */
+/* device-side copies of the constant tables, for tests: which = 0 frozen set (2048 u32) / 1 SCL schedule of modes 6..9,
+ * 2 / 3 the same for modes 10..13 */
 int ofdmrx_get_table(ofdmrx_t *h, int which, void *dst, size_t bytes);
 const char *ofdmrx_version(void);
 

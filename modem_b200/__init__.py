@@ -43,6 +43,8 @@ STATUS_DTYPE = np.dtype([
 ])
 assert STATUS_DTYPE.itemsize == 112
 
+# (rows, carriers) of the payload symbols per operation mode (decode.cc:302-374)
+MODE_GEOMETRY = {6: (50, 432), 7: (54, 400), 8: (81, 400), 9: (90, 360), 10: (42, 512), 11: (56, 384), 12: (84, 384), 13: (126, 256)}
 EXPORTS = ["ofdmrx_create", "ofdmrx_destroy", "ofdmrx_set_option", "ofdmrx_decode_batch", "ofdmrx_polar_decode",
            "ofdmrx_get_taps", "ofdmrx_tap_elems", "ofdmrx_last_launches", "ofdmrx_stage_times", "ofdmrx_get_table",
            "ofdmrx_version", "ofdmrx_theil_sen"]
@@ -70,7 +72,7 @@ def load():
     L.ofdmrx_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
     L.ofdmrx_polar_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.ofdmrx_theil_sen.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.ofdmrx_theil_sen.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.ofdmrx_get_taps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.ofdmrx_tap_elems.argtypes = [C.c_void_p, C.c_int]
     L.ofdmrx_tap_elems.restype = C.c_int64
@@ -143,8 +145,10 @@ class Receiver:
         _check(self._lib.ofdmrx_decode_batch(self._h, samples_ptr, mem_kind, fmt, n_frames, stride, ns_ptr, skip,
                                              payload_ptr, status_ptr, stream), "ofdmrx_decode_batch")
 
-    def polar_decode(self, llr, want_xbits=False):
-        """llr: float32 [n, 65536] after lengthen().  Returns (payload, status[, xbits uint32 [n,8,2048]])."""
+    def polar_decode(self, llr, want_xbits=False, table=0):
+        """llr: float32 [n, 65536] after lengthen(); table 0 = frozen set of modes 6..9, 1 = modes 10..13.
+        Returns (payload, status[, xbits uint32 [n,8,2048]])."""
+        _check(self._lib.ofdmrx_set_option(self._h, b"polar_table", int(table)), "set_option")
         llr = np.ascontiguousarray(llr, np.float32).reshape(-1, CODE_LEN)
         n = llr.shape[0]
         payload = np.empty((n, PAYLOAD_BYTES), np.uint8)
@@ -155,31 +159,29 @@ class Receiver:
         return (payload, status, xb) if want_xbits else (payload, status)
 
     def theil_sen(self, y):
-        """DSP::TheilSenEstimator over rows of 432 phase values (decode.cc:488): y [n, 432] -> (slope [n], yint [n]).
-        The device works on groups of 50 rows (one window); the input is padded to a multiple of 50."""
+        """DSP::TheilSenEstimator over rows of phase values at x = i - cols/2 (decode.cc:452,484,488):
+        y [n, cols], cols <= 512 -> (slope [n], yint [n])."""
         y = np.ascontiguousarray(y, np.float32)
-        n = y.shape[0]
-        assert y.ndim == 2 and y.shape[1] == 432
-        m = -(-n // 50) * 50
-        yp = np.zeros((m, 432), np.float32)
-        yp[:n] = y
-        out = np.zeros((m, 3), np.float32)
-        _check(self._lib.ofdmrx_theil_sen(self._h, yp.ctypes.data, m, out.ctypes.data), "ofdmrx_theil_sen")
-        self.last_sweeps = out[:n, 2].astype(int)   # pair sweeps per row (>= 100: the bisection fallback ran)
-        return out[:n, 0].copy(), out[:n, 1].copy()
+        assert y.ndim == 2
+        n, cols = y.shape
+        out = np.zeros((n, 3), np.float32)
+        _check(self._lib.ofdmrx_theil_sen(self._h, y.ctypes.data, n, cols, out.ctypes.data), "ofdmrx_theil_sen")
+        self.last_sweeps = out[:, 2].astype(int)   # pair sweeps per row (>= 100: the bisection fallback ran)
+        return out[:, 0].copy(), out[:, 1].copy()
 
-    def taps(self, stage, first=0, count=1):
+    def taps(self, stage, first=0, count=1, mode=6):
         per = int(self._lib.ofdmrx_tap_elems(self._h, stage))
         out = np.empty((count, per), _TAP_DTYPE[stage])
         _check(self._lib.ofdmrx_get_taps(self._h, stage, first, count, out.ctypes.data, out.nbytes), "ofdmrx_get_taps")
         if stage in (TAP_CONS_RAW, TAP_CONS, TAP_PHASE):
-            return out.reshape(count, 50, 432)
+            rows, cols = MODE_GEOMETRY[mode]   # rows x cols values at the front of the window's 32400 slots
+            return out[:, :rows * cols].reshape(count, rows, cols)
         if stage == TAP_TS:
-            return out.reshape(count, 50, 3)
+            return out.reshape(count, 126, 3)[:, :MODE_GEOMETRY[mode][0]]
         return out
 
     def table(self, which):
-        n = self._lib.ofdmrx_get_table(self._h, which, None, 0) if False else (2048 if which == 0 else 16384)
+        n = 2048 if which in (0, 2) else 16384   # 0/2: frozen sets of modes 6..9 / 10..13, 1/3: their SCL schedules
         buf = np.zeros(n, np.uint32)
         got = self._lib.ofdmrx_get_table(self._h, which, buf.ctypes.data, buf.nbytes)
         if got < 0:

@@ -399,7 +399,6 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 			if (!crc_ok) status = ST_HDR_CRC;
 			else if (r_mode < 6 || r_mode > 13) status = ST_BAD_MODE;
 			else if ((r_md >> 8) == 0ull || (long long)(r_md >> 8) >= kCallSignLimit) status = ST_BAD_CALL;
-			else if (r_mode != 6) status = ST_UNSUPPORTED_MODE; // modes 7..13: SURVEY.md §8(f3), not built yet
 			else good = true;
 		}
 		okay = good;
@@ -423,27 +422,33 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 
 __global__ void k_compact(const FrameState *st, int n_frames, int *cw_list, int *n_cw)
 {
-	// single CTA: ordered compaction of header-ok frames (keeps frame order so groups of 4 stay contiguous)
+	// single CTA: ordered compaction of the header-ok frames, code table 0 (modes 6..9) first, then — from the next
+	// multiple of four on — code table 1 (modes 10..13): the list decoder takes four codewords of ONE table per warp
 	__shared__ int base;
 	__shared__ int wsum[32];
-	if (threadIdx.x == 0) base = 0;
-	__syncthreads();
-	for (int f0 = 0; f0 < n_frames; f0 += blockDim.x) {
-		const int f = f0 + threadIdx.x;
-		const int ok = f < n_frames && st[f].status == ST_OK;
-		const unsigned bal = __ballot_sync(FULL, ok);
-		const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-		if (lane == 0) wsum[wid] = __popc(bal);
+	for (int tb = 0; tb < 2; ++tb) {
 		__syncthreads();
-		int off = base;
-		for (int w = 0; w < wid; ++w) off += wsum[w];
-		if (ok) cw_list[off + __popc(bal & ((1u << lane) - 1u))] = f;
+		if (threadIdx.x == 0) base = tb ? (n_cw[0] + 3) & ~3 : 0;
 		__syncthreads();
-		if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w]; base += t; }
-		__syncthreads();
+		const int first = base;
+		for (int f0 = 0; f0 < n_frames; f0 += blockDim.x) {
+			const int f = f0 + threadIdx.x;
+			const int ok = f < n_frames && st[f].status == ST_OK && mode_info(st[f].mode).table == tb;
+			const unsigned bal = __ballot_sync(FULL, ok);
+			const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+			if (lane == 0) wsum[wid] = __popc(bal);
+			__syncthreads();
+			int off = base;
+			for (int w = 0; w < wid; ++w) off += wsum[w];
+			if (ok) cw_list[off + __popc(bal & ((1u << lane) - 1u))] = f;
+			__syncthreads();
+			if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w]; base += t; }
+			__syncthreads();
+		}
+		if (threadIdx.x == 0) n_cw[tb] = base - first;
 	}
-	if (threadIdx.x == 0) *n_cw = base;
 }
+
 
 } // namespace
 

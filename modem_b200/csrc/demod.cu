@@ -25,15 +25,26 @@ namespace ofdmrx {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int kDmThreads = 448, kDmWarps = kDmThreads / 32;
-constexpr int kCols = kConsCols;           // 432
-constexpr int kPairs = kCols * (kCols - 1) / 2; // 93096
-constexpr int kRankSlope = kPairs / 2;      // element count/2 after nth_element
-constexpr int kRankYint = kCols / 2;
+constexpr int kDmThreads = 512; // >= the widest mode's carrier count (mode 10: 512)
+
+// per-row geometry of the Theil-Sen estimator: n carriers at x = i - n/2 (decode.cc:452,484), ranks as std::nth_element
+// is asked for them (element count/2 of the n(n-1)/2 slopes and of the n intercepts; mode 6: 432 -> 93 096 / 46 548 / 216)
+struct TsDims {
+	int n, half, nblk, pairs, rank_slope, rank_yint;
+	__device__ explicit TsDims(int cols) : n(cols), half(cols / 2), nblk((cols + 31) >> 5), pairs(cols * (cols - 1) / 2),
+		rank_slope(cols * (cols - 1) / 4), rank_yint(cols / 2) {}
+};
 
 __device__ __forceinline__ int f2ord(float v) { const int i = __float_as_int(v); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
+// PhaseShiftKeying<4>::hard + map (psk.hh:72-87)
+__device__ __forceinline__ void psk4_hard_map(cfx c, cfx &m)
+{
+	const float r = 0.70710678118654752440f;
+	m = make_float2(c.x < 0.f ? -r : r, c.y < 0.f ? -r : r);
+}
+// PhaseShiftKeying<8>::hard + map (psk.hh:118-139)
 __device__ __forceinline__ void psk8_hard_map(cfx c, cfx &m)
 {
 	const float cos_pi_8 = 0.92387953251128675613f, sin_pi_8 = 0.38268343236508977173f;
@@ -41,12 +52,17 @@ __device__ __forceinline__ void psk8_hard_map(cfx c, cfx &m)
 	const float re = swap ? sin_pi_8 : cos_pi_8, im = swap ? cos_pi_8 : sin_pi_8;
 	m = make_float2(c.x < 0.f ? -re : re, c.y < 0.f ? -im : im);
 }
+__device__ __forceinline__ void psk_hard_map(cfx c, cfx &m, bool qpsk)
+{
+	if (qpsk) psk4_hard_map(c, m);
+	else psk8_hard_map(c, m);
+}
 
 // ================================================================================================ k_demod_fft
 struct FftShared {
 	cfx buf0[kSymLen];
 	cfx buf1[kSymLen];
-	cfx prev[kCols];
+	cfx prev[kMaxCols];
 };
 
 __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *stv,
@@ -57,9 +73,12 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 	const FrameState &st = stv[f];
 	if (st.status != ST_OK) return;
 	const cfx *a = iq + (size_t)f * iq_stride;
+	const ModeInfo mi = mode_info(st.mode);
+	const int cols = mi.cols;
+	const bool qpsk = mi.mod_bits == 2;
 	const int p0 = st.sc_pos + 2 * kPitch; // pilot body (decode.cc:456-459)
 	const double turns = -(double)st.cfo_rad / 6.283185307179586476925286766559;
-	for (int sym = 0; sym <= kConsRows; ++sym) {
+	for (int sym = 0; sym <= mi.rows; ++sym) {
 		const int w0 = p0 + kPitch * sym;
 		const int n0 = kSymLen + kPitch * sym; // phasor steps since the header symbol (decode.cc:404-405,459-461,468-470)
 		for (int i = tid; i < kSymLen; i += kDmThreads) {
@@ -69,15 +88,15 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 		}
 		__syncthreads();
 		fft_fwd<kSymLen>(s.buf0, s.buf1, tw1280, tid, kDmThreads);
-		if (tid < kCols) {
-			const cfx cur = s.buf1[(tid - kCols / 2 + kSymLen) % kSymLen];
+		if (tid < cols) {
+			const cfx cur = s.buf1[(tid - cols / 2 + kSymLen) % kSymLen];
 			if (sym > 0) {
 				const int row = sym - 1;
 				const cfx c = demod_or_erase(cur, s.prev[tid]);
-				const size_t o = ((size_t)f * kConsRows + row) * kCols + tid;
+				const size_t o = (size_t)f * kMaxCons + row * cols + tid;
 				cons_raw[o] = c;
 				cfx m;
-				psk8_hard_map(c, m);
+				psk_hard_map(c, m, qpsk);
 				const cfx e = cmulc(c, m);
 				yph[o] = atan2f(e.y, e.x); // decode.cc:483-486
 			}
@@ -91,8 +110,8 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 constexpr int kTsWarps = 4;            // rows in flight per CTA (one per warp)
 constexpr int kTsCap = 2048;           // in-bracket pairs a warp can queue ...
 constexpr int kTsLaneCap = kTsCap / 32; // ... as 32 private sub-queues
-constexpr int kTsPad = 448;            // 14 x 32 columns, the tail holds +inf
-constexpr int kTsRows = kTsPad / 32;   // 14 row blocks: lane L owns carriers i = 32 R + L
+constexpr int kTsPad = kMaxCols;       // 16 x 32 columns, the tail beyond the mode's carrier count holds +inf
+constexpr int kTsRows = kTsPad / 32;   // up to 16 row blocks: lane L owns carriers i = 32 R + L
 
 constexpr int kTsCandCap = 1536;       // in-bracket quotients kept for the final select
 
@@ -169,24 +188,24 @@ __device__ __noinline__ int warp_select_kth(const int *v, int n, int k, int *his
 // v_j < c_i needs u_j < c_i + w x_j <= c_i + w x_max(chunk), w = bhi - blo >= 0, which bounds the scan.  The chunk
 // holding i itself only counts columns j > i: the prefix sets pm[] turn that into one popcount.
 // Lane L owns the rows i = 32 R + L; in-bracket pairs go to the lane's private sub-queue s.q[32 n + L].
-__device__ __forceinline__ void ts_sort_chunks(TsShared &s, int lane, float blo, float bhi)
+__device__ __forceinline__ void ts_sort_chunks(TsShared &s, const TsDims &d, int lane, float blo, float bhi)
 {
 	const float inf = __int_as_float(0x7f800000);
 #pragma unroll 1
-	for (int K = 0; K < kTsRows; ++K) {
+	for (int K = 0; K < d.nblk; ++K) {
 		const int j = 32 * K + lane;
-		const float yj = s.y[j], x = (float)(j - kCols / 2);
-		float key = j < kCols ? fmaf(-blo, x, yj) : inf;
-		const float v = j < kCols ? fmaf(-bhi, x, yj) : inf;
+		const float yj = s.y[j], x = (float)(j - d.half);
+		float key = j < d.n ? fmaf(-blo, x, yj) : inf;
+		const float v = j < d.n ? fmaf(-bhi, x, yj) : inf;
 		int idx = lane;
 		// bitonic sort of (key, idx) across the warp, ascending
 #pragma unroll
 		for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-			for (int d = k >> 1; d > 0; d >>= 1) {
-				const float ok = __shfl_xor_sync(FULL, key, d);
-				const int oi = __shfl_xor_sync(FULL, idx, d);
-				const bool keep_min = ((lane & d) == 0) == ((lane & k) == 0);
+			for (int dd = k >> 1; dd > 0; dd >>= 1) {
+				const float ok = __shfl_xor_sync(FULL, key, dd);
+				const int oi = __shfl_xor_sync(FULL, idx, dd);
+				const bool keep_min = ((lane & dd) == 0) == ((lane & k) == 0);
 				const bool other_less = ok < key || (ok == key && oi < idx);
 				if (keep_min == other_less) { key = ok; idx = oi; }
 			}
@@ -196,7 +215,7 @@ __device__ __forceinline__ void ts_sort_chunks(TsShared &s, int lane, float blo,
 		s.sw.sj[j] = (uint16_t)(32 * K + idx);
 		uint32_t m = 1u << idx; // inclusive prefix union over the sorted order
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL, m, d); if (lane >= d) m |= o; }
+		for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULL, m, dd); if (lane >= dd) m |= o; }
 		s.sw.pm[33 * K + lane + 1] = m;
 		if (lane == 0) s.sw.pm[33 * K] = 0u;
 	}
@@ -215,25 +234,25 @@ __device__ __forceinline__ int ts_lower_bound(const float2 *chunk, float a)
 
 // all pairs: returns this lane's count of pairs definitely below the bracket; nq = pairs this lane queued
 // (searching several chunks at once for more loads in flight was tried and measured slower)
-__device__ __forceinline__ int sweep_pairs(TsShared &s, int lane, float blo, float bhi, float eps, int &nq)
+__device__ __forceinline__ int sweep_pairs(TsShared &s, const TsDims &d, int lane, float blo, float bhi, float eps, int &nq)
 {
 	const float ninf = __int_as_float(0xff800000);
 	const float w = bhi - blo;
 	const uint32_t above = lane == 31 ? 0u : 0xfffffffeu << lane; // column offsets beyond the lane's own
 	int cb = 0;
 #pragma unroll 1
-	for (int R = 0; R < kTsRows; ++R) {
+	for (int R = 0; R < d.nblk; ++R) {
 		const int i = 32 * R + lane;
-		const float yi = s.y[i], x = (float)(i - kCols / 2);
-		const float a = i < kCols ? fmaf(-blo, x, yi) - eps : ninf;
-		const float c = i < kCols ? fmaf(-bhi, x, yi) + eps : ninf;
+		const float yi = s.y[i], x = (float)(i - d.half);
+		const float a = i < d.n ? fmaf(-blo, x, yi) - eps : ninf;
+		const float c = i < d.n ? fmaf(-bhi, x, yi) + eps : ninf;
 #pragma unroll 1
-		for (int K = R; K < kTsRows; ++K) {
+		for (int K = R; K < d.nblk; ++K) {
 			const float2 *chunk = s.sw.suv + 32 * K;
 			int p = ts_lower_bound(chunk, a);
 			cb += K == R ? __popc(s.sw.pm[33 * K + p] & above) : p;
 			// in-bracket candidates: sorted entries from p on while u < c + w x_max(K) (+ eps for the roundings of u and v)
-			const float t = c + fmaf(w, (float)(32 * K + 31 - kCols / 2), eps);
+			const float t = c + fmaf(w, (float)(32 * K + 31 - d.half), eps);
 			while (p < 32) {
 				const float2 e = chunk[p];
 				if (!(e.x < t)) break;
@@ -251,25 +270,25 @@ __device__ __forceinline__ int sweep_pairs(TsShared &s, int lane, float blo, flo
 
 // fallback for rows that defeat the bracket search: smallest value T with #(quotient <= T) > rank, by a binary
 // search over the ordered-int image of the floats with an exact count (one IEEE division per pair) per step.
-__device__ __noinline__ float ts_slope_bisect(const float *y, int lane)
+__device__ __noinline__ float ts_slope_bisect(const float *y, int n, int rank, int lane)
 {
 	int lo = (int)0x80000000, hi = 0x7fffffff; // answer in [lo, hi]
 	while (lo < hi) {
 		const int mid = (int)(((long long)lo + (long long)hi) >> 1);
 		const float t = ord2f(mid);
 		int cnt = 0;
-		for (int i = 0; i < kCols - 1; ++i) {
+		for (int i = 0; i < n - 1; ++i) {
 			const float yi = y[i];
-			for (int j = i + 1 + lane; j < kCols; j += 32) cnt += __fdiv_rn(y[j] - yi, (float)(j - i)) <= t;
+			for (int j = i + 1 + lane; j < n; j += 32) cnt += __fdiv_rn(y[j] - yi, (float)(j - i)) <= t;
 		}
 		cnt = __reduce_add_sync(FULL, cnt);
-		if (cnt > kRankSlope) hi = mid; else lo = mid + 1;
+		if (cnt > rank) hi = mid; else lo = mid + 1;
 	}
 	return ord2f(lo);
 }
 
 // exact upper median of the pairwise slopes of (x = i - 216, y[i]); one warp, y in s.y (tail padded)
-__device__ float ts_slope(TsShared &s, int lane, int &sweeps)
+__device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps)
 {
 	// ---- pilot: least-squares line and residual spread (only steers the bracket, so fp32 sums are good enough)
 	float yv[kTsRows];
@@ -278,38 +297,41 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 #pragma unroll
 	for (int r = 0; r < kTsRows; ++r) {
 		const int i = 32 * r + lane;
-		const bool ok = i < kCols;
+		const bool ok = i < d.n;
 		yv[r] = ok ? s.y[i] : 0.f;
 		if (ok) {
 			a0 += yv[r];
-			a1 = fmaf((float)(i - kCols / 2) + 0.5f, yv[r], a1);
+			a1 = fmaf((float)(i - d.half) + 0.5f, yv[r], a1);
 			ymin = fminf(ymin, yv[r]);
 			ymax = fmaxf(ymax, yv[r]);
 		}
 	}
 #pragma unroll
-	for (int d = 16; d; d >>= 1) {
-		a0 += __shfl_xor_sync(FULL, a0, d);
-		a1 += __shfl_xor_sync(FULL, a1, d);
-		ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, d));
-		ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, d));
+	for (int dd = 16; dd; dd >>= 1) {
+		a0 += __shfl_xor_sync(FULL, a0, dd);
+		a1 += __shfl_xor_sync(FULL, a1, dd);
+		ymin = fminf(ymin, __shfl_xor_sync(FULL, ymin, dd));
+		ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, dd));
 	}
 	if (ymin == ymax) return 0.f; // erased row: every difference is 0, every quotient +0
-	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(s.y, lane); // non-finite input: stay total
-	const float sxx = (float)((double)kCols * ((double)kCols * kCols - 1.0) / 12.0);
-	const float c0 = a1 / sxx, mean = a0 / (float)kCols;
+	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(s.y, d.n, d.rank_slope, lane); // non-finite input: stay total
+	const float sxx = (float)d.n * ((float)d.n * (float)d.n - 1.f) / 12.f;
+	const float c0 = a1 / sxx, mean = a0 / (float)d.n;
 	float r2 = 0.f;
 #pragma unroll
 	for (int r = 0; r < kTsRows; ++r) {
 		const int i = 32 * r + lane;
-		if (i < kCols) {
-			const float e = yv[r] - mean - c0 * ((float)(i - kCols / 2) + 0.5f);
+		if (i < d.n) {
+			const float e = yv[r] - mean - c0 * ((float)(i - d.half) + 0.5f);
 			r2 = fmaf(e, e, r2);
 		}
 	}
 #pragma unroll
-	for (int d = 16; d; d >>= 1) r2 += __shfl_xor_sync(FULL, r2, d);
-	const float sigma = sqrtf(r2 / (float)(kCols - 2));
+	for (int dd = 16; dd; dd >>= 1) r2 += __shfl_xor_sync(FULL, r2, dd);
+	// residual spread, rescaled so that the bracket below (sized for 432 carriers) keeps its width in units of the
+	// standard deviation of (Theil-Sen - OLS), which goes like sigma / n^1.5
+	const float scale = 432.f / (float)d.n;
+	const float sigma = sqrtf(r2 / (float)(d.n - 2)) * scale * sqrtf(scale);
 	const float yabs = fmaxf(fabsf(ymin), fabsf(ymax));
 	// The Theil–Sen median differs from the OLS slope by about 0.84e-4 sigma (its efficiency relative to OLS is 0.955);
 	// +-1.35e-4 sigma holds rank 46 548 in ~90 % of the rows and ~1000 of the 93 096 quotients (~32 per lane's sub-queue).
@@ -318,16 +340,16 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 	// enclosure of the answer established so far: #(q < L) = cL <= rank < cU = #(q < U)  (exact counts; +-inf = unknown)
 	const float inf = __int_as_float(0x7f800000);
 	float L = -inf, U = inf;
-	int cL = 0, cU = kPairs;
+	int cL = 0, cU = d.pairs;
 	for (int attempt = 0; attempt < 16; ++attempt) {
 		++sweeps;
 		const float bmax = fmaxf(fabsf(blo), fabsf(bhi));
 		// |u_k| rounding (fma, <= 2^-24 |u|) on both sides plus the two roundings of the reference's quotient
 		const float eps = 6e-7f * (yabs + 432.f * bmax) + 1e-30f;
 		__syncwarp();
-		ts_sort_chunks(s, lane, blo, bhi);
+		ts_sort_chunks(s, d, lane, blo, bhi);
 		int nql = 0; // pairs this lane queued
-		int cb = sweep_pairs(s, lane, blo, bhi, eps, nql);
+		int cb = sweep_pairs(s, d, lane, blo, bhi, eps, nql);
 		__syncwarp();
 		const int nq = __reduce_add_sync(FULL, nql), nqmax = __reduce_max_sync(FULL, nql);
 		const float width = bhi - blo;
@@ -335,7 +357,7 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 			// more in-bracket pairs than a sub-queue holds.  The definite counts are still complete: cd pairs lie below blo
 			// for certain and at most cd + nq lie below bhi, which tells where inside the bracket the rank sits.
 			const int cd = __reduce_add_sync(FULL, cb);
-			const int kd = kRankSlope - cd;
+			const int kd = d.rank_slope - cd;
 			if (kd < 0) { U = blo; cU = cd; }
 			else if (kd >= nq) { L = bhi; cL = cd + nq; }
 			else {
@@ -367,7 +389,7 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 			}
 			cb = __reduce_add_sync(FULL, cb);
 			__syncwarp();
-			const int kk = kRankSlope - cb;
+			const int kk = d.rank_slope - cb;
 			if (kk >= 0 && kk < nin) {
 				if (nin <= kTsCandCap) return ord2f(warp_select_kth(s.cand, nin, kk, s.hist, lane));
 				// the rank is inside but the bracket holds more quotients than the select scratch: zoom in (counts are exact)
@@ -396,7 +418,7 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 		if (L > -inf && U < inf) {
 			const float span = U - L;
 			const float dens = (float)max(cU - cL, 1);
-			const float centre = L + span * (((float)(kRankSlope - cL) + 0.5f) / dens);
+			const float centre = L + span * (((float)(d.rank_slope - cL) + 0.5f) / dens);
 			const float hw = fmaxf(span * ((float)kTsCap / (8.f * dens)), 0.25f * half);
 			blo = fmaxf(centre - hw, L);
 			bhi = fminf(centre + hw, U);
@@ -405,38 +427,47 @@ __device__ float ts_slope(TsShared &s, int lane, int &sweeps)
 		if (!(blo < bhi)) break;
 	}
 	sweeps += 100;
-	return ts_slope_bisect(s.y, lane);
+	return ts_slope_bisect(s.y, d.n, d.rank_slope, lane);
 }
 
-__global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, const FrameState *stv, int n_frames, float *ts_out)
+// Rows: with a status array, window f owns the rows f * kMaxRows + r, r < rows(mode), of cols(mode) phase values at
+// yph + f * kMaxCons + r * cols; without one (test hook) n_rows dense rows of fixed_cols values.
+__global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, const FrameState *stv, int n_rows, int fixed_cols, float *ts_out)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	TsShared &s = reinterpret_cast<TsShared *>(smraw)[wid];
-	const int n_rows = n_frames * kConsRows;
 	for (int row = blockIdx.x * kTsWarps + wid; row < n_rows; row += gridDim.x * kTsWarps) {
-		const int f = row / kConsRows;
-		if (stv && stv[f].status != ST_OK) continue;
-		const float *y = yph + (size_t)row * kCols;
+		int cols = fixed_cols;
+		const float *y = yph + (size_t)row * fixed_cols;
+		if (stv) {
+			const int f = row / kMaxRows, r = row - f * kMaxRows;
+			if (stv[f].status != ST_OK) continue;
+			const ModeInfo mi = mode_info(stv[f].mode);
+			if (r >= mi.rows) continue;
+			cols = mi.cols;
+			y = yph + (size_t)f * kMaxCons + r * cols;
+		}
+		const TsDims d(cols);
 		__syncwarp();
 #pragma unroll
 		for (int r = 0; r < kTsRows; ++r) {
 			const int i = 32 * r + lane;
-			s.y[i] = i < kCols ? y[i] : __int_as_float(0x7f800000);
+			s.y[i] = i < d.n ? y[i] : __int_as_float(0x7f800000);
 		}
 		__syncwarp();
 		int sweeps = 0;
-		const float slope = ts_slope(s, lane, sweeps);
+		const float slope = ts_slope(s, d, lane, sweeps);
 		// intercept: upper median of y_i - slope * x_i
 		__syncwarp();
 		int *z = s.cand;
 #pragma unroll
 		for (int r = 0; r < kTsRows; ++r) {
 			const int i = 32 * r + lane;
-			if (i < kCols) z[i] = f2ord(__fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - kCols / 2))));
+			if (i < d.n) z[i] = f2ord(__fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - d.half))));
 		}
 		__syncwarp();
-		const float yint = ord2f(warp_select_kth(z, kCols, kRankYint, s.hist, lane));
+		const float yint = ord2f(warp_select_kth(z, d.n, d.rank_yint, s.hist, lane));
 		if (lane == 0) {
 			ts_out[(size_t)row * 3 + 0] = slope;
 			ts_out[(size_t)row * 3 + 1] = yint;
@@ -448,9 +479,9 @@ __global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, c
 // ================================================================================================ k_soft_demap
 constexpr int kSdThreads = 512, kSdWarps = kSdThreads / 32;
 
-__device__ __forceinline__ cfx derotate(cfx c, float slope, float yint, int col)
+__device__ __forceinline__ cfx derotate(cfx c, float slope, float yint, int x)
 {
-	const float th = -__fadd_rn(yint, __fmul_rn(slope, (float)(col - kCols / 2))); // decode.cc:493-494
+	const float th = -__fadd_rn(yint, __fmul_rn(slope, (float)x)); // decode.cc:493-494, x = i + code_off
 	float sn, cs;
 	sincosf(th, &sn, &cs);
 	return cmul(c, make_float2(cs, sn));
@@ -458,23 +489,26 @@ __device__ __forceinline__ cfx derotate(cfx c, float slope, float yint, int col)
 
 __global__ void __launch_bounds__(kSdThreads) k_soft_demap(const cfx *cons_raw, const FrameState *stv, float *ts, cfx *cons_out, float *llr)
 {
-	__shared__ float rsp[kConsRows], rnp[kConsRows], prec[kConsRows], rsl[kConsRows], ryi[kConsRows];
+	__shared__ float rsp[kMaxRows], rnp[kMaxRows], prec[kMaxRows], rsl[kMaxRows], ryi[kMaxRows];
 	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	if (stv[f].status != ST_OK) return;
-	const cfx *cr = cons_raw + (size_t)f * kConsCnt;
+	const ModeInfo mi = mode_info(stv[f].mode);
+	const int cols = mi.cols, rows = mi.rows, half = cols / 2;
+	const bool qpsk = mi.mod_bits == 2;
+	const cfx *cr = cons_raw + (size_t)f * kMaxCons;
 	float *code = llr + (size_t)f * kCodeLen;
-	float *tsf = ts + (size_t)f * kConsRows * 3;
-	if (tid < kConsRows) { rsl[tid] = tsf[3 * tid]; ryi[tid] = tsf[3 * tid + 1]; }
+	float *tsf = ts + (size_t)f * kMaxRows * 3;
+	if (tid < rows) { rsl[tid] = tsf[3 * tid]; ryi[tid] = tsf[3 * tid + 1]; }
 	__syncthreads();
 	// pass 1: signal and noise power of every row after derotation (decode.cc:507-516)
-	for (int row = wid; row < kConsRows; row += kSdWarps) {
+	for (int row = wid; row < rows; row += kSdWarps) {
 		const float slope = rsl[row], yint = ryi[row];
 		float lsp = 0.f, lnp = 0.f;
-		for (int i = lane; i < kCols; i += 32) {
-			const cfx c = derotate(cr[row * kCols + i], slope, yint, i);
-			if (cons_out) cons_out[(size_t)f * kConsCnt + row * kCols + i] = c;
+		for (int i = lane; i < cols; i += 32) {
+			const cfx c = derotate(cr[row * cols + i], slope, yint, i - half);
+			if (cons_out) cons_out[(size_t)f * kMaxCons + row * cols + i] = c;
 			cfx m;
-			psk8_hard_map(c, m);
+			psk_hard_map(c, m, qpsk);
 			lsp += cnorm(m);
 			lnp += cnorm(csub(c, m));
 		}
@@ -485,26 +519,33 @@ __global__ void __launch_bounds__(kSdThreads) k_soft_demap(const cfx *cons_raw, 
 	__syncthreads();
 	if (tid == 0) { // cumulative over rows, never reset (decode.cc:507)
 		float sp = 0.f, np = 0.f;
-		for (int row = 0; row < kConsRows; ++row) {
+		for (int row = 0; row < rows; ++row) {
 			sp += rsp[row]; np += rnp[row];
 			prec[row] = sp / np;
 			tsf[3 * row + 2] = prec[row];
 		}
 	}
 	__syncthreads();
-	// pass 2: PhaseShiftKeying<8>::soft with the row's precision (psk.hh:125-130)
-	const float rcp_sqrt_2 = 0.70710678118654752440f, DIST = 2.f * 0.38268343236508977173f;
-	for (int idx = tid; idx < kConsCnt; idx += kSdThreads) {
-		const int row = idx / kCols, i = idx - row * kCols;
-		const cfx c = derotate(cr[idx], rsl[row], ryi[row], i);
-		const float g = DIST * prec[row];
-		float *o = code + 3 * idx;
-		o[0] = (rcp_sqrt_2 * (fabsf(c.x) - fabsf(c.y))) * g;
-		o[1] = c.x * g;
-		o[2] = c.y * g;
+	// pass 2: PhaseShiftKeying<8|4>::soft with the row's precision (psk.hh:125-130, 78-82)
+	const float rcp_sqrt_2 = 0.70710678118654752440f;
+	const float dist = qpsk ? 2.f * rcp_sqrt_2 : 2.f * 0.38268343236508977173f;
+	for (int idx = tid; idx < rows * cols; idx += kSdThreads) {
+		const int row = idx / cols, i = idx - row * cols;
+		const cfx c = derotate(cr[idx], rsl[row], ryi[row], i - half);
+		const float g = dist * prec[row];
+		if (qpsk) {
+			float *o = code + 2 * idx;
+			o[0] = c.x * g;
+			o[1] = c.y * g;
+		} else {
+			float *o = code + 3 * idx;
+			o[0] = (rcp_sqrt_2 * (fabsf(c.x) - fabsf(c.y))) * g;
+			o[1] = c.x * g;
+			o[2] = c.y * g;
+		}
 	}
-	// lengthen(): the 736 trailing indices are non-frozen positions carrying a known +1 (decode.cc:245-253,529)
-	for (int i = kConsBits + tid; i < kCodeLen; i += kSdThreads) code[i] = 9000.f;
+	// lengthen(): the trailing indices are non-frozen positions carrying a known +1 (decode.cc:245-253,529)
+	for (int i = mi.cons_bits + tid; i < kCodeLen; i += kSdThreads) code[i] = 9000.f;
 }
 
 } // namespace
@@ -523,13 +564,13 @@ static int theil_sen_grid(int rows, int n_sm, int *smem)
 	return grid;
 }
 
-// test hook: rows of 432 phase values -> (slope, yint, unused) per row; rows must be a multiple of 50
-cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, float *ts, int n_sm, cudaStream_t s)
+// test hook: n_rows dense rows of `cols` phase values -> (slope, yint, sweeps) per row
+cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float *ts, int n_sm, cudaStream_t s)
 {
 	if (n_rows <= 0) return cudaSuccess;
 	int smem;
 	const int grid = theil_sen_grid(n_rows, n_sm, &smem);
-	k_theil_sen<<<grid, kTsWarps * 32, smem, s>>>(yph, nullptr, n_rows / kConsRows, ts);
+	k_theil_sen<<<grid, kTsWarps * 32, smem, s>>>(yph, nullptr, n_rows, cols, ts);
 	return cudaGetLastError();
 }
 
@@ -539,8 +580,8 @@ cudaError_t launch_demod(const cfx *iq, int64_t iq_stride, int iq_len, const Fra
 	if (n_frames <= 0) return cudaSuccess;
 	k_demod_fft<<<n_frames, kDmThreads, 0, s>>>(iq, iq_stride, iq_len, st, tw1280, cons_raw, yph);
 	int ts_smem;
-	const int grid = theil_sen_grid(n_frames * kConsRows, n_sm, &ts_smem);
-	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames, ts);
+	const int grid = theil_sen_grid(n_frames * kMaxRows, n_sm, &ts_smem);
+	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames * kMaxRows, 0, ts);
 	k_soft_demap<<<n_frames, kSdThreads, 0, s>>>(cons_raw, st, ts, cons, llr);
 	return cudaGetLastError();
 }

@@ -7,6 +7,12 @@
 #pragma once
 #include <cstdint>
 #include <vector>
+#ifndef __CUDACC__
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
+#endif
 
 namespace ofdmrx {
 
@@ -20,6 +26,19 @@ constexpr int kFilterLen = 21;
 constexpr int kConsCols = 432, kConsRows = 50, kModBits = 3, kConsCnt = 21600, kConsBits = 64800;
 constexpr int kCodeOrder = 16, kCodeLen = 65536, kMesgBits = 43808, kDataBits = 43040, kCrcBits = 43072, kDataBytes = 5380;
 constexpr int kHdrBits = 255, kHdrK = 71;
+
+// ---- operation modes 6..13 (decode.cc:302-374): carriers per symbol, bits per carrier, transmitted code bits ----------
+// rows = cons_bits / mod_bits / cols symbols follow the pilot; modes 6..9 use the frozen set of (64800, 43072), modes
+// 10..13 that of (64512, 43072); payload (43040 bits) and CRC span (43072 bits) are the same for all.
+struct ModeInfo { int cols, mod_bits, cons_bits, rows, table; };
+__host__ __device__ constexpr ModeInfo mode_info(int mode)
+{
+	return mode == 6 ? ModeInfo{432, 3, 64800, 50, 0} : mode == 7 ? ModeInfo{400, 3, 64800, 54, 0}
+		: mode == 8 ? ModeInfo{400, 2, 64800, 81, 0} : mode == 9 ? ModeInfo{360, 2, 64800, 90, 0}
+		: mode == 10 ? ModeInfo{512, 3, 64512, 42, 1} : mode == 11 ? ModeInfo{384, 3, 64512, 56, 1}
+		: mode == 12 ? ModeInfo{384, 2, 64512, 84, 1} : mode == 13 ? ModeInfo{256, 2, 64512, 126, 1} : ModeInfo{0, 0, 0, 0, 0};
+}
+constexpr int kMaxCols = 512, kMaxRows = 126, kMaxCons = 32400; // largest carrier count, row count, constellation count
 constexpr long long kCallSignLimit = 129961739795077LL;
 
 // ---- frozen set ---------------------------------------------------------------------------------------------

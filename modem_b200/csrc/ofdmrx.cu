@@ -27,11 +27,12 @@ struct ofdmrx_handle {
 	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0, scl_stream_level = 17;
 	int launches = 0;
 	// constants
-	uint32_t *d_frozen = nullptr, *d_ops = nullptr, *d_msg_off = nullptr, *d_scr = nullptr, *d_bch = nullptr;
+	uint32_t *d_tbl[2] = {}, *d_scr = nullptr, *d_bch = nullptr; // [code table]: frozen set | message offsets | SCL schedule
+	int polar_table = 0; // table used by ofdmrx_polar_decode (option "polar_table")
 	uint8_t *d_mls1 = nullptr;
 	cfx *d_tw1280 = nullptr, *d_tw640 = nullptr, *d_kern = nullptr;
 	FrontendConsts fc;
-	std::vector<uint32_t> h_frozen, h_ops;
+	std::vector<uint32_t> h_frozen[2], h_ops[2];
 	// per-chunk scratch
 	void *d_in = nullptr; size_t in_bytes = 0;
 	int32_t *d_nsamp = nullptr;
@@ -96,7 +97,7 @@ int ensure_scl_scratch(ofdmrx_handle *h)
 
 extern "C" {
 
-const char *ofdmrx_version(void) { return "ofdmrx 0.1 (sm_100a; mode 6 @ 8 kHz; SCL L=8)"; }
+const char *ofdmrx_version(void) { return "ofdmrx 0.2 (sm_100a; modes 6-13 @ 8 kHz; SCL L=8)"; }
 
 int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int max_samples)
 {
@@ -121,20 +122,19 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	h->max_samples = max_samples;
 	h->iq_len = ((max_samples + 1 + 127) / 128) * 128; // stream steps t = 0..n, padded
 	// ---- constant tables
-	h->h_frozen = make_frozen(kCodeOrder, kConsBits, kCrcBits);
-	{
-		int fuse = 2; // F/G chain fusion depth of the SCL schedule (1 = none); OFDMRX_SCL_FUSE overrides for A/B runs
-		if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(kSclMaxFuse, std::atoi(e)));
-		h->scl_stream_level = 11; // alpha levels >= 11 stream through L2 (evict-first), smaller ones are kept (evict-last)
-		if (const char *e = std::getenv("OFDMRX_SCL_STREAM_LEVEL")) h->scl_stream_level = std::atoi(e);
-		bool top = true; // levels 16..14 recomputed from the channel LLRs (OP_TOP); OFDMRX_SCL_TOP=0 stores them instead
-		if (const char *e = std::getenv("OFDMRX_SCL_TOP")) top = std::atoi(e) != 0;
-		h->h_ops = make_scl_schedule(h->h_frozen, kCodeOrder, fuse, top);
-	}
-	std::vector<uint32_t> msg_off(2048);
-	{
+	int fuse = kSclMaxFuse; // F/G chain fusion depth of the SCL schedule (1 = none); OFDMRX_SCL_FUSE overrides for A/B runs
+	if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(kSclMaxFuse, std::atoi(e)));
+	h->scl_stream_level = 11; // alpha levels >= 11 written by the TOP ops stream through L2 (evict-first)
+	if (const char *e = std::getenv("OFDMRX_SCL_STREAM_LEVEL")) h->scl_stream_level = std::atoi(e);
+	bool top = true; // levels 16..14 recomputed from the channel LLRs (OP_TOP); OFDMRX_SCL_TOP=0 stores them instead
+	if (const char *e = std::getenv("OFDMRX_SCL_TOP")) top = std::atoi(e) != 0;
+	std::vector<uint32_t> msg_off[2];
+	for (int tb = 0; tb < 2; ++tb) { // code tables of modes 6..9 and 10..13 (decode.cc:310-311,342-343)
+		h->h_frozen[tb] = make_frozen(kCodeOrder, tb ? 64512 : 64800, kCrcBits);
+		h->h_ops[tb] = make_scl_schedule(h->h_frozen[tb], kCodeOrder, fuse, top);
+		msg_off[tb].resize(2048);
 		uint32_t acc = 0;
-		for (int w = 0; w < 2048; ++w) { msg_off[w] = acc; acc += 32 - __builtin_popcount(h->h_frozen[w]); }
+		for (int w = 0; w < 2048; ++w) { msg_off[tb][w] = acc; acc += 32 - __builtin_popcount(h->h_frozen[tb][w]); }
 	}
 	std::vector<uint32_t> scr(kDataBytes / 4, 0);
 	{
@@ -154,9 +154,12 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	h->fc.reco = reco;
 	for (int i = 0; i < 5; ++i) h->fc.imco[i] = imco[i];
 	int r = 0;
-	if (!r) r = dev_upload(&h->d_frozen, h->h_frozen.data(), 2048);
-	if (!r) r = dev_upload(&h->d_ops, h->h_ops.data(), h->h_ops.size());
-	if (!r) r = dev_upload(&h->d_msg_off, msg_off.data(), 2048);
+	for (int tb = 0; tb < 2; ++tb) {
+		std::vector<uint32_t> tbl(h->h_frozen[tb]);
+		tbl.insert(tbl.end(), msg_off[tb].begin(), msg_off[tb].end());
+		tbl.insert(tbl.end(), h->h_ops[tb].begin(), h->h_ops[tb].end());
+		if (!r) r = dev_upload(&h->d_tbl[tb], tbl.data(), tbl.size());
+	}
 	if (!r) r = dev_upload(&h->d_scr, scr.data(), scr.size());
 	if (!r) r = dev_upload(&h->d_bch, bch.data(), bch.size());
 	if (!r) r = dev_upload(&h->d_mls1, mls1.data(), mls1.size());
@@ -175,11 +178,11 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_st, F);
 	if (!r) r = dev_alloc(&h->d_soft, F * 256);
 	if (!r) r = dev_alloc(&h->d_llr, F * (size_t)kCodeLen);
-	if (!r) r = dev_alloc(&h->d_cons_raw, F * kConsCnt);
-	if (!r) r = dev_alloc(&h->d_y, F * kConsCnt);
-	if (!r) r = dev_alloc(&h->d_ts, F * kConsRows * 3);
-	if (!r) r = dev_alloc(&h->d_cwlist, F);
-	if (!r) r = dev_alloc(&h->d_ncw, (size_t)1);
+	if (!r) r = dev_alloc(&h->d_cons_raw, F * kMaxCons);
+	if (!r) r = dev_alloc(&h->d_y, F * kMaxCons);
+	if (!r) r = dev_alloc(&h->d_ts, F * kMaxRows * 3);
+	if (!r) r = dev_alloc(&h->d_cwlist, F + 4);
+	if (!r) r = dev_alloc(&h->d_ncw, (size_t)2);
 	if (!r) r = dev_alloc(&h->d_payload, F * (size_t)(kDataBytes / 4));
 	for (int i = 0; i < 10 && !r; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) r = -12;
 	for (int i = 0; i < 16 && !r; ++i) if (cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming) != cudaSuccess) r = -12;
@@ -195,7 +198,7 @@ void ofdmrx_destroy(ofdmrx_t *h)
 {
 	if (!h) return;
 	cudaSetDevice(h->device);
-	void *ptrs[] = {h->d_frozen, h->d_ops, h->d_msg_off, h->d_scr, h->d_bch, h->d_mls1, h->d_tw1280, h->d_tw640, h->d_kern, h->d_in,
+	void *ptrs[] = {h->d_tbl[0], h->d_tbl[1], h->d_scr, h->d_bch, h->d_mls1, h->d_tw1280, h->d_tw640, h->d_kern, h->d_in,
 		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr, h->d_y,
 		h->d_cwlist, h->d_ncw, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
@@ -214,8 +217,13 @@ int ofdmrx_set_option(ofdmrx_t *h, const char *key, int value)
 		if (h->keep_taps && !h->d_cons) {
 			cudaSetDevice(h->device);
 			const size_t F = (size_t)h->max_frames;
-			return dev_alloc(&h->d_cons, F * kConsCnt);
+			return dev_alloc(&h->d_cons, F * kMaxCons);
 		}
+		return 0;
+	}
+	if (!std::strcmp(key, "polar_table")) {
+		if (value < 0 || value > 1) return -22;
+		h->polar_table = value;
 		return 0;
 	}
 	if (!std::strcmp(key, "scl_ctas_per_sm")) {
@@ -242,8 +250,10 @@ int ofdmrx_get_table(ofdmrx_t *h, int which, void *dst, size_t bytes)
 {
 	if (!h || !dst) return -22;
 	cudaSetDevice(h->device);
-	const void *src = which == 0 ? (const void *)h->d_frozen : (const void *)h->d_ops;
-	const size_t have = which == 0 ? 2048 * 4 : h->h_ops.size() * 4;
+	if (which < 0 || which > 3) return -22;
+	const int tb = which >> 1;
+	const void *src = (which & 1) == 0 ? (const void *)h->d_tbl[tb] : (const void *)(h->d_tbl[tb] + kSclTblOps);
+	const size_t have = (which & 1) == 0 ? 2048 * 4 : h->h_ops[tb].size() * 4;
 	if (bytes > have) bytes = have;
 	OFDMRX_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
 	return (int)(have / 4);
@@ -268,8 +278,8 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 	OFDMRX_CUDA_TRY(launch_acquire(iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
 		h->d_soft + (size_t)f0 * 256, ac, s));
 	if (record) cudaEventRecord(h->ev[4], s);
-	OFDMRX_CUDA_TRY(launch_demod(iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kConsCnt,
-		h->d_y + (size_t)f0 * kConsCnt, h->keep_taps ? h->d_cons + (size_t)f0 * kConsCnt : nullptr, h->d_ts + (size_t)f0 * kConsRows * 3,
+	OFDMRX_CUDA_TRY(launch_demod(iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kMaxCons,
+		h->d_y + (size_t)f0 * kMaxCons, h->keep_taps ? h->d_cons + (size_t)f0 * kMaxCons : nullptr, h->d_ts + (size_t)f0 * kMaxRows * 3,
 		h->d_llr + (size_t)f0 * kCodeLen, h->n_sm, s));
 	if (record) cudaEventRecord(h->ev[5], s);
 	h->launches += 7;
@@ -284,8 +294,9 @@ static int run_scl(ofdmrx_handle *h, int nf, cudaStream_t s)
 	if (int r = ensure_scl_scratch(h)) return r;
 	cudaEventRecord(h->ev[6], s);
 	SclParams p{};
-	p.llr = h->d_llr; p.cw_list = h->d_cwlist; p.n_cw = 0; p.n_cw_ptr = h->d_ncw; p.A = h->d_A; p.B = h->d_B;
-	p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr; p.stream_level = h->scl_stream_level;
+	p.llr = h->d_llr; p.cw_list = h->d_cwlist; p.n_cw_ptr = h->d_ncw; p.A = h->d_A; p.B = h->d_B;
+	p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1];
+	p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr; p.stream_level = h->scl_stream_level;
 	OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
 	cudaEventRecord(h->ev[7], s);
 	h->ev_valid = true;
@@ -368,8 +379,10 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
 			h->xbits_frames = nf;
 		}
 		SclParams p{};
-		p.llr = h->d_llr; p.cw_list = nullptr; p.n_cw = nf; p.n_cw_ptr = nullptr; p.A = h->d_A; p.B = h->d_B;
-		p.ops = h->d_ops; p.frozen = h->d_frozen; p.msg_off = h->d_msg_off; p.payload = h->d_payload; p.st = h->d_st;
+		p.llr = h->d_llr; p.cw_list = nullptr; p.n_cw_ptr = nullptr; p.A = h->d_A; p.B = h->d_B;
+		p.n_cw[h->polar_table] = nf; p.n_cw[1 - h->polar_table] = 0;
+		p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1];
+		p.payload = h->d_payload; p.st = h->d_st;
 		p.xbits = xbits ? h->d_xbits : nullptr;
 		p.stream_level = h->scl_stream_level;
 		OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
@@ -382,15 +395,15 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
 	return 0;
 }
 
-int ofdmrx_theil_sen(ofdmrx_t *h, const float *y, int n_rows, float *out3)
+int ofdmrx_theil_sen(ofdmrx_t *h, const float *y, int n_rows, int cols, float *out3)
 {
-	if (!h || !y || !out3 || n_rows < 0 || n_rows % kConsRows) return -22;
-	if (n_rows > h->max_frames * kConsRows) return -27;
+	if (!h || !y || !out3 || n_rows < 0 || cols < 8 || cols > kMaxCols) return -22;
+	if ((size_t)n_rows * cols > (size_t)h->max_frames * kMaxCons || n_rows > h->max_frames * kMaxRows) return -27;
 	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
 	cudaStream_t s = nullptr;
-	OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_y, y, (size_t)n_rows * kConsCols * 4, cudaMemcpyHostToDevice, s));
+	OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_y, y, (size_t)n_rows * cols * 4, cudaMemcpyHostToDevice, s));
 	OFDMRX_CUDA_TRY(cudaMemsetAsync(h->d_ts, 0, (size_t)n_rows * 3 * 4, s));
-	OFDMRX_CUDA_TRY(launch_theil_sen_rows(h->d_y, n_rows, h->d_ts, h->n_sm, s));
+	OFDMRX_CUDA_TRY(launch_theil_sen_rows(h->d_y, n_rows, cols, h->d_ts, h->n_sm, s));
 	OFDMRX_CUDA_TRY(cudaMemcpyAsync(out3, h->d_ts, (size_t)n_rows * 3 * 4, cudaMemcpyDeviceToHost, s));
 	OFDMRX_CUDA_TRY(cudaStreamSynchronize(s));
 	h->launches = 1;
@@ -403,10 +416,10 @@ int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage)
 	switch (stage) {
 	case OFDMRX_TAP_IQ: case OFDMRX_TAP_TIMING: return h->iq_len;
 	case OFDMRX_TAP_SOFT: return 256;
-	case OFDMRX_TAP_CONS_RAW: case OFDMRX_TAP_CONS: return kConsCnt;
-	case OFDMRX_TAP_TS: return kConsRows * 3;
+	case OFDMRX_TAP_CONS_RAW: case OFDMRX_TAP_CONS: return kMaxCons;
+	case OFDMRX_TAP_TS: return kMaxRows * 3;
 	case OFDMRX_TAP_LLR: return kCodeLen;
-	case OFDMRX_TAP_PHASE: return kConsCnt;
+	case OFDMRX_TAP_PHASE: return kMaxCons;
 	}
 	return -22;
 }

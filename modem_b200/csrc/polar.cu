@@ -401,11 +401,19 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 	float4 *S = scl_smem;
 	c.A5 = lvl_ptr(A, S, 5);
 
-	const int n_cw = p.n_cw_ptr ? *p.n_cw_ptr : p.n_cw;
-	for (int g4 = warp_global; g4 * 4 < n_cw; g4 += n_warps) {
-		const int slot = g4 * 4 + (lane32 >> 3);
+	// groups of four codewords never mix code tables (the four walk one schedule in lock step): table 0's groups first
+	const int n0 = p.n_cw_ptr ? p.n_cw_ptr[0] : p.n_cw[0], n1 = p.n_cw_ptr ? p.n_cw_ptr[1] : p.n_cw[1];
+	const int g0 = (n0 + 3) >> 2, g1 = (n1 + 3) >> 2;
+	for (int g4 = warp_global; g4 < g0 + g1; g4 += n_warps) {
+		const int tb = g4 < g0 ? 0 : 1;
+		const int first = tb ? 4 * g0 : 0, n_cw = tb ? n1 : n0; // table 1's list starts at the next multiple of 4
+		const int slot = (g4 - (tb ? g0 : 0)) * 4 + (lane32 >> 3);
 		const bool active = slot < n_cw;
-		const int frame = p.cw_list ? p.cw_list[active ? slot : n_cw - 1] : (active ? slot : n_cw - 1);
+		const int pos = first + (active ? slot : n_cw - 1);
+		const int frame = p.cw_list ? p.cw_list[pos] : pos;
+		// (a ternary, not p.tbl[tb]: a run-time index into the kernel parameters makes the compiler copy them to local memory)
+		const uint32_t *frozen = tb ? p.tbl[1] : p.tbl[0];
+		const uint32_t *ops = frozen + kSclTblOps;
 		const float *C = p.llr + (size_t)frame * kCodeLen;
 		const float4 *C4 = reinterpret_cast<const float4 *>(C);
 		c.metric = c.t == 0 ? 0.f : 1000.f;
@@ -413,7 +421,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 		uint64_t lmstack = 0;
 
 		for (int pc = 0;; ++pc) {
-			const uint32_t opw = __ldg(&p.ops[pc]);
+			const uint32_t opw = __ldg(&ops[pc]);
 			const uint32_t op = opw & 7u, l = (opw >> 3) & 31u, iw = (opw >> 8) & 0x3fffffu; // iw = first word of the node
 			if (op == OP_END) break;
 			const int hq = 1 << (l - 3);               // quads per half node
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 				top_op<2>(A, C4, B, j, s15, s14, lane32, p.stream_level); // always chained with the F step below (host_tables.cc)
 				__syncwarp();
 			} else if (op == OP_WORD) {
-				c.fmask = __ldg(&p.frozen[iw]);
+				c.fmask = __ldg(&frozen[iw]);
 				word32(c);
 				B[(size_t)iw * 32 + lane32] = c.W;
 				__syncwarp();
@@ -500,7 +508,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 			int cnt = 0;
 			for (int w = 0; w < kCodeLen / 32 && cnt < kCrcBits; ++w) {
 				const uint32_t x = B[(size_t)w * 32 + lane32];
-				uint32_t fr = ~__ldg(&p.frozen[w]);
+				uint32_t fr = ~__ldg(&frozen[w]);
 				while (fr && cnt < kCrcBits) {
 					const int b = __ffs(fr) - 1;
 					fr &= fr - 1;
@@ -522,14 +530,14 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 			st.metrics[rank] = c.metric;
 			if (p.xbits)
 				for (int w = 0; w < kCodeLen / 32; ++w)
-					p.xbits[((size_t)slot * 8 + rank) * (kCodeLen / 32) + w] = B[(size_t)w * 32 + lane32];
+					p.xbits[((size_t)(first + slot) * 8 + rank) * (kCodeLen / 32) + w] = B[(size_t)w * 32 + lane32];
 			if (win >= 0) {
 				uint32_t *out = p.payload + (size_t)frame * (kDataBytes / 4);
 				for (int w = c.t; w < kCodeLen / 32; w += 8) {
-					const int base = (int)__ldg(&p.msg_off[w]);
+					const int base = (int)__ldg(&frozen[kSclTblMsgOff + w]);
 					if (base >= kDataBits) break;
 					const uint32_t x = B[(size_t)w * 32 + c.gbase + win];
-					uint32_t fr = ~__ldg(&p.frozen[w]);
+					uint32_t fr = ~__ldg(&frozen[w]);
 					uint64_t m = 0;
 					int k = 0;
 					while (fr && base + k < kDataBits) {
@@ -580,7 +588,7 @@ cudaError_t launch_payload_init(uint32_t *payload, const uint32_t *scr_words, in
 
 cudaError_t launch_polar_scl(const SclParams &p, int grid, cudaStream_t s)
 {
-	if (!p.n_cw_ptr && p.n_cw <= 0) return cudaSuccess;
+	if (!p.n_cw_ptr && p.n_cw[0] + p.n_cw[1] <= 0) return cudaSuccess;
 	k_polar_scl<<<grid, kSclThreads, kSclSmemBytes, s>>>(p);
 	return cudaGetLastError();
 }

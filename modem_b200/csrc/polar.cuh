@@ -12,16 +12,18 @@ __host__ __device__ constexpr size_t scl_off(int l) { return (size_t)((1 << l) -
 // same offset in float4 units: level l holds 2^l/4 quads per lane, laid out [quad][warp lane]
 __host__ __device__ constexpr size_t scl_off4(int l) { return (size_t)((1 << l) - 32) * 8; }
 
+constexpr int kSclTblMsgOff = 2048, kSclTblOps = 4096; // word offsets inside SclParams::tbl
+
 struct SclParams {
 	const float *llr;        // [frames][65536] channel LLRs after lengthen() (decode.cc:529)
-	const int *cw_list;      // frames to decode (compacted header-ok list) or nullptr for identity
-	int n_cw;                // number of codewords, or read from n_cw_ptr (device) when that is set
+	const int *cw_list;      // frames to decode: the header-ok frames of code table 0 (modes 6..9), then from the next
+	                         // multiple of 4 on those of table 1 (modes 10..13); nullptr = identity (one table)
+	int n_cw[2];             // codewords per code table, or read from n_cw_ptr (device, 2 ints) when that is set
 	const int *n_cw_ptr;
 	float *A;                // scratch: resident warps x kSclWarpFloats
 	uint32_t *B;             // scratch: resident warps x kSclWarpWords
-	const uint32_t *ops;     // schedule (host_tables.cc)
-	const uint32_t *frozen;  // 2048 words
-	const uint32_t *msg_off; // number of non-frozen indices before word w
+	const uint32_t *tbl[2];  // per code table, one array: frozen set (2048 words), number of non-frozen indices before each
+	                         // word (2048), op schedule (host_tables.cc) — one base pointer keeps the kernel's registers down
 	uint32_t *payload;       // [frames][1345] words pre-filled with the scrambler sequence
 	FrameState *st;
 	int stream_level;        // alpha levels >= this use the L2 evict-first policy (17 = none)

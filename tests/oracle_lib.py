@@ -102,10 +102,19 @@ def encode(payloads, rate=8000, channels=1, freq_off=2000, call_sign=b"CALLSIGN"
     return out[: n * channels].reshape(n, channels) if channels == 2 else out[:n]
 
 
+# payload symbols per mode (decode.cc:302-374): a single-frame stream is 1 s + (5 + rows) symbols + 1 s (encode.cc:288-313,423,441)
+MODE_ROWS = {6: 50, 7: 54, 8: 81, 9: 90, 10: 42, 11: 56, 12: 84, 13: 126}
+
+
+def frame_samples(mode=6, rate=8000):
+    return 2 * rate + (5 + MODE_ROWS[mode]) * (1440 * rate // 8000)
+
+
 def encode_batch(n, seed0=0, rate=8000, channels=1, freq_off=2000, call_sign=b"CALLSIGN", mode=6, imp=None,
-                 stride=FRAME_SAMPLES, nthreads=None):
+                 stride=None, nthreads=None):
     """n single-frame windows of `stride` sample frames; payload i = make_payload(seed0 + i)."""
     nthreads = nthreads or os.cpu_count() or 1
+    stride = stride or frame_samples(mode, rate)
     pcm = np.zeros((n, stride * channels), np.int16)
     ns = np.zeros(n, np.int32)
     pay = np.zeros((n, DATA_BYTES), np.uint8)

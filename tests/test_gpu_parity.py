@@ -27,9 +27,10 @@ def _noisy_llr(oracle, seed, sigma):
 
 def test_device_tables_match_oracle(rx, oracle):
     import ctypes as C
-    fr = np.zeros(2048, np.uint32)
-    oracle.lib().ref_frozen_table(0, fr.ctypes.data_as(C.c_void_p))
-    assert (rx.table(0) == fr).all()
+    for tb in (0, 1):
+        fr = np.zeros(2048, np.uint32)
+        oracle.lib().ref_frozen_table(tb, fr.ctypes.data_as(C.c_void_p))
+        assert (rx.table(2 * tb) == fr).all()
 
 
 def test_polar_list_decoder_bit_exact(rx, oracle):
@@ -77,12 +78,13 @@ def _theil_sen_exact(y):
     """What DSP::TheilSenEstimator computes, restated with numpy fp32 (IEEE) arithmetic: the element of rank count/2 of
     all pairwise quotients (y_j - y_i) / (x_j - x_i), then of y_i - slope * x_i (decode.cc:488; oracle/ref_dsp.hh)."""
     y = np.asarray(y, np.float32)
-    i, j = np.triu_indices(432, 1)
+    n = y.shape[0]
+    i, j = np.triu_indices(n, 1)
     q = ((y[j] - y[i]).astype(np.float32) / (j - i).astype(np.float32)).astype(np.float32)
     slope = np.partition(q, q.size // 2)[q.size // 2]
-    x = (np.arange(432) - 216).astype(np.float32)
+    x = (np.arange(n) - n // 2).astype(np.float32)
     z = (y - (slope * x).astype(np.float32)).astype(np.float32)
-    return slope, np.partition(z, 216)[216]
+    return slope, np.partition(z, n // 2)[n // 2]
 
 
 def test_theil_sen_is_the_exact_order_statistic(rx):
@@ -106,6 +108,15 @@ def test_theil_sen_is_the_exact_order_statistic(rx):
     for k in range(y.shape[0]):
         es, ey = _theil_sen_exact(y[k])
         assert slope[k] == es and yint[k] == ey, (k, slope[k], es, yint[k], ey)
+    # the carrier counts of the other operation modes (decode.cc:313-368) and odd sizes
+    for cols in (512, 400, 384, 360, 256, 33, 8):
+        xc = np.arange(cols) - cols // 2
+        yc = np.stack([np.clip(0.02 + s1 * xc + sg * rng.standard_normal(cols), -np.pi / 4, np.pi / 4)
+                       for sg in (1e-3, 0.05, 0.2) for s1 in (0.0, 2e-4)] + [np.zeros(cols), np.round(rng.standard_normal(cols) * 2) / 8]).astype(np.float32)
+        slope, yint = rx.theil_sen(yc)
+        for k in range(yc.shape[0]):
+            es, ey = _theil_sen_exact(yc[k])
+            assert slope[k] == es and yint[k] == ey, (cols, k, slope[k], es, yint[k], ey)
 
 
 def test_theil_sen_exact_on_pipeline_rows(rx, oracle):
@@ -117,7 +128,7 @@ def test_theil_sen_exact_on_pipeline_rows(rx, oracle):
     assert (st["status"] == 0).all()
     for f in range(3):
         y = rx.taps(M.TAP_PHASE, f, 1)[0]
-        ts = rx.taps(M.TAP_TS, f, 1)[0]
+        ts = rx.taps(M.TAP_TS, f, 1)[0]   # mode 6 geometry
         for row in range(0, 50, 7):
             es, ey = _theil_sen_exact(y[row])
             assert ts[row, 0] == es and ts[row, 1] == ey, (f, row)
@@ -137,15 +148,17 @@ def _compare_frames(rx, oracle, pcm, channels, sent, strict_payload=True):
             assert dsoft.max() <= 1 and (dsoft != 0).sum() <= 4   # rint() of a float that differs in the last ulps
             assert ((int(s["md_hi"]) << 32) | int(s["md_lo"])) == tp.md and s["mode"] == tp.mode
         if ost in (0, 6):
-            assert np.abs(rx.taps(M.TAP_CONS_RAW, i, 1)[0] - oracle.taps_np(tp, "cons_raw")).max() < TOL_CONS
-            assert np.abs(rx.taps(M.TAP_CONS, i, 1)[0] - oracle.taps_np(tp, "cons")).max() < TOL_CONS * 2
-            ts = rx.taps(M.TAP_TS, i, 1)[0]
+            md = int(s["mode"])
+            assert np.abs(rx.taps(M.TAP_CONS_RAW, i, 1, md)[0] - oracle.taps_np(tp, "cons_raw")).max() < TOL_CONS
+            oc = oracle.taps_np(tp, "cons")   # derotated: the phase-line difference acts on |cons| (> 1 under multipath) at |x| <= 256
+            assert (np.abs(rx.taps(M.TAP_CONS, i, 1, md)[0] - oc) / np.maximum(1.0, np.abs(oc))).max() < TOL_CONS * 3
+            ts = rx.taps(M.TAP_TS, i, 1, md)[0]
             osl = oracle.taps_np(tp, "slope")
             assert np.abs(ts[:, 0] - osl).max() <= TOL_SLOPE_REL * np.abs(osl).max() + 1e-7
             assert np.abs(ts[:, 1] - oracle.taps_np(tp, "yint")).max() < TOL_YINT
             assert (np.abs(ts[:, 2] - oracle.taps_np(tp, "precision")) / oracle.taps_np(tp, "precision")).max() < TOL_PRECISION
             ollr = oracle.taps_np(tp, "llr")
-            assert np.abs(rx.taps(M.TAP_LLR, i, 1)[0] - ollr).max() / np.abs(ollr[:64800]).mean() < TOL_LLR
+            assert np.abs(rx.taps(M.TAP_LLR, i, 1)[0] - ollr).max() / np.abs(ollr[:64512]).mean() < TOL_LLR
         if ost == 0:
             assert (payload[i] == opay).all() and (payload[i] == sent[i]).all()
             assert s["best_lane"] == tp.best_lane
@@ -167,6 +180,62 @@ def test_pipeline_impaired_iq_config3(rx, oracle):
     pcm, ns, sent = oracle.encode_batch(16, seed0=2000, channels=2, imp=imp)
     st = _compare_frames(rx, oracle, pcm, 2, sent)
     assert (st["status"] == 0).all()
+
+
+@pytest.mark.parametrize("mode", [7, 8, 9, 10, 11, 12, 13])
+def test_pipeline_other_modes(oracle, mode):
+    """Modes 7..13 (decode.cc:313-368): QPSK and 8PSK on 256..512 carriers, 42..126 rows, both frozen sets — clean mono
+    frames bit-exact with taps in tolerance, and impaired analytic frames decoding to the oracle's bytes."""
+    import modem_b200 as M
+    stride = oracle.frame_samples(mode) + 64   # slack: a negative sampling-frequency offset stretches the stream
+    pcm, ns, sent = oracle.encode_batch(5, seed0=100 * mode, mode=mode, stride=stride)
+    rxm = M.Receiver(max_frames=8, max_samples=stride, keep_taps=True)
+    try:
+        st = _compare_frames(rxm, oracle, pcm, 1, sent)
+        assert (st["status"] == 0).all() and (st["mode"] == mode).all() and (st["flips"] == 0).all()
+        imp = oracle.impair(multipath=True, cfo_hz=-77.7, sfo_ppm=-60, awgn_db=-26, seed=mode)
+        pcm, ns, sent = oracle.encode_batch(5, seed0=100 * mode + 50, channels=2, mode=mode, imp=imp, stride=pcm.shape[1])
+        _compare_frames(rxm, oracle, pcm, 2, sent)
+    finally:
+        rxm.close()
+
+
+def test_mixed_modes_in_one_batch(oracle):
+    """Windows of different modes (both code tables) in one call: each decodes as it does alone."""
+    import modem_b200 as M
+    frames = [oracle.encode_batch(2, seed0=7000 + m, mode=m) for m in (13, 6, 10, 8, 6, 11)]
+    stride = max(f[0].shape[1] for f in frames)
+    pcm = np.zeros((12, stride), np.int16)
+    sent = np.concatenate([f[2] for f in frames])
+    ns = np.zeros(12, np.int32)
+    for k, f in enumerate(frames):
+        pcm[2 * k:2 * k + 2, :f[0].shape[1]] = f[0]
+        ns[2 * k:2 * k + 2] = f[0].shape[1]
+    rxm = M.Receiver(max_frames=12, max_samples=stride)
+    try:
+        payload, st = rxm.decode(pcm, n_samples=ns)
+        assert (st["status"] == 0).all() and (payload == sent).all()
+        assert list(st["mode"]) == [13, 13, 6, 6, 10, 10, 8, 8, 6, 6, 11, 11]
+    finally:
+        rxm.close()
+
+
+def test_polar_second_code_table(rx, oracle):
+    """frozen_64512_43072 (modes 10..13): all 8 survivors and metrics equal the oracle's."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    for k, sigma in enumerate((0.0, 0.6, 0.72, 0.8)):
+        pl = oracle.make_payload(800 + k)
+        code = np.zeros(64512, np.uint8)
+        oracle.lib().ref_payload_to_code(pl.ctypes.data_as(C.c_void_p), 10, code.ctypes.data_as(C.c_void_p))
+        y = (1.0 - 2.0 * code) + sigma * rng.standard_normal(64512)
+        llr = np.concatenate([2 * y / max(sigma, 0.3) ** 2, np.full(65536 - 64512, 9000.0)]).astype(np.float32)
+        payload, st, xb = rx.polar_decode(llr[None], want_xbits=True, table=1)
+        best, lanes, met, opay, flips = oracle.polar_decode(llr, table=1)
+        glanes = np.unpackbits(xb[0].view(np.uint8), bitorder="little").reshape(8, 65536)
+        assert (glanes == lanes).all() and (st["metrics"][0] == met).all()
+        assert st["best_lane"][0] == best and (payload[0] == opay).all() and st["flips"][0] == flips
+    rx.polar_decode(llr[None], table=0)   # leave the shared fixture on table 0
 
 
 def test_pipeline_awgn_near_threshold(rx, oracle):
