@@ -1,4 +1,4 @@
-/* include/ofdmrx.h — C-ABI of libofdmrx.so: batched B200 (sm_100a) receive path for aicodix/modem mode-6 frames.
+/* include/ofdmrx.h — C-ABI of libofdmrx.so: batched B200 (sm_100a) receive path for aicodix/modem frames (modes 6..13, 8000 Hz).
  *
  * The reference has NO plugin / FFI interface: its only stable contract is the command line
  * `decode OUTPUT INPUT [SKIP]` with WAV in / 5380 payload bytes out (/root/reference/decode.cc:559-620).  This

@@ -29,7 +29,7 @@ ST_OK, ST_NO_SYNC, ST_OSD_FAIL, ST_HDR_CRC, ST_BAD_MODE, ST_BAD_CALL, ST_PAYLOAD
 STATUS_TEXT = {  # the reference's stderr strings (decode.cc:419,430,435,440,543)
     ST_OK: "ok", ST_NO_SYNC: "no sync", ST_OSD_FAIL: "OSD error.", ST_HDR_CRC: "header CRC error.",
     ST_BAD_MODE: "operation mode unsupported.", ST_BAD_CALL: "call sign unsupported.",
-    ST_PAYLOAD_CRC: "payload decoding error.", ST_UNSUPPORTED_MODE: "operation mode not built (7..13).",
+    ST_PAYLOAD_CRC: "payload decoding error.", ST_UNSUPPORTED_MODE: "operation mode not built.",
 }
 TAP_IQ, TAP_TIMING, TAP_SOFT, TAP_CONS_RAW, TAP_CONS, TAP_TS, TAP_LLR, TAP_PHASE = range(8)
 _TAP_DTYPE = {TAP_IQ: np.complex64, TAP_TIMING: np.float32, TAP_SOFT: np.int8, TAP_CONS_RAW: np.complex64,
