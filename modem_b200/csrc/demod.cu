@@ -25,7 +25,7 @@ namespace ofdmrx {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int kDmThreads = 512; // >= the widest mode's carrier count (mode 10: 512)
+constexpr int kDmThreads = 320; // one radix-4 butterfly of the FFT-1280 per thread
 
 // per-row geometry of the Theil-Sen estimator: n carriers at x = i - n/2 (decode.cc:452,484), ranks as std::nth_element
 // is asked for them (element count/2 of the n(n-1)/2 slopes and of the n intercepts; mode 6: 432 -> 93 096 / 46 548 / 216)
@@ -62,6 +62,7 @@ __device__ __forceinline__ void psk_hard_map(cfx c, cfx &m, bool qpsk)
 struct FftShared {
 	cfx buf0[kSymLen];
 	cfx buf1[kSymLen];
+	cfx rot[kSymLen];   // exp(-j cfo i), i = 0..1279: the frame phasor inside one symbol
 	cfx prev[kMaxCols];
 };
 
@@ -78,29 +79,34 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 	const bool qpsk = mi.mod_bits == 2;
 	const int p0 = st.sc_pos + 2 * kPitch; // pilot body (decode.cc:456-459)
 	const double turns = -(double)st.cfo_rad / 6.283185307179586476925286766559;
+	// the frame phasor osc (decode.cc:403,459-461,468-470) at sample i of symbol sym is exp(-j cfo (n0 + i)): the factor
+	// of i comes from a per-window table, the factor of n0 is one evaluation per symbol (both from a double phase)
+	for (int i = tid; i < kSymLen; i += kDmThreads) s.rot[i] = phasor_turns(turns * (double)i);
+	__syncthreads();
 	for (int sym = 0; sym <= mi.rows; ++sym) {
 		const int w0 = p0 + kPitch * sym;
-		const int n0 = kSymLen + kPitch * sym; // phasor steps since the header symbol (decode.cc:404-405,459-461,468-470)
+		const int n0 = kSymLen + kPitch * sym; // phasor steps since the header symbol
+		const cfx base = phasor_turns(turns * (double)n0);
 		for (int i = tid; i < kSymLen; i += kDmThreads) {
 			const int idx = w0 + i;
 			const cfx v = (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
-			s.buf0[i] = cmul(v, phasor_turns(turns * (double)(n0 + i)));
+			s.buf0[i] = cmul(v, cmul(base, s.rot[i]));
 		}
 		__syncthreads();
 		fft_fwd<kSymLen>(s.buf0, s.buf1, tw1280, tid, kDmThreads);
-		if (tid < cols) {
-			const cfx cur = s.buf1[(tid - cols / 2 + kSymLen) % kSymLen];
+		for (int k = tid; k < cols; k += kDmThreads) {
+			const cfx cur = s.buf1[(k - cols / 2 + kSymLen) % kSymLen];
 			if (sym > 0) {
 				const int row = sym - 1;
-				const cfx c = demod_or_erase(cur, s.prev[tid]);
-				const size_t o = (size_t)f * kMaxCons + row * cols + tid;
+				const cfx c = demod_or_erase(cur, s.prev[k]);
+				const size_t o = (size_t)f * kMaxCons + row * cols + k;
 				cons_raw[o] = c;
 				cfx m;
 				psk_hard_map(c, m, qpsk);
 				const cfx e = cmulc(c, m);
 				yph[o] = atan2f(e.y, e.x); // decode.cc:483-486
 			}
-			s.prev[tid] = cur;
+			s.prev[k] = cur;
 		}
 		__syncthreads();
 	}

@@ -233,66 +233,51 @@ __global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64
 
 // ------------------------------------------------------------------------------------------------ K1b detection
 // Schmitt trigger (low 0.17*161, high 0.19*161) + falling edge + first strict maximum inside each
-// [rise, fall] segment (decode.cc:93-108).  One CTA per window; the hysteresis is resolved with a scan over
-// the 4 possible {0,1}->{0,1} maps of each thread's chunk.
+// [rise, fall] segment (decode.cc:93-108).  One CTA per window.  The trigger only ever reacts to "v > high" while low
+// and to "v < low" while high, so the stream is first reduced — with coalesced loads, one ballot per 32 samples — to two
+// bit masks per 32-sample word; one thread then walks the words (almost all of them are skipped with one test) and
+// lists the edges in stream order; a warp per (rise, fall) segment finds the maximum.
 constexpr int kDtThreads = 256;
+constexpr int kDtTile = 65536;                 // samples per pass (state and edge list carry over)
+constexpr int kDtWords = kDtTile / 32;
 
 __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples,
 	int n_default, Detection *det, int32_t *det_count)
 {
-	__shared__ unsigned char fmap[kDtThreads]; // bit0 = f(0), bit1 = f(1)
-	__shared__ unsigned char instate[kDtThreads];
-	__shared__ int ev_cnt[kDtThreads], ev_off[kDtThreads + 1];
+	__shared__ uint32_t hi_m[kDtWords], lo_m[kDtWords];
 	__shared__ int ev_t[2 * kMaxDet + 2];
-	__shared__ int first_is_fall;
-	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+	__shared__ int n_ev_s, state_s;
+	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = (n_samples ? n_samples[f] : n_default) + 1; // steps t = 0..n_samples
 	const float *tm = timing + (size_t)f * timing_stride;
 	const float low = (float)(0.17 * kMatchLen), high = (float)(0.19 * kMatchLen);
-	const int per = (n + kDtThreads - 1) / kDtThreads;
-	const int b = tid * per, e = min(n, b + per);
-	// pass 1: the chunk as a map on the trigger state
-	bool s0 = false, s1 = true;
-	for (int t = b; t < e; ++t) {
-		const float v = tm[t];
-		if (s0) { if (v < low) s0 = false; } else { if (v > high) s0 = true; }
-		if (s1) { if (v < low) s1 = false; } else { if (v > high) s1 = true; }
+	if (tid == 0) { n_ev_s = 0; state_s = 0; } // the trigger starts low, so the first edge is always a rise
+	for (int t0 = 0; t0 < n; t0 += kDtTile) {
+		const int words = min(kDtWords, (n - t0 + 31) >> 5);
+		for (int w = wid; w < words; w += kDtThreads / 32) {
+			const int t = t0 + 32 * w + lane;
+			const float v = t < n ? tm[t] : 0.f;
+			const unsigned h = __ballot_sync(FULL, t < n && v > high), l = __ballot_sync(FULL, t < n && v < low);
+			if (lane == 0) { hi_m[w] = h; lo_m[w] = l; }
+		}
+		__syncthreads();
+		if (tid == 0) {
+			int s = state_s, ne = n_ev_s;
+			for (int w = 0; w < words; ++w) {
+				uint32_t m = s ? lo_m[w] : hi_m[w];
+				while (m) {
+					const int b = __ffs(m) - 1;
+					if (ne < 2 * kMaxDet) ev_t[ne] = t0 + 32 * w + b;
+					++ne;
+					s ^= 1;
+					m = b == 31 ? 0u : (s ? lo_m[w] : hi_m[w]) & (0xfffffffeu << b);
+				}
+			}
+			state_s = s; n_ev_s = ne;
+		}
+		__syncthreads();
 	}
-	fmap[tid] = (unsigned char)((s0 ? 1 : 0) | (s1 ? 2 : 0));
-	__syncthreads();
-	if (tid == 0) {
-		bool s = false;
-		for (int k = 0; k < kDtThreads; ++k) { instate[k] = s; s = (fmap[k] >> (s ? 1 : 0)) & 1; }
-	}
-	__syncthreads();
-	// pass 2: count edges (rise or fall) in my chunk, then write them in stream order
-	bool s = instate[tid];
-	int cnt = 0;
-	for (int t = b; t < e; ++t) {
-		const float v = tm[t];
-		const bool ns = s ? !(v < low) : (v > high);
-		cnt += ns != s;
-		s = ns;
-	}
-	ev_cnt[tid] = cnt;
-	__syncthreads();
-	if (tid == 0) {
-		int acc = 0;
-		for (int k = 0; k < kDtThreads; ++k) { ev_off[k] = acc; acc += ev_cnt[k]; }
-		ev_off[kDtThreads] = acc;
-		first_is_fall = 0; // the trigger starts low, so the first edge is always a rise
-	}
-	__syncthreads();
-	s = instate[tid];
-	int pos = ev_off[tid];
-	for (int t = b; t < e; ++t) {
-		const float v = tm[t];
-		const bool ns = s ? !(v < low) : (v > high);
-		if (ns != s) { if (pos < 2 * kMaxDet) ev_t[pos] = t; ++pos; }
-		s = ns;
-	}
-	__syncthreads();
-	const int n_ev = min(ev_off[kDtThreads], 2 * kMaxDet);
+	const int n_ev = min(n_ev_s, 2 * kMaxDet);
 	const int n_seg = n_ev / 2; // (rise, fall) pairs; an unfinished segment never fires
 	// segments: edges alternate rise, fall, rise, ...  One warp per segment finds the first strict maximum.
 	for (int sgi = tid >> 5; sgi < n_seg; sgi += kDtThreads / 32) {
