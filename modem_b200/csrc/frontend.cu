@@ -254,26 +254,38 @@ __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing,
 	if (tid == 0) { n_ev_s = 0; state_s = 0; } // the trigger starts low, so the first edge is always a rise
 	for (int t0 = 0; t0 < n; t0 += kDtTile) {
 		const int words = min(kDtWords, (n - t0 + 31) >> 5);
-		for (int w = wid; w < words; w += kDtThreads / 32) {
-			const int t = t0 + 32 * w + lane;
-			const float v = t < n ? tm[t] : 0.f;
-			const unsigned h = __ballot_sync(FULL, t < n && v > high), l = __ballot_sync(FULL, t < n && v < low);
-			if (lane == 0) { hi_m[w] = h; lo_m[w] = l; }
+		for (int w0 = wid * 4; w0 < words; w0 += (kDtThreads / 32) * 4) { // four independent loads in flight per lane
+			float v[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const int t = t0 + 32 * (w0 + k) + lane;
+				v[k] = t < n ? tm[t] : __int_as_float(0x7fc00000); // NaN: neither above high nor below low
+			}
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const unsigned h = __ballot_sync(FULL, v[k] > high), l = __ballot_sync(FULL, v[k] < low);
+				if (lane == 0 && w0 + k < words) { hi_m[w0 + k] = h; lo_m[w0 + k] = l; }
+			}
 		}
 		__syncthreads();
-		if (tid == 0) {
+		if (wid == 0) { // all lanes run the same walk (uniform); 32 words are skipped per step while nothing can happen
 			int s = state_s, ne = n_ev_s;
-			for (int w = 0; w < words; ++w) {
-				uint32_t m = s ? lo_m[w] : hi_m[w];
-				while (m) {
-					const int b = __ffs(m) - 1;
-					if (ne < 2 * kMaxDet) ev_t[ne] = t0 + 32 * w + b;
-					++ne;
-					s ^= 1;
-					m = b == 31 ? 0u : (s ? lo_m[w] : hi_m[w]) & (0xfffffffeu << b);
+			for (int w0 = 0; w0 < words; w0 += 32) {
+				const int wl = w0 + lane;
+				const uint32_t mine = wl < words ? (s ? lo_m[wl] : hi_m[wl]) : 0u;
+				if (__ballot_sync(FULL, mine != 0u) == 0u) continue;
+				for (int w = w0; w < min(w0 + 32, words); ++w) {
+					uint32_t m = s ? lo_m[w] : hi_m[w];
+					while (m) {
+						const int b = __ffs(m) - 1;
+						if (ne < 2 * kMaxDet && lane == 0) ev_t[ne] = t0 + 32 * w + b;
+						++ne;
+						s ^= 1;
+						m = b == 31 ? 0u : (s ? lo_m[w] : hi_m[w]) & (0xfffffffeu << b);
+					}
 				}
 			}
-			state_s = s; n_ev_s = ne;
+			if (lane == 0) { state_s = s; n_ev_s = ne; }
 		}
 		__syncthreads();
 	}
