@@ -88,7 +88,7 @@ def make_batch(n, seed0, threads):
     return O.encode_batch(n, seed0=seed0, nthreads=threads)
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, json_out):
     """CPU arm: the oracle port of decode.cc on the box's host cores (the reference itself cannot be built: DESIGN.md)."""
     if rank != 0:
         return
@@ -118,7 +118,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
 
 
 def workload_config(args, sample_note=None):
@@ -139,11 +139,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="windows for the cpu_baseline leg (0 = 2 x cores)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr instead
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, json_out)
         return
 
     import torch
@@ -313,7 +316,7 @@ def main():
             assert (cout == got[:sample]).all(), "GPU payload differs from the CPU oracle"
             line["cpu_baseline"] = {"value": sample / dt * PAYLOAD_BITS / 1e6, "unit": "Mbit/s", "frames_per_s": sample / dt, "cores": cores,
                                     "kind": "port", "sample": "first %d windows of the same batch, %d threads, oracle port -Ofast -march=native; payloads equal the GPU's" % (sample, cores)}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     rx.close()
     if e2e_state:
         e2e_state["rx2"].close()
