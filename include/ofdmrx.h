@@ -57,7 +57,8 @@ typedef struct ofdmrx_frame_status {
 	int32_t flips;       /* "bit flips" (decode.cc:546-555) */
 	float metrics[8];    /* final path metrics, ascending */
 	int32_t osd_visited;
-	int32_t reserved[2];
+	int32_t ts_sweeps;   /* pair sweeps the Theil-Sen search took, summed over the rows (rows = the minimum) */
+	int32_t reserved;
 } ofdmrx_frame_status;
 
 /* stages whose outputs can be read back for parity tests (ofdmrx_get_taps); layouts are per window */

@@ -39,7 +39,7 @@ STATUS_DTYPE = np.dtype([
     ("status", "<i4"), ("detections", "<i4"), ("t_fire", "<i4"), ("symbol_pos", "<i4"), ("sc_pos", "<i4"),
     ("index_max", "<i4"), ("shift", "<i4"), ("pos_err", "<i4"), ("timing_max", "<f4"), ("frac_cfo", "<f4"),
     ("cfo_rad", "<f4"), ("osd_unique", "<i4"), ("mode", "<i4"), ("md_lo", "<u4"), ("md_hi", "<u4"),
-    ("best_lane", "<i4"), ("flips", "<i4"), ("metrics", "<f4", (8,)), ("osd_visited", "<i4"), ("reserved", "<i4", (2,)),
+    ("best_lane", "<i4"), ("flips", "<i4"), ("metrics", "<f4", (8,)), ("osd_visited", "<i4"), ("ts_sweeps", "<i4"), ("reserved", "<i4"),
 ])
 assert STATUS_DTYPE.itemsize == 112
 

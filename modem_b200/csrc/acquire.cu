@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		st.best_lane = -1; st.flips = -1;
 		for (int k = 0; k < 8; ++k) st.metrics[k] = 0.f;
 		st.osd_visited = 0;
+		st.ts_sweeps = 0; st.reserved = 0;
 	}
 }
 

@@ -53,7 +53,8 @@ struct FrameState {
 	int32_t best_lane, flips;
 	float metrics[8];
 	int32_t osd_visited;
-	int32_t reserved[2];
+	int32_t ts_sweeps;    // pair sweeps the Theil-Sen search took, summed over the window's rows
+	int32_t reserved;
 };
 static_assert(sizeof(FrameState) == 112, "FrameState layout");
 

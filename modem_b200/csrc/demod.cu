@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "frontend.cuh"
 #include "fft.cuh"
+#include <algorithm>
 
 namespace ofdmrx {
 namespace {
@@ -294,8 +295,11 @@ __device__ __noinline__ float ts_slope_bisect(const float *y, int n, int rank, i
 }
 
 // exact upper median of the pairwise slopes of (x = i - 216, y[i]); one warp, y in s.y (tail padded)
-__device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps)
+// hint: expected (Theil-Sen - OLS) of this row, in slope units (0 = none); pilot_out / half_out: the OLS slope and the
+// bracket half-width used, for the caller's running estimate of that gap
+__device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, float hint, float &pilot_out, float &half_out)
 {
+	pilot_out = 0.f; half_out = 0.f;
 	// ---- pilot: least-squares line and residual spread (only steers the bracket, so fp32 sums are good enough)
 	float yv[kTsRows];
 	float a0 = 0.f, a1 = 0.f;
@@ -322,27 +326,74 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps)
 	if (ymin == ymax) return 0.f; // erased row: every difference is 0, every quotient +0
 	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(s.y, d.n, d.rank_slope, lane); // non-finite input: stay total
 	const float sxx = (float)d.n * ((float)d.n * (float)d.n - 1.f) / 12.f;
-	const float c0 = a1 / sxx, mean = a0 / (float)d.n;
+	float c0 = a1 / sxx, icpt = a0 / (float)d.n; // least-squares line through the centred abscissa x + 0.5
 	float r2 = 0.f;
 #pragma unroll
 	for (int r = 0; r < kTsRows; ++r) {
 		const int i = 32 * r + lane;
 		if (i < d.n) {
-			const float e = yv[r] - mean - c0 * ((float)(i - d.half) + 0.5f);
+			const float e = yv[r] - icpt - c0 * ((float)(i - d.half) + 0.5f);
 			r2 = fmaf(e, e, r2);
 		}
 	}
 #pragma unroll
 	for (int dd = 16; dd; dd >>= 1) r2 += __shfl_xor_sync(FULL, r2, dd);
-	// residual spread, rescaled so that the bracket below (sized for 432 carriers) keeps its width in units of the
-	// standard deviation of (Theil-Sen - OLS), which goes like sigma / n^1.5
+	float srob = sqrtf(r2 / (float)(d.n - 2));
+	// Huber M-estimate of the line (k = 1.345, scale by Huber's proposal 2, four re-weighted least-squares steps).  Least
+	// squares is a poor stand-in for Theil-Sen once a few carriers misbehave (multipath notch at a band edge, wrapped phase
+	// decisions): on the README impairment chain the two differ by ~5 bracket widths (3 sweeps per row); the Huber line
+	// stays within ~0.4 bracket widths of the Theil-Sen slope on clean, AWGN and multipath rows alike.
+	{
+		const float kh = 1.345f, beta = 0.71016f; // beta = E[min(z^2, k^2)], z ~ N(0,1)
+#pragma unroll 1
+		for (int it = 0; it < 4; ++it) {
+			const float cap = kh * srob;
+			float acc = 0.f;
+#pragma unroll
+			for (int r = 0; r < kTsRows; ++r) {
+				const int i = 32 * r + lane;
+				if (i < d.n) {
+					const float e = yv[r] - icpt - c0 * ((float)(i - d.half) + 0.5f);
+					acc += fminf(e * e, cap * cap);
+				}
+			}
+#pragma unroll
+			for (int dd = 16; dd; dd >>= 1) acc += __shfl_xor_sync(FULL, acc, dd);
+			srob = sqrtf(acc / ((float)d.n * beta));
+			const float lim = kh * srob;
+			float sw = 0.f, swx = 0.f, swy = 0.f, swxx = 0.f, swxy = 0.f;
+#pragma unroll
+			for (int r = 0; r < kTsRows; ++r) {
+				const int i = 32 * r + lane;
+				if (i < d.n) {
+					const float x = (float)(i - d.half) + 0.5f;
+					const float e = fabsf(yv[r] - icpt - c0 * x);
+					const float w = e <= lim ? 1.f : __fdividef(lim, e);
+					sw += w; swx = fmaf(w, x, swx); swy = fmaf(w, yv[r], swy);
+					swxx = fmaf(w * x, x, swxx); swxy = fmaf(w * x, yv[r], swxy);
+				}
+			}
+#pragma unroll
+			for (int dd = 16; dd; dd >>= 1) {
+				sw += __shfl_xor_sync(FULL, sw, dd); swx += __shfl_xor_sync(FULL, swx, dd); swy += __shfl_xor_sync(FULL, swy, dd);
+				swxx += __shfl_xor_sync(FULL, swxx, dd); swxy += __shfl_xor_sync(FULL, swxy, dd);
+			}
+			const float den = sw * swxx - swx * swx;
+			if (!(den > 0.f) || !(srob > 0.f)) break; // degenerate weights: keep the previous line
+			c0 = (sw * swxy - swx * swy) / den;
+			icpt = (swy - c0 * swx) / sw;
+		}
+	}
+	// robust residual scale, rescaled so that the bracket below (sized for 432 carriers) keeps its width in units of the
+	// standard deviation of (Theil-Sen - pilot), which goes like sigma / n^1.5
 	const float scale = 432.f / (float)d.n;
-	const float sigma = sqrtf(r2 / (float)(d.n - 2)) * scale * sqrtf(scale);
+	const float sigma = srob * scale * sqrtf(scale);
 	const float yabs = fmaxf(fabsf(ymin), fabsf(ymax));
-	// The Theil–Sen median differs from the OLS slope by about 0.84e-4 sigma (its efficiency relative to OLS is 0.955);
-	// +-1.35e-4 sigma holds rank 46 548 in ~90 % of the rows and ~1000 of the 93 096 quotients (~32 per lane's sub-queue).
+	// +-1.35e-4 sigma around the pilot holds rank 46 548 in ~99 % of the rows and ~1100 of the 93 096 quotients
+	// (~35 per lane's sub-queue).
 	float half = fmaxf(1.35e-4f * sigma, fmaxf(fabsf(c0) * 4e-6f, 1e-12f));
-	float blo = c0 - half, bhi = c0 + half;
+	pilot_out = c0; half_out = half;
+	float blo = c0 + hint - half, bhi = c0 + hint + half;
 	// enclosure of the answer established so far: #(q < L) = cL <= rank < cU = #(q < U)  (exact counts; +-inf = unknown)
 	const float inf = __int_as_float(0x7f800000);
 	float L = -inf, U = inf;
@@ -436,49 +487,63 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps)
 	return ts_slope_bisect(s.y, d.n, d.rank_slope, lane);
 }
 
-// Rows: with a status array, window f owns the rows f * kMaxRows + r, r < rows(mode), of cols(mode) phase values at
-// yph + f * kMaxCons + r * cols; without one (test hook) n_rows dense rows of fixed_cols values.
-__global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, const FrameState *stv, int n_rows, int fixed_cols, float *ts_out)
+// Work items: with a status array, item = (window f, chain c of n_chains): the chain walks a contiguous block of the window's
+// rows (row r: cols(mode) phase values at yph + f * kMaxCons + r * cols) one after the other.  Without a status array (test
+// hook) every item is one dense row of fixed_cols values.
+__global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, FrameState *stv, int n_items, int n_chains, int fixed_cols, float *ts_out)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	TsShared &s = reinterpret_cast<TsShared *>(smraw)[wid];
-	for (int row = blockIdx.x * kTsWarps + wid; row < n_rows; row += gridDim.x * kTsWarps) {
-		int cols = fixed_cols;
-		const float *y = yph + (size_t)row * fixed_cols;
+	for (int item = blockIdx.x * kTsWarps + wid; item < n_items; item += gridDim.x * kTsWarps) {
+		int cols = fixed_cols, r0 = 0, r1 = 1, total_sweeps = 0, frame = -1;
+		const float *ybase = yph + (size_t)item * fixed_cols;
+		float *tbase = ts_out + (size_t)item * 3;
 		if (stv) {
-			const int f = row / kMaxRows, r = row - f * kMaxRows;
+			const int f = item / n_chains, c = item - f * n_chains;
 			if (stv[f].status != ST_OK) continue;
+			frame = f;
 			const ModeInfo mi = mode_info(stv[f].mode);
-			if (r >= mi.rows) continue;
+			const int per = (mi.rows + n_chains - 1) / n_chains;
+			r0 = c * per;
+			r1 = min(mi.rows, r0 + per);
 			cols = mi.cols;
-			y = yph + (size_t)f * kMaxCons + r * cols;
+			ybase = yph + (size_t)f * kMaxCons;
+			tbase = ts_out + (size_t)f * kMaxRows * 3;
 		}
 		const TsDims d(cols);
-		__syncwarp();
+		const float gap = 0.f; // no re-centring: the Huber pilot leaves no systematic gap to the Theil-Sen slope
+		for (int r = r0; r < r1; ++r) {
+			const float *y = ybase + (size_t)r * cols;
+			__syncwarp();
 #pragma unroll
-		for (int r = 0; r < kTsRows; ++r) {
-			const int i = 32 * r + lane;
-			s.y[i] = i < d.n ? y[i] : __int_as_float(0x7f800000);
-		}
-		__syncwarp();
-		int sweeps = 0;
-		const float slope = ts_slope(s, d, lane, sweeps);
-		// intercept: upper median of y_i - slope * x_i
-		__syncwarp();
-		int *z = s.cand;
+			for (int k = 0; k < kTsRows; ++k) {
+				const int i = 32 * k + lane;
+				s.y[i] = i < d.n ? y[i] : __int_as_float(0x7f800000);
+			}
+			__syncwarp();
+			int sweeps = 0;
+			float pilot, half;
+			const float slope = ts_slope(s, d, lane, sweeps, gap, pilot, half);
+			total_sweeps += sweeps;
+			// intercept: upper median of y_i - slope * x_i
+			__syncwarp();
+			int *z = s.cand;
 #pragma unroll
-		for (int r = 0; r < kTsRows; ++r) {
-			const int i = 32 * r + lane;
-			if (i < d.n) z[i] = f2ord(__fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - d.half))));
+			for (int k = 0; k < kTsRows; ++k) {
+				const int i = 32 * k + lane;
+				if (i < d.n) z[i] = f2ord(__fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - d.half))));
+			}
+			__syncwarp();
+			const float yint = ord2f(warp_select_kth(z, d.n, d.rank_yint, s.hist, lane));
+			if (lane == 0) {
+				float *t = tbase + (size_t)(stv ? r : 0) * 3;
+				t[0] = slope;
+				t[1] = yint;
+				t[2] = (float)sweeps; // diagnostic; k_soft_demap stores the row's precision here
+			}
 		}
-		__syncwarp();
-		const float yint = ord2f(warp_select_kth(z, d.n, d.rank_yint, s.hist, lane));
-		if (lane == 0) {
-			ts_out[(size_t)row * 3 + 0] = slope;
-			ts_out[(size_t)row * 3 + 1] = yint;
-			ts_out[(size_t)row * 3 + 2] = (float)sweeps; // diagnostic; k_soft_demap stores the row's precision here
-		}
+		if (lane == 0 && frame >= 0) atomicAdd(&stv[frame].ts_sweeps, total_sweeps);
 	}
 }
 
@@ -576,18 +641,22 @@ cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float 
 	if (n_rows <= 0) return cudaSuccess;
 	int smem;
 	const int grid = theil_sen_grid(n_rows, n_sm, &smem);
-	k_theil_sen<<<grid, kTsWarps * 32, smem, s>>>(yph, nullptr, n_rows, cols, ts);
+	k_theil_sen<<<grid, kTsWarps * 32, smem, s>>>(yph, nullptr, n_rows, 1, cols, ts);
 	return cudaGetLastError();
 }
 
-cudaError_t launch_demod(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *st, int n_frames, const cfx *tw1280,
+cudaError_t launch_demod(const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
 	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
 	k_demod_fft<<<n_frames, kDmThreads, 0, s>>>(iq, iq_stride, iq_len, st, tw1280, cons_raw, yph);
+	// chains per window: one when there are windows enough to fill the GPU twice over, more (shorter) ones for small batches
 	int ts_smem;
-	const int grid = theil_sen_grid(n_frames * kMaxRows, n_sm, &ts_smem);
-	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames * kMaxRows, 0, ts);
+	theil_sen_grid(1, n_sm, &ts_smem);
+	const int resident_warps = n_sm * (int)((227 * 1024) / (ts_smem + 1024)) * kTsWarps;
+	const int n_chains = std::max(5, std::min(9, (2 * resident_warps + n_frames - 1) / n_frames)); // >= 5: short items keep the tail short
+	const int grid = theil_sen_grid(n_frames * n_chains, n_sm, &ts_smem);
+	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames * n_chains, n_chains, 0, ts);
 	k_soft_demap<<<n_frames, kSdThreads, 0, s>>>(cons_raw, st, ts, cons, llr);
 	return cudaGetLastError();
 }
