@@ -64,6 +64,7 @@ struct FftShared {
 	cfx buf0[kSymLen];
 	cfx buf1[kSymLen];
 	cfx rot[kSymLen];   // exp(-j cfo i), i = 0..1279: the frame phasor inside one symbol
+	cfx base[kMaxRows + 2]; // exp(-j cfo n0(sym)): the frame phasor at the start of every symbol
 	cfx prev[kMaxCols];
 };
 
@@ -83,15 +84,30 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 	// the frame phasor osc (decode.cc:403,459-461,468-470) at sample i of symbol sym is exp(-j cfo (n0 + i)): the factor
 	// of i comes from a per-window table, the factor of n0 is one evaluation per symbol (both from a double phase)
 	for (int i = tid; i < kSymLen; i += kDmThreads) s.rot[i] = phasor_turns(turns * (double)i);
+	for (int sym = tid; sym <= mi.rows; sym += kDmThreads) s.base[sym] = phasor_turns(turns * (double)(kSymLen + kPitch * sym)); // steps since the header symbol
 	__syncthreads();
+	// the samples of symbol sym + 1 are loaded into registers while symbol sym goes through its FFT passes
+	constexpr int kPerThread = kSymLen / kDmThreads; // 4
+	cfx nxt[kPerThread];
+#pragma unroll
+	for (int k = 0; k < kPerThread; ++k) {
+		const int idx = p0 + tid + k * kDmThreads;
+		nxt[k] = (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
+	}
 	for (int sym = 0; sym <= mi.rows; ++sym) {
-		const int w0 = p0 + kPitch * sym;
-		const int n0 = kSymLen + kPitch * sym; // phasor steps since the header symbol
-		const cfx base = phasor_turns(turns * (double)n0);
-		for (int i = tid; i < kSymLen; i += kDmThreads) {
-			const int idx = w0 + i;
-			const cfx v = (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
-			s.buf0[i] = cmul(v, cmul(base, s.rot[i]));
+		const cfx base = s.base[sym];
+#pragma unroll
+		for (int k = 0; k < kPerThread; ++k) {
+			const int i = tid + k * kDmThreads;
+			s.buf0[i] = cmul(nxt[k], cmul(base, s.rot[i]));
+		}
+		if (sym < mi.rows) {
+			const int w1 = p0 + kPitch * (sym + 1);
+#pragma unroll
+			for (int k = 0; k < kPerThread; ++k) {
+				const int idx = w1 + tid + k * kDmThreads;
+				nxt[k] = (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
+			}
 		}
 		__syncthreads();
 		fft_fwd<kSymLen>(s.buf0, s.buf1, tw1280, tid, kDmThreads);
