@@ -230,11 +230,12 @@ struct Emu {
 
 extern "C" {
 // llr[65536] -> lanes[8][65536] codeword bits in ascending (metric, lane) order + metrics[8]
-void emu_polar_decode(const float *llr, uint8_t *lanes_out, float *metrics_out, long long *forks)
+static void emu_polar_decode_table(int table, const float *llr, uint8_t *lanes_out, float *metrics_out, long long *forks)
 {
-	static Emu e;
+	static Emu emu[2];
+	Emu &e = emu[table ? 1 : 0];
 	if (e.frozen.empty()) {
-		e.frozen = make_frozen(kCodeOrder, kConsBits, kCrcBits);
+		e.frozen = make_frozen(kCodeOrder, table ? 64512 : kConsBits, kCrcBits);
 		e.ops = make_scl_schedule(e.frozen, kCodeOrder);
 	}
 	e.run(llr);
@@ -247,6 +248,9 @@ void emu_polar_decode(const float *llr, uint8_t *lanes_out, float *metrics_out, 
 	}
 	if (forks) { forks[0] = e.forks; forks[1] = e.fast_hits; forks[2] = e.keep_all; }
 }
+void emu_polar_decode(const float *llr, uint8_t *lanes_out, float *metrics_out, long long *forks) { emu_polar_decode_table(0, llr, lanes_out, metrics_out, forks); }
+// table 1: the frozen set of modes 10..13 (decode.cc:342-343)
+void emu_polar_decode_alt(const float *llr, uint8_t *lanes_out, float *metrics_out, long long *forks) { emu_polar_decode_table(1, llr, lanes_out, metrics_out, forks); }
 void host_frozen(uint32_t *out) { auto f = make_frozen(kCodeOrder, kConsBits, kCrcBits); std::memcpy(out, f.data(), 2048 * 4); }
 void host_frozen_alt(uint32_t *out) { auto f = make_frozen(kCodeOrder, 64512, kCrcBits); std::memcpy(out, f.data(), 2048 * 4); }
 int host_schedule(uint32_t *out, int cap)

@@ -82,6 +82,23 @@ def test_emulator_matches_oracle_bit_exact(oracle, hostlib):
             assert best == 0 and (payload == pl).all()
 
 
+def test_emulator_second_code_table(oracle, hostlib):
+    """frozen_64512_43072 (modes 10..13): schedule incl. TOP ops, map algebra and metrics against the oracle."""
+    rng = np.random.default_rng(3)
+    for seed, sigma in enumerate([0.0, 0.65, 0.8]):
+        pl = oracle.make_payload(600 + seed)
+        code = np.zeros(64512, np.uint8)
+        oracle.lib().ref_payload_to_code(_p(pl), 10, _p(code))
+        y = (1.0 - 2.0 * code) + sigma * rng.standard_normal(64512)
+        llr = np.concatenate([2 * y / max(sigma, 0.3) ** 2, np.full(65536 - 64512, 9000.0)]).astype(np.float32)
+        best, lanes, met, payload, flips = oracle.polar_decode(llr, table=1)
+        el, em = np.zeros((8, 65536), np.uint8), np.zeros(8, np.float32)
+        hostlib.emu_polar_decode_alt(_p(llr), _p(el), _p(em), None)
+        assert (el == lanes).all() and (em == met).all(), sigma
+        if sigma <= 0.65:
+            assert best == 0 and (payload == pl).all()
+
+
 def test_emulator_ties_and_zero_llrs(oracle, hostlib):
     """Degenerate inputs: all-equal magnitudes (every fork ties) and exact zeros."""
     pl, llr = _noisy(oracle, 9, 0.0)
