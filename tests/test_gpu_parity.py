@@ -350,6 +350,12 @@ def test_decode_cli_matches_reference_contract(oracle, tmp_path):
             assert (tmp_path / "gpu.dat").read_bytes() == (tmp_path / "cpu.dat").read_bytes() == data[skip]
             for line in (b"symbol pos:", b"coarse cfo:", b"oper mode: 6", b"call sign:  CALLSIGN", b"bit flips: 0"):
                 assert line in r.stderr, line
+    # another operation mode through the same command line (mode 13: QPSK, 256 carriers, 126 rows, second code table)
+    subprocess.run([enc, wav, "8000", "16", "1", "1500", "13", "N0CALL", str(tmp_path / "in1.dat")], check=True)
+    r = subprocess.run([dec, str(tmp_path / "gpu.dat"), wav], capture_output=True)
+    q = subprocess.run([ref, str(tmp_path / "cpu.dat"), wav], capture_output=True)
+    assert r.returncode == 0 and (tmp_path / "gpu.dat").read_bytes() == (tmp_path / "cpu.dat").read_bytes() == data[1]
+    assert b"oper mode: 13" in r.stderr and b"call sign:    N0CALL" in r.stderr and b"bit flips: 0" in r.stderr
     r = subprocess.run([dec], capture_output=True)
     assert r.returncode == 1 and b"usage:" in r.stderr
     raw = bytearray(open(wav, "rb").read())
