@@ -20,9 +20,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int kAcqThreads = 320, kAcqWarps = kAcqThreads / 32;
 constexpr int K = kHdrK, NB = kHdrBits;
 
-struct AcqShared {
-	cfx buf0[kSymLen];
-	cfx buf1[kSymLen];
+struct AcqShared { // followed in dynamic shared memory by the two FFT buffers of symbol_len values each
 	uint32_t rows[K][8];
 	short lut[32][256];
 	int soft[256];
@@ -242,11 +240,19 @@ __device__ __forceinline__ cfx load_iq(const cfx *a, int idx, int iq_len)
 	return (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
 }
 
+constexpr size_t kAcqBufOff = (sizeof(AcqShared) + 15) & ~(size_t)15;
+
+template <int S>
 __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det,
 	const int32_t *det_count, int skip, FrameState *stv, int8_t *soft_out, AcquireConsts ac)
 {
+	// geometry of this sample rate (shadows the 8 kHz constants of host_tables.h)
+	constexpr int kSymLen = Geo<S>::kSymLen, kHalf = Geo<S>::kHalf, kPitch = Geo<S>::kPitch, kGuardLen = Geo<S>::kGuardLen;
+	constexpr int kBufferLen = Geo<S>::kBufferLen, kSearchPos = Geo<S>::kSearchPos, kMatchDel = Geo<S>::kMatchDel;
+	constexpr int kOffOld = kBufferLen - 1 - (kSearchPos + kHalf), kOffCur = kBufferLen - 1 - (kSearchPos + kSymLen); // 5119, 4479
 	extern __shared__ __align__(16) unsigned char smraw[];
 	AcqShared &s = *reinterpret_cast<AcqShared *>(smraw);
+	cfx *const buf0 = reinterpret_cast<cfx *>(smraw + kAcqBufOff), *const buf1 = buf0 + kSymLen;
 	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const cfx *a = iq + (size_t)f * iq_stride;
 	FrameState &st = stv[f];
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 			const int tau = D.t_max - kMatchDel;
 			float pr = 0.f, pi = 0.f;
 			for (int k = tid; k < kHalf; k += kAcqThreads) {
-				const cfx c = cmulc(load_iq(a, tau - k - 5119, iq_len), load_iq(a, tau - k - 4479, iq_len));
+				const cfx c = cmulc(load_iq(a, tau - k - kOffOld, iq_len), load_iq(a, tau - k - kOffCur, iq_len));
 				pr += c.x; pi += c.y;
 			}
 #pragma unroll
@@ -287,25 +293,25 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		for (int i = tid; i < kHalf; i += kAcqThreads) {
 			float sn, cs;
 			sincosf(frac_cfo * (float)i, &sn, &cs);
-			s.buf0[i] = cmul(load_iq(a, win0 + symbol_pos + kHalf + i, iq_len), make_float2(cs, sn));
+			buf0[i] = cmul(load_iq(a, win0 + symbol_pos + kHalf + i, iq_len), make_float2(cs, sn));
 		}
 		__syncthreads();
-		fft_fwd<kHalf>(s.buf0, s.buf1, ac.tw640, tid, kAcqThreads); // spectrum in buf1
-		for (int i = tid; i < kHalf; i += kAcqThreads) s.buf0[i] = demod_or_erase(s.buf1[i], s.buf1[(i + kHalf - 1) % kHalf]);
+		fft_fwd<kHalf>(buf0, buf1, ac.tw640, tid, kAcqThreads); // spectrum in buf1
+		for (int i = tid; i < kHalf; i += kAcqThreads) buf0[i] = demod_or_erase(buf1[i], buf1[(i + kHalf - 1) % kHalf]);
 		__syncthreads();
-		fft_fwd<kHalf>(s.buf0, s.buf1, ac.tw640, tid, kAcqThreads);
+		fft_fwd<kHalf>(buf0, buf1, ac.tw640, tid, kAcqThreads);
 		// * kern, then backward transform as conj(fwd(conj(.)))
 		for (int i = tid; i < kHalf; i += kAcqThreads) {
-			const cfx v = cmul(s.buf1[i], ac.kern640[i]);
-			s.buf0[i] = make_float2(v.x, -v.y);
+			const cfx v = cmul(buf1[i], ac.kern640[i]);
+			buf0[i] = make_float2(v.x, -v.y);
 		}
 		__syncthreads();
-		fft_fwd<kHalf>(s.buf0, s.buf1, ac.tw640, tid, kAcqThreads); // buf1 = conj(result)
+		fft_fwd<kHalf>(buf0, buf1, ac.tw640, tid, kAcqThreads); // buf1 = conj(result)
 		// peak / runner-up (decode.cc:127-139): first index of the maximum, second largest of the multiset
 		float pk = -1.f;
 		int pki = 1 << 30;
 		for (int i = tid; i < kHalf; i += kAcqThreads) {
-			const float p = cnorm(s.buf1[i]);
+			const float p = cnorm(buf1[i]);
 			if (p > pk) { pk = p; pki = i; }
 		}
 #pragma unroll
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		const int shift = peak > 0.f ? s.bc_i[0] : 0;
 		float nx = 0.f;
 		for (int i = tid; i < kHalf; i += kAcqThreads)
-			if (i != shift) nx = fmaxf(nx, cnorm(s.buf1[i]));
+			if (i != shift) nx = fmaxf(nx, cnorm(buf1[i]));
 #pragma unroll
 		for (int d = 16; d; d >>= 1) nx = fmaxf(nx, __shfl_xor_sync(FULL, nx, d));
 		if (lane == 0) s.redf[wid][1] = nx;
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		const float next = s.bc_f[2];
 		const float pkv = fmaxf(peak, 0.f);
 		if (pkv <= next * 4.f) { __syncthreads(); continue; }
-		const cfx top = make_float2(s.buf1[shift].x, -s.buf1[shift].y); // undo the conj of the backward transform
+		const cfx top = make_float2(buf1[shift].x, -buf1[shift].y); // undo the conj of the backward transform
 		const int pos_err = (int)rintf(__fdiv_rn(atan2f(top.y, top.x) * (float)kHalf, 6.28318530717958647692f));
 		if (abs(pos_err) > kGuardLen / 2) { __syncthreads(); continue; }
 		symbol_pos -= pos_err;
@@ -357,14 +363,14 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		r_poserr = pos_err; r_tmax = D.timing_max; r_frac = frac_cfo; r_cfo = cfo_rad;
 		const double turns = -(double)cfo_rad / 6.283185307179586476925286766559;
 		for (int i = tid; i < kSymLen; i += kAcqThreads)
-			s.buf0[i] = cmul(load_iq(a, r_scpos + kPitch + i, iq_len), phasor_turns(turns * (double)i));
+			buf0[i] = cmul(load_iq(a, r_scpos + kPitch + i, iq_len), phasor_turns(turns * (double)i));
 		__syncthreads();
-		fft_fwd<kSymLen>(s.buf0, s.buf1, ac.tw1280, tid, kAcqThreads);
+		const cfx *const X = fft_fwd<kSymLen>(buf0, buf1, ac.tw1280, tid, kAcqThreads);
 		if (tid < 256) s.soft[tid] = 0;
 		__syncthreads();
 		if (tid < NB) {
 			const int kc = (tid - 127 + kSymLen) % kSymLen, kp = (tid - 128 + kSymLen) % kSymLen;
-			cfx cur = s.buf1[kc], prev = s.buf1[kp];
+			cfx cur = X[kc], prev = X[kp];
 			if (ac.mls1[tid]) { cur.x = -cur.x; cur.y = -cur.y; }
 			if (tid > 0 && ac.mls1[tid - 1]) { prev.x = -prev.x; prev.y = -prev.y; }
 			float v = rintf(127.f * demod_or_erase(cur, prev).x);
@@ -453,17 +459,26 @@ __global__ void k_compact(const FrameState *st, int n_frames, int *cw_list, int 
 
 } // namespace
 
-cudaError_t launch_acquire(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+template <int S>
+static cudaError_t launch_acquire_t(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s)
+{
+	static bool attr = false;
+	const size_t smem = kAcqBufOff + 2 * (size_t)Geo<S>::kSymLen * sizeof(cfx);
+	if (!attr) {
+		cudaFuncSetAttribute(k_acquire<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		attr = true;
+	}
+	k_acquire<S><<<n_frames, kAcqThreads, smem, s>>>(iq, iq_stride, iq_len, det, det_count, skip, st, soft_out, ac);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_acquire(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	static bool attr = false;
-	if (!attr) {
-		cudaFuncSetAttribute(k_acquire, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AcqShared));
-		attr = true;
-	}
-	k_acquire<<<n_frames, kAcqThreads, sizeof(AcqShared), s>>>(iq, iq_stride, iq_len, det, det_count, skip, st, soft_out, ac);
-	return cudaGetLastError();
+	return rate_scale == 2 ? launch_acquire_t<2>(iq, iq_stride, iq_len, det, det_count, skip, n_frames, st, soft_out, ac, s)
+		: launch_acquire_t<1>(iq, iq_stride, iq_len, det, det_count, skip, n_frames, st, soft_out, ac, s);
 }
 
 cudaError_t launch_compact(const FrameState *st, int n_frames, int *cw_list, int *n_cw, cudaStream_t s)

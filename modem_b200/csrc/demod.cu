@@ -60,18 +60,22 @@ __device__ __forceinline__ void psk_hard_map(cfx c, cfx &m, bool qpsk)
 }
 
 // ================================================================================================ k_demod_fft
+template <int S>
 struct FftShared {
-	cfx buf0[kSymLen];
-	cfx buf1[kSymLen];
-	cfx rot[kSymLen];   // exp(-j cfo i), i = 0..1279: the frame phasor inside one symbol
-	cfx base[kMaxRows + 2]; // exp(-j cfo n0(sym)): the frame phasor at the start of every symbol
+	cfx buf0[Geo<S>::kSymLen];
+	cfx buf1[Geo<S>::kSymLen];
+	cfx rot[Geo<S>::kSymLen];   // exp(-j cfo i), i < symbol_len: the frame phasor inside one symbol
+	cfx base[kMaxRows + 2];     // exp(-j cfo n0(sym)): the frame phasor at the start of every symbol
 	cfx prev[kMaxCols];
 };
 
+template <int S>
 __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *stv,
-	const cfx *tw1280, cfx *cons_raw, float *yph)
+	const cfx *tw, cfx *cons_raw, float *yph)
 {
-	__shared__ FftShared s;
+	constexpr int kSymLen = Geo<S>::kSymLen, kPitch = Geo<S>::kPitch; // shadow the 8 kHz constants
+	extern __shared__ __align__(16) unsigned char smraw_fft[];
+	FftShared<S> &s = *reinterpret_cast<FftShared<S> *>(smraw_fft);
 	const int f = blockIdx.x, tid = threadIdx.x;
 	const FrameState &st = stv[f];
 	if (st.status != ST_OK) return;
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 	for (int sym = tid; sym <= mi.rows; sym += kDmThreads) s.base[sym] = phasor_turns(turns * (double)(kSymLen + kPitch * sym)); // steps since the header symbol
 	__syncthreads();
 	// the samples of symbol sym + 1 are loaded into registers while symbol sym goes through its FFT passes
-	constexpr int kPerThread = kSymLen / kDmThreads; // 4
+	constexpr int kPerThread = kSymLen / kDmThreads; // 4 (8 at 16 kHz)
 	cfx nxt[kPerThread];
 #pragma unroll
 	for (int k = 0; k < kPerThread; ++k) {
@@ -110,9 +114,9 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 			}
 		}
 		__syncthreads();
-		fft_fwd<kSymLen>(s.buf0, s.buf1, tw1280, tid, kDmThreads);
+		const cfx *const X = fft_fwd<kSymLen>(s.buf0, s.buf1, tw, tid, kDmThreads);
 		for (int k = tid; k < cols; k += kDmThreads) {
-			const cfx cur = s.buf1[(k - cols / 2 + kSymLen) % kSymLen];
+			const cfx cur = X[(k - cols / 2 + kSymLen) % kSymLen];
 			if (sym > 0) {
 				const int row = sym - 1;
 				const cfx c = demod_or_erase(cur, s.prev[k]);
@@ -661,11 +665,24 @@ cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float 
 	return cudaGetLastError();
 }
 
-cudaError_t launch_demod(const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
+template <int S>
+static void launch_demod_fft_t(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *st, int n_frames, const cfx *tw,
+	cfx *cons_raw, float *yph, cudaStream_t s)
+{
+	static bool attr = false;
+	if (!attr) {
+		cudaFuncSetAttribute(k_demod_fft<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FftShared<S>));
+		attr = true;
+	}
+	k_demod_fft<S><<<n_frames, kDmThreads, sizeof(FftShared<S>), s>>>(iq, iq_stride, iq_len, st, tw, cons_raw, yph);
+}
+
+cudaError_t launch_demod(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
 	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	k_demod_fft<<<n_frames, kDmThreads, 0, s>>>(iq, iq_stride, iq_len, st, tw1280, cons_raw, yph);
+	if (rate_scale == 2) launch_demod_fft_t<2>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s);
+	else launch_demod_fft_t<1>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s);
 	// chains per window: one when there are windows enough to fill the GPU twice over, more (shorter) ones for small batches
 	int ts_smem;
 	theil_sen_grid(1, n_sm, &ts_smem);

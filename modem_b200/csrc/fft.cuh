@@ -57,20 +57,28 @@ __device__ __forceinline__ void fft_pass(const cfx *src, cfx *dst, int m, const 
 	}
 }
 
-// in: buf0 (N values), scratch buf1; result ends up in buf1.  All threads of the CTA must call.
+// in: buf0 (N values), scratch buf1; returns the buffer holding the result (buf1 for 640 / 1280, buf0 for 2560, which takes
+// an even number of passes).  All threads of the CTA must call.
 template <int N>
-__device__ __forceinline__ void fft_fwd(cfx *buf0, cfx *buf1, const cfx *tw, int tid, int nthr)
+__device__ __forceinline__ cfx *fft_fwd(cfx *buf0, cfx *buf1, const cfx *tw, int tid, int nthr)
 {
-	static_assert(N == 1280 || N == 640, "lengths of the 8 kHz receive path");
+	static_assert(N == 2560 || N == 1280 || N == 640, "lengths of the 8 / 16 kHz receive paths");
 	fft_pass<N, 4>(buf0, buf1, 1, tw, tid, nthr); __syncthreads();
 	fft_pass<N, 4>(buf1, buf0, 4, tw, tid, nthr); __syncthreads();
 	fft_pass<N, 4>(buf0, buf1, 16, tw, tid, nthr); __syncthreads();
-	if constexpr (N == 1280) {
+	if constexpr (N == 2560) {
+		fft_pass<N, 4>(buf1, buf0, 64, tw, tid, nthr); __syncthreads();
+		fft_pass<N, 2>(buf0, buf1, 256, tw, tid, nthr); __syncthreads();
+		fft_pass<N, 5>(buf1, buf0, 512, tw, tid, nthr); __syncthreads();
+		return buf0;
+	} else if constexpr (N == 1280) {
 		fft_pass<N, 4>(buf1, buf0, 64, tw, tid, nthr); __syncthreads();
 		fft_pass<N, 5>(buf0, buf1, 256, tw, tid, nthr); __syncthreads();
+		return buf1;
 	} else {
 		fft_pass<N, 2>(buf1, buf0, 64, tw, tid, nthr); __syncthreads();
 		fft_pass<N, 5>(buf0, buf1, 128, tw, tid, nthr); __syncthreads();
+		return buf1;
 	}
 }
 

@@ -22,17 +22,22 @@ constexpr unsigned FULL = 0xffffffffu;
 // across threads by a scan over (alpha, beta) pairs of the affine map y_out = alpha * y_in + beta.
 constexpr int kFeThreads = 256, kFePer = 8, kFeTile = kFeThreads * kFePer;
 
+template <int S>
 __global__ void __launch_bounds__(kFeThreads) k_frontend_mono(const int16_t *pcm, int64_t pcm_stride, const int32_t *n_samples,
-	int n_default, cfx *iq, int64_t iq_stride, int iq_len, float dc_a, float dc_b, float reco, float im0, float im1, float im2, float im3, float im4)
+	int n_default, cfx *iq, int64_t iq_stride, int iq_len, FrontendConsts fc)
 {
-	__shared__ float ybuf[20 + kFeTile];
+	// Hilbert<T>: the output at step t is formed before x[t] is pushed: centre tap y[t-1-mid], odd offsets up to mid-1,
+	// i.e. it uses y[t-2 mid .. t-2] (T = 21: y[t-20 .. t-2]); ybuf[j] = y[t0 - 2 mid + j]
+	constexpr int T = Geo<S>::kFilterLen, kMid = (T - 1) / 2, kHist = 2 * kMid, kCo = (T - 1) / 4;
+	__shared__ float ybuf[kHist + kFeTile];
 	__shared__ float2 wsum[kFeThreads / 32];
 	__shared__ float carry_y, carry_x;
+	const float dc_a = fc.dc_a, dc_b = fc.dc_b;
 	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = n_samples ? n_samples[f] : n_default;
 	const int16_t *src = pcm + (size_t)f * pcm_stride;
 	cfx *dst = iq + (size_t)f * iq_stride;
-	if (tid < 20) ybuf[tid] = 0.f;
+	if (tid < kHist) ybuf[tid] = 0.f;
 	if (tid == 0) { carry_y = 0.f; carry_x = 0.f; }
 	__syncthreads();
 	float a8 = dc_a;
@@ -74,28 +79,25 @@ __global__ void __launch_bounds__(kFeThreads) k_frontend_mono(const int16_t *pcm
 #pragma unroll
 		for (int k = 0; k < kFePer; ++k) {
 			yy = u[k] + dc_a * yy;
-			ybuf[20 + tid * kFePer + k] = yy;
+			ybuf[kHist + tid * kFePer + k] = yy;
 		}
 		__syncthreads();
 		if (tid == kFeThreads - 1) { carry_y = yy; carry_x = x[kFePer - 1]; }
-		// Hilbert: output t uses y[t-20 .. t-2]; ybuf[j] = y[t0 - 20 + j]
 #pragma unroll
 		for (int k = 0; k < kFePer; ++k) {
 			const int j = k * kFeThreads + tid; // coalesced store order
 			const int t = t0 + j;
 			if (t < iq_len) {
-				const float *c = &ybuf[j + 9]; // y[t-11]
-				const float re = reco * c[0];
-				float im = im0 * (c[-1] - c[1]);
-				im += im1 * (c[-3] - c[3]);
-				im += im2 * (c[-5] - c[5]);
-				im += im3 * (c[-7] - c[7]);
-				im += im4 * (c[-9] - c[9]);
+				const float *c = &ybuf[j + kMid - 1]; // y[t-1-mid]
+				const float re = fc.reco * c[0];
+				float im = fc.imco[0] * (c[-1] - c[1]);
+#pragma unroll
+				for (int i = 1; i < kCo; ++i) im += fc.imco[i] * (c[-(2 * i + 1)] - c[2 * i + 1]);
 				dst[t] = make_float2(re, im);
 			}
 		}
 		__syncthreads();
-		if (tid < 20) ybuf[tid] = ybuf[kFeTile + tid];
+		if (tid < kHist) ybuf[tid] = ybuf[kFeTile + tid];
 		__syncthreads();
 	}
 }
@@ -130,9 +132,18 @@ __global__ void k_frontend_f32(const cfx *in, int64_t in_stride, const int32_t *
 // P[t] = sum_{k<640} c[t-k], R[t] = max(0.5 sum_{k<1280} e[t-k], 0.064), m[t] = |P|^2/R^2,
 // timing[t] = sum_{k<161} m[t-k]  (decode.cc:86-90 with search_pos = 2880, buffer_len = 8640).
 // Tile of kMtTile outputs; extended index j = t - t0 + kMtHalo addresses a[t0 - 5918 + j].
-constexpr int kMtThreads = 256, kMtTile = 2048, kMtHalo = 1439, kMtExt = kMtTile + kMtHalo; // 3487
-constexpr int kMtPer = (kMtExt + kMtThreads - 1) / kMtThreads;                                 // 14
-constexpr int kMtPad = kMtThreads * kMtPer;                                                    // 3584
+constexpr int kMtThreads = 256, kMtTile = 2048;
+template <int S>
+struct Mt {
+	using G = Geo<S>;
+	static constexpr int kHalo = 2 * G::kHalf + G::kMatchLen - 2, kExt = kMtTile + kHalo;      // 1439, 3487 at 8 kHz
+	static constexpr int kPer = (kExt + kMtThreads - 1) / kMtThreads;                           // 14
+	static constexpr int kPad = kMtThreads * kPer;                                              // 3584
+	// newest sample is buffer tap kBufferLen - 1: the correlator's taps search_pos + half and search_pos + symbol_len
+	// (decode.cc:86) are the stream samples t - kOffOld and t - kOffCur
+	static constexpr int kOffOld = G::kBufferLen - 1 - (G::kSearchPos + G::kHalf);              // 5119
+	static constexpr int kOffCur = G::kBufferLen - 1 - (G::kSearchPos + G::kSymLen);            // 4479
+};
 
 template <typename T>
 __device__ __forceinline__ T warp_incl_scan(T v, int lane)
@@ -145,9 +156,12 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane)
 	return v;
 }
 
+template <int S>
 __global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples,
 	int n_default, float *timing, int64_t timing_stride)
 {
+	constexpr int kMtHalo = Mt<S>::kHalo, kMtExt = Mt<S>::kExt, kMtPer = Mt<S>::kPer, kMtPad = Mt<S>::kPad;
+	constexpr int kLag = Geo<S>::kHalf, kLen2 = Geo<S>::kSymLen, kBox = Geo<S>::kMatchLen;
 	extern __shared__ float sm[];
 	cfx *sa = reinterpret_cast<cfx *>(sm);              // [kMtPad] samples
 	float *sre = sm + 2 * kMtPad;                       // prefix of c.re, later prefix of m
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64
 	const int t0 = blockIdx.x * kMtTile;
 	if (t0 > n) return; // stream has n+1 steps: t = 0..n
 	const cfx *a = iq + (size_t)f * iq_stride;
-	const int base = t0 - 5918;
+	const int base = t0 - (Mt<S>::kOffCur + kMtHalo); // extended index j <-> a[t - kOffCur], t = t0 + j - kMtHalo
 	{ // all kMtPer loads of a thread are issued before the first shared-memory store (memory-level parallelism)
 		cfx v[kMtPer];
 #pragma unroll
@@ -179,7 +193,7 @@ __global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64
 	for (int k = 0; k < kMtPer; ++k) {
 		const int j = j0 + k;
 		const cfx cur = sa[j];
-		const cfx old = j >= 640 ? sa[j - 640] : make_float2(0.f, 0.f);
+		const cfx old = j >= kLag ? sa[j - kLag] : make_float2(0.f, 0.f);
 		const cfx c = cmulc(old, cur);
 		s0 += c.x; s1 += c.y; s2 += cnorm(cur);
 		cre[k] = s0; cim[k] = s1; ce[k] = s2;
@@ -203,10 +217,10 @@ __global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64
 	for (int k = 0; k < kMtPer; ++k) {
 		const int j = j0 + k;
 		float m = 0.f;
-		if (j >= 1279 && j < kMtExt) {
-			const float pr = sre[j] - sre[j - 640], pi = sim[j] - sim[j - 640];
-			float r = 0.5f * (se[j] - (j >= 1280 ? se[j - 1280] : 0.f));
-			r = fmaxf(r, 0.064f);
+		if (j >= kLen2 - 1 && j < kMtExt) {
+			const float pr = sre[j] - sre[j - kLag], pi = sim[j] - sim[j - kLag];
+			float r = 0.5f * (se[j] - (j >= kLen2 ? se[j - kLen2] : 0.f));
+			r = fmaxf(r, 0.0001f * (float)kLag); // decode.cc:87-89
 			m = __fdiv_rn(pr * pr + pi * pi, r * r);
 			// windows that start before the stream did (t < 0 contributions) are zero because a[<0] = 0
 		}
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64
 		const int t = t0 + i;
 		if (t > n) break;
 		const int j = i + kMtHalo;
-		out[t] = sre[j] - sre[j - 161];
+		out[t] = sre[j] - sre[j - kBox];
 	}
 }
 
@@ -241,9 +255,11 @@ constexpr int kDtThreads = 256;
 constexpr int kDtTile = 65536;                 // samples per pass (state and edge list carry over)
 constexpr int kDtWords = kDtTile / 32;
 
+template <int S>
 __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples,
 	int n_default, Detection *det, int32_t *det_count)
 {
+	constexpr int kMatchLen = Geo<S>::kMatchLen, kMatchDel = Geo<S>::kMatchDel, kHalf = Geo<S>::kHalf, kGuardLen = Geo<S>::kGuardLen;
 	__shared__ uint32_t hi_m[kDtWords], lo_m[kDtWords];
 	__shared__ int ev_t[2 * kMaxDet + 2];
 	__shared__ int n_ev_s, state_s;
@@ -321,13 +337,15 @@ __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing,
 
 } // namespace
 
-cudaError_t launch_frontend(int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_frontend(int rate_scale, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
 	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
 	if (format == 0) {
-		k_frontend_mono<<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len,
-			fc.dc_a, fc.dc_b, fc.reco, fc.imco[0], fc.imco[1], fc.imco[2], fc.imco[3], fc.imco[4]);
+		if (rate_scale == 2)
+			k_frontend_mono<2><<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc);
+		else
+			k_frontend_mono<1><<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc);
 	} else if (format == 1) {
 		dim3 g((iq_len + 1023) / 1024, n_frames);
 		k_frontend_iq16<<<g, 256, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len);
@@ -338,27 +356,35 @@ cudaError_t launch_frontend(int format, const void *samples, int64_t stride, con
 	return cudaGetLastError();
 }
 
-size_t sync_metric_smem() { return (size_t)5 * kMtPad * sizeof(float); }
-
-cudaError_t launch_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
+template <int S>
+static cudaError_t launch_sync_metric_t(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
 	float *timing, int64_t timing_stride, cudaStream_t s)
 {
-	if (n_frames <= 0) return cudaSuccess;
 	static bool attr = false;
+	const size_t smem = (size_t)5 * Mt<S>::kPad * sizeof(float);
 	if (!attr) {
-		cudaFuncSetAttribute(k_sync_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sync_metric_smem());
+		cudaFuncSetAttribute(k_sync_metric<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		attr = true;
 	}
 	dim3 g((n_max + 1 + kMtTile - 1) / kMtTile, n_frames);
-	k_sync_metric<<<g, kMtThreads, sync_metric_smem(), s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride);
+	k_sync_metric<S><<<g, kMtThreads, smem, s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride);
 	return cudaGetLastError();
 }
 
-cudaError_t launch_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_sync_metric(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
+	float *timing, int64_t timing_stride, cudaStream_t s)
+{
+	if (n_frames <= 0) return cudaSuccess;
+	return rate_scale == 2 ? launch_sync_metric_t<2>(iq, iq_stride, iq_len, n_samples, n_default, n_max, n_frames, timing, timing_stride, s)
+		: launch_sync_metric_t<1>(iq, iq_stride, iq_len, n_samples, n_default, n_max, n_frames, timing, timing_stride, s);
+}
+
+cudaError_t launch_sync_detect(int rate_scale, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
 	Detection *det, int32_t *det_count, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	k_sync_detect<<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count);
+	if (rate_scale == 2) k_sync_detect<2><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count);
+	else k_sync_detect<1><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count);
 	return cudaGetLastError();
 }
 

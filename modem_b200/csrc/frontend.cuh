@@ -15,27 +15,27 @@ struct Detection {
 
 struct FrontendConsts {
 	float dc_a, dc_b;  // BlockDC for 2*(1280+160) samples (decode.cc:386)
-	float reco, imco[5];
+	float reco, imco[kMaxHilbertCoeffs]; // Hilbert<21>: 5 coefficients, Hilbert<41>: 10
 };
 
 struct AcquireConsts {
-	const cfx *tw1280, *tw640; // forward twiddles exp(-2 pi j k / N)
-	const cfx *kern640;        // conj(FFT640(MLS0 template)) / 640 (decode.cc:76-83)
+	const cfx *tw1280, *tw640; // forward twiddles exp(-2 pi j k / N) for N = symbol_len and symbol_len / 2 (names: 8 kHz)
+	const cfx *kern640;        // conj(FFT_half(MLS0 template)) / half (decode.cc:76-83)
 	const uint8_t *mls1;       // 255 scrambler bits (decode.cc:407)
 	const uint32_t *bch_rows;  // 71 x 8 words, systematic generator (decode.cc:378-384)
 };
 
-cudaError_t launch_frontend(int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_frontend(int rate_scale, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
 	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s);
-cudaError_t launch_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
+cudaError_t launch_sync_metric(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
 	float *timing, int64_t timing_stride, cudaStream_t s);
-cudaError_t launch_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_sync_detect(int rate_scale, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
 	Detection *det, int32_t *det_count, cudaStream_t s);
-cudaError_t launch_acquire(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+cudaError_t launch_acquire(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s);
 // three kernels: FFT + differential demodulation (cons_raw, phase errors yph), Theil-Sen per row (ts[row] = slope, yint,
 // precision), soft demapping (llr; cons = derotated constellation, optional)
-cudaError_t launch_demod(const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
+cudaError_t launch_demod(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
 	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s);
 cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float *ts, int n_sm, cudaStream_t s);
 cudaError_t launch_compact(const FrameState *st, int n_frames, int *cw_list, int *n_cw, cudaStream_t s);

@@ -86,7 +86,7 @@ int main(int argc, char **argv)
 	}
 	int skip = argc > 3 ? std::atoi(argv[3]) : 0;
 	if (skip < 0) skip = 0;
-	if (w.rate != 8000) { // 16000/44100/48000 are valid for the reference (decode.cc:590-606) but not built here yet
+	if (w.rate != 8000 && w.rate != 16000) { // 44100/48000 are valid for the reference (decode.cc:590-606) but not built here yet
 		std::cerr << "Unsupported sample rate." << std::endl;
 		return 1;
 	}
@@ -95,7 +95,7 @@ int main(int argc, char **argv)
 	const int n_frames = batch ? (int)(total / stride) : 1;
 	if (n_frames < 1) { std::cerr << "input shorter than one window" << std::endl; return 1; }
 	ofdmrx_t *h = nullptr;
-	int rc = ofdmrx_create(&h, 0, 8000, std::min(n_frames, 4096), (int)stride);
+	int rc = ofdmrx_create(&h, 0, w.rate, std::min(n_frames, 4096), (int)stride);
 	if (rc) { std::cerr << "ofdmrx_create failed (" << rc << "): a B200 is required, there is no CPU path" << std::endl; return 1; }
 	std::vector<uint8_t> out((size_t)n_frames * OFDMRX_PAYLOAD_BYTES);
 	std::vector<ofdmrx_frame_status> st(n_frames);
@@ -110,7 +110,7 @@ int main(int argc, char **argv)
 		if (batch) std::cerr << "window " << i << ":" << std::endl;
 		if (s.detections > 0) {
 			std::cerr << "symbol pos: " << s.symbol_pos << std::endl;
-			std::cerr << "coarse cfo: " << s.cfo_rad * (8000 / 6.28318530717958647692f) << " Hz " << std::endl;
+			std::cerr << "coarse cfo: " << s.cfo_rad * ((float)w.rate / 6.28318530717958647692f) << " Hz " << std::endl;
 		}
 		switch (s.status) {
 		case OFDMRX_ST_OSD_FAIL: std::cerr << "OSD error." << std::endl; break;

@@ -174,8 +174,9 @@ std::vector<float> twiddles(int n, int sign)
 	return t;
 }
 
-std::vector<float> mls0_kernel()
+std::vector<float> mls0_kernel(int half)
 {
+	const int kHalf = half; // shadows the 8 kHz constant
 	// template: +-1 at bins -63..63 of 640 (decode.cc:236-244); spectrum by direct DFT in double, conj, / 640
 	std::vector<double> seq(kHalf, 0.0);
 	std::vector<uint8_t> m = mls_bits(0b10001001, 127);

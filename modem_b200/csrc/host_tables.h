@@ -16,13 +16,23 @@
 
 namespace ofdmrx {
 
-// ---- fixed geometry: mode 6 at 8000 Hz (decode.cc:171-189, 305-312) ------------------------------------
-constexpr int kRate = 8000;
-constexpr int kSymLen = 1280, kGuardLen = 160, kPitch = 1440, kHalf = 640;
-constexpr int kBufferLen = 6 * kPitch;            // 8640
-constexpr int kSearchPos = kBufferLen - 4 * kPitch; // 2880
-constexpr int kMatchLen = 161, kMatchDel = 80;
-constexpr int kFilterLen = 21;
+// ---- sample-rate geometry (decode.cc:171-173,188-189,196; SchmidlCox template arguments decode.cc:41-42) -------------
+// S = rate / 8000.  Built: S = 1 (8000 Hz) and S = 2 (16000 Hz); 44100 / 48000 Hz need radix-3/7 FFT passes (7056, 7680).
+template <int S>
+struct Geo {
+	static constexpr int kRate = 8000 * S;
+	static constexpr int kSymLen = 1280 * S, kGuardLen = kSymLen / 8, kPitch = kSymLen + kGuardLen, kHalf = kSymLen / 2;
+	static constexpr int kBufferLen = 6 * kPitch;               // 8640 at 8 kHz
+	static constexpr int kSearchPos = kBufferLen - 4 * kPitch;  // 2880
+	static constexpr int kMatchLen = kGuardLen | 1, kMatchDel = (kMatchLen - 1) / 2; // 161, 80
+	static constexpr int kFilterLen = ((21 * S) & ~3) | 1;      // 21 (41 at 16 kHz)
+};
+constexpr int kRate = Geo<1>::kRate;
+constexpr int kSymLen = Geo<1>::kSymLen, kGuardLen = Geo<1>::kGuardLen, kPitch = Geo<1>::kPitch, kHalf = Geo<1>::kHalf;
+constexpr int kBufferLen = Geo<1>::kBufferLen, kSearchPos = Geo<1>::kSearchPos;
+constexpr int kMatchLen = Geo<1>::kMatchLen, kMatchDel = Geo<1>::kMatchDel;
+constexpr int kFilterLen = Geo<1>::kFilterLen;
+constexpr int kMaxHilbertCoeffs = 10; // (41 - 1) / 4
 constexpr int kConsCols = 432, kConsRows = 50, kModBits = 3, kConsCnt = 21600, kConsBits = 64800;
 constexpr int kCodeOrder = 16, kCodeLen = 65536, kMesgBits = 43808, kDataBits = 43040, kCrcBits = 43072, kDataBytes = 5380;
 constexpr int kHdrBits = 255, kHdrK = 71;
@@ -73,7 +83,7 @@ std::vector<uint8_t> mls_bits(int poly, int n);              // first n outputs 
 std::vector<uint32_t> bch_generator_rows();                  // 71 rows x 8 words, bit j of row i = G[i][j], systematic [I|P]
 std::vector<float> hilbert_coeffs(int taps, float *reco);    // imag-branch coefficients for odd offsets 1,3,..
 std::vector<float> twiddles(int n, int sign);                // n complex values exp(sign*2*pi*j*k/n) as (re,im) pairs
-std::vector<float> mls0_kernel();                            // conj(FFT640(template))/640, 640 complex (decode.cc:76-83,236-244)
+std::vector<float> mls0_kernel(int half = kHalf);             // conj(FFT_half(template))/half, `half` complex values (decode.cc:76-83,236-244)
 void crc32_table(uint32_t poly, uint32_t *lut256);
 uint16_t crc16_u64(uint64_t v);                              // CRC-16 0xA8F4 over the 8 LE bytes (decode.cc:428-429)
 void base37_decode(char *str, long long val, int len);       // decode.cc:155-159

@@ -22,6 +22,7 @@ static_assert(sizeof(ofdmrx_frame_status) == sizeof(FrameState), "ABI status str
 
 struct ofdmrx_handle {
 	int device = 0, n_sm = 0;
+	int rate_scale = 1; // sample rate / 8000 (1 or 2)
 	int max_frames = 0, max_samples = 0, iq_len = 0;
 	bool keep_taps = false;
 	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0, scl_stream_level = 17;
@@ -101,7 +102,7 @@ const char *ofdmrx_version(void) { return "ofdmrx 0.2 (sm_100a; modes 6-13 @ 8 k
 
 int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int max_samples)
 {
-	if (!out || rate_hz != kRate || max_frames < 1 || max_samples < 1) return -22;
+	if (!out || (rate_hz != 8000 && rate_hz != 16000) || max_frames < 1 || max_samples < 1) return -22; // 44100 / 48000: not built
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
 		std::fprintf(stderr, "ofdmrx: no CUDA device %d (there is no CPU fallback)\n", device);
@@ -117,6 +118,7 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	ofdmrx_handle *h = new (std::nothrow) ofdmrx_handle;
 	if (!h) return -12;
 	h->device = device;
+	h->rate_scale = rate_hz / 8000;
 	h->n_sm = prop.multiProcessorCount;
 	h->max_frames = max_frames;
 	h->max_samples = max_samples;
@@ -146,13 +148,15 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	}
 	std::vector<uint32_t> bch = bch_generator_rows();
 	std::vector<uint8_t> mls1 = mls_bits(0b100101011, 255);
-	std::vector<float> tw1280 = twiddles(kSymLen, -1), tw640 = twiddles(kHalf, -1), kern = mls0_kernel();
+	const int sym_len = kSymLen * h->rate_scale, half = sym_len / 2, pitch = kPitch * h->rate_scale;
+	const int filter_len = h->rate_scale == 2 ? Geo<2>::kFilterLen : Geo<1>::kFilterLen;
+	std::vector<float> tw1280 = twiddles(sym_len, -1), tw640 = twiddles(half, -1), kern = mls0_kernel(half);
 	float reco;
-	std::vector<float> imco = hilbert_coeffs(kFilterLen, &reco);
-	h->fc.dc_a = float(2 * kPitch - 1) / float(2 * kPitch);
+	std::vector<float> imco = hilbert_coeffs(filter_len, &reco);
+	h->fc.dc_a = float(2 * pitch - 1) / float(2 * pitch);
 	h->fc.dc_b = (1.f + h->fc.dc_a) / 2.f;
 	h->fc.reco = reco;
-	for (int i = 0; i < 5; ++i) h->fc.imco[i] = imco[i];
+	for (int i = 0; i < kMaxHilbertCoeffs; ++i) h->fc.imco[i] = i < (int)imco.size() ? imco[i] : 0.f;
 	int r = 0;
 	for (int tb = 0; tb < 2; ++tb) {
 		std::vector<uint32_t> tbl(h->h_frozen[tb]);
@@ -163,9 +167,9 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_upload(&h->d_scr, scr.data(), scr.size());
 	if (!r) r = dev_upload(&h->d_bch, bch.data(), bch.size());
 	if (!r) r = dev_upload(&h->d_mls1, mls1.data(), mls1.size());
-	if (!r) r = dev_upload(&h->d_tw1280, tw1280.data(), (size_t)kSymLen);
-	if (!r) r = dev_upload(&h->d_tw640, tw640.data(), (size_t)kHalf);
-	if (!r) r = dev_upload(&h->d_kern, kern.data(), (size_t)kHalf);
+	if (!r) r = dev_upload(&h->d_tw1280, tw1280.data(), (size_t)sym_len);
+	if (!r) r = dev_upload(&h->d_tw640, tw640.data(), (size_t)half);
+	if (!r) r = dev_upload(&h->d_kern, kern.data(), (size_t)half);
 	// ---- per-chunk scratch
 	const size_t F = (size_t)max_frames;
 	h->in_bytes = F * (size_t)max_samples * sizeof(cfx); // large enough for any supported input format
@@ -268,17 +272,17 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 	float *timing = h->d_timing + (size_t)f0 * L;
 	const int32_t *ns = d_ns ? d_ns + f0 : nullptr;
 	if (record) cudaEventRecord(h->ev[0], s);
-	OFDMRX_CUDA_TRY(launch_frontend(format, d_samples, stride, ns, n_default, nf, iq, h->iq_len, h->iq_len, h->fc, s));
+	OFDMRX_CUDA_TRY(launch_frontend(h->rate_scale, format, d_samples, stride, ns, n_default, nf, iq, h->iq_len, h->iq_len, h->fc, s));
 	if (record) cudaEventRecord(h->ev[1], s);
-	OFDMRX_CUDA_TRY(launch_sync_metric(iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, s));
+	OFDMRX_CUDA_TRY(launch_sync_metric(h->rate_scale, iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, s));
 	if (record) cudaEventRecord(h->ev[2], s);
-	OFDMRX_CUDA_TRY(launch_sync_detect(timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, s));
+	OFDMRX_CUDA_TRY(launch_sync_detect(h->rate_scale, timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, s));
 	if (record) cudaEventRecord(h->ev[3], s);
 	AcquireConsts ac{h->d_tw1280, h->d_tw640, h->d_kern, h->d_mls1, h->d_bch};
-	OFDMRX_CUDA_TRY(launch_acquire(iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
+	OFDMRX_CUDA_TRY(launch_acquire(h->rate_scale, iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
 		h->d_soft + (size_t)f0 * 256, ac, s));
 	if (record) cudaEventRecord(h->ev[4], s);
-	OFDMRX_CUDA_TRY(launch_demod(iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kMaxCons,
+	OFDMRX_CUDA_TRY(launch_demod(h->rate_scale, iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kMaxCons,
 		h->d_y + (size_t)f0 * kMaxCons, h->keep_taps ? h->d_cons + (size_t)f0 * kMaxCons : nullptr, h->d_ts + (size_t)f0 * kMaxRows * 3,
 		h->d_llr + (size_t)f0 * kCodeLen, h->n_sm, s));
 	if (record) cudaEventRecord(h->ev[5], s);

@@ -202,6 +202,38 @@ def test_pipeline_other_modes(oracle, mode):
         rxm.close()
 
 
+def _compare_frames_16k(rxh, oracle, pcm, channels, sent):
+    payload, st = rxh.decode(pcm, channels=channels)
+    for i in range(pcm.shape[0]):
+        ost, opay, tp = oracle.decode(pcm[i], channels=channels, rate=16000)
+        s = st[i]
+        assert s["status"] == ost, (i, s["status"], ost)
+        assert (s["sc_pos"], s["shift"]) == (tp.sc_pos, tp.shift) and abs(int(s["pos_err"]) - tp.pos_err) <= 1
+        assert abs(s["cfo_rad"] - tp.cfo_rad) < 1e-5 and s["mode"] == tp.mode
+        if ost == 0:
+            assert (payload[i] == opay).all() and (payload[i] == sent[i]).all() and s["best_lane"] == tp.best_lane
+    return st
+
+
+@pytest.mark.parametrize("mode", [6, 9, 12])
+def test_pipeline_16khz(oracle, mode):
+    """16000 Hz (decode.cc:171-173,594-596): symbol length 2560, guard 320, Hilbert<41>, correlator length 1280,
+    FFT-2560 / FFT-1280 — clean mono and impaired analytic frames against the oracle at the same rate."""
+    import modem_b200 as M
+    stride = oracle.frame_samples(mode, 16000) + 128
+    pcm, ns, sent = oracle.encode_batch(4, seed0=1600 + mode, rate=16000, mode=mode, stride=stride)
+    rxh = M.Receiver(max_frames=4, max_samples=stride, rate=16000)
+    try:
+        st = _compare_frames_16k(rxh, oracle, pcm, 1, sent)
+        assert (st["status"] == 0).all() and (st["flips"] == 0).all()
+        imp = oracle.impair(multipath=True, cfo_hz=91.3, sfo_ppm=80, awgn_db=-28, seed=16 + mode)
+        pcm, ns, sent = oracle.encode_batch(4, seed0=1700 + mode, rate=16000, channels=2, mode=mode, imp=imp, stride=stride)
+        st = _compare_frames_16k(rxh, oracle, pcm, 2, sent)
+        assert (st["status"] == 0).all()
+    finally:
+        rxh.close()
+
+
 def test_mixed_modes_in_one_batch(oracle):
     """Windows of different modes (both code tables) in one call: each decodes as it does alone."""
     import modem_b200 as M
