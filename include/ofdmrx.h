@@ -1,4 +1,4 @@
-/* include/ofdmrx.h — C-ABI of libofdmrx.so: batched B200 (sm_100a) receive path for aicodix/modem frames (modes 6..13, 8000 Hz).
+/* include/ofdmrx.h — C-ABI of libofdmrx.so: batched B200 (sm_100a) receive path for aicodix/modem frames (modes 6..13 at 8000, 16000, 44100 and 48000 Hz).
  *
  * The reference has NO plugin / FFI interface: its only stable contract is the command line
  * `decode OUTPUT INPUT [SKIP]` with WAV in / 5380 payload bytes out (/root/reference/decode.cc:559-620).  This
@@ -74,7 +74,8 @@ typedef struct ofdmrx_frame_status {
 
 /* Replaces: `new Decoder<float, Complex<float>, 8000>` set-up work (decode.cc:375-387,590-606): constant tables,
  * BCH generator, correlator kernel — plus device scratch for up to max_frames windows of max_samples sample frames
- * processed at a time (larger batches are chunked internally).  rate_hz must be 8000 (other rates: SURVEY §8 f3). */
+ * processed at a time (larger batches are chunked internally).  rate_hz: 8000, 16000, 44100 or 48000 — the four rates the
+ * reference instantiates (decode.cc:590-606); anything else returns -22 ("Unsupported sample rate."). */
 int ofdmrx_create(ofdmrx_t **h, int device, int rate_hz, int max_frames, int max_samples_per_frame);
 void ofdmrx_destroy(ofdmrx_t *h);
 

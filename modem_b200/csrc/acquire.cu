@@ -296,22 +296,26 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 			buf0[i] = cmul(load_iq(a, win0 + symbol_pos + kHalf + i, iq_len), make_float2(cs, sn));
 		}
 		__syncthreads();
-		fft_fwd<kHalf>(buf0, buf1, ac.tw640, tid, kAcqThreads); // spectrum in buf1
-		for (int i = tid; i < kHalf; i += kAcqThreads) buf0[i] = demod_or_erase(buf1[i], buf1[(i + kHalf - 1) % kHalf]);
+		// three half-length transforms; each result lands in one of the two buffers (depends on the pass count of the
+		// length), the next input is written into the other one
+		cfx *const sp = fft_fwd<kHalf>(buf0, buf1, ac.tw640, tid, kAcqThreads); // spectrum
+		cfx *const in2 = sp == buf0 ? buf1 : buf0;
+		for (int i = tid; i < kHalf; i += kAcqThreads) in2[i] = demod_or_erase(sp[i], sp[(i + kHalf - 1) % kHalf]);
 		__syncthreads();
-		fft_fwd<kHalf>(buf0, buf1, ac.tw640, tid, kAcqThreads);
+		cfx *const x2 = fft_fwd<kHalf>(in2, sp, ac.tw640, tid, kAcqThreads);
+		cfx *const in3 = x2 == in2 ? sp : in2;
 		// * kern, then backward transform as conj(fwd(conj(.)))
 		for (int i = tid; i < kHalf; i += kAcqThreads) {
-			const cfx v = cmul(buf1[i], ac.kern640[i]);
-			buf0[i] = make_float2(v.x, -v.y);
+			const cfx v = cmul(x2[i], ac.kern640[i]);
+			in3[i] = make_float2(v.x, -v.y);
 		}
 		__syncthreads();
-		fft_fwd<kHalf>(buf0, buf1, ac.tw640, tid, kAcqThreads); // buf1 = conj(result)
+		const cfx *const xc = fft_fwd<kHalf>(in3, x2, ac.tw640, tid, kAcqThreads); // conj(result)
 		// peak / runner-up (decode.cc:127-139): first index of the maximum, second largest of the multiset
 		float pk = -1.f;
 		int pki = 1 << 30;
 		for (int i = tid; i < kHalf; i += kAcqThreads) {
-			const float p = cnorm(buf1[i]);
+			const float p = cnorm(xc[i]);
 			if (p > pk) { pk = p; pki = i; }
 		}
 #pragma unroll
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		const int shift = peak > 0.f ? s.bc_i[0] : 0;
 		float nx = 0.f;
 		for (int i = tid; i < kHalf; i += kAcqThreads)
-			if (i != shift) nx = fmaxf(nx, cnorm(buf1[i]));
+			if (i != shift) nx = fmaxf(nx, cnorm(xc[i]));
 #pragma unroll
 		for (int d = 16; d; d >>= 1) nx = fmaxf(nx, __shfl_xor_sync(FULL, nx, d));
 		if (lane == 0) s.redf[wid][1] = nx;
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		const float next = s.bc_f[2];
 		const float pkv = fmaxf(peak, 0.f);
 		if (pkv <= next * 4.f) { __syncthreads(); continue; }
-		const cfx top = make_float2(buf1[shift].x, -buf1[shift].y); // undo the conj of the backward transform
+		const cfx top = make_float2(xc[shift].x, -xc[shift].y); // undo the conj of the backward transform
 		const int pos_err = (int)rintf(__fdiv_rn(atan2f(top.y, top.x) * (float)kHalf, 6.28318530717958647692f));
 		if (abs(pos_err) > kGuardLen / 2) { __syncthreads(); continue; }
 		symbol_pos -= pos_err;
@@ -473,12 +477,15 @@ static cudaError_t launch_acquire_t(const cfx *iq, int64_t iq_stride, int iq_len
 	return cudaGetLastError();
 }
 
-cudaError_t launch_acquire(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	return rate_scale == 2 ? launch_acquire_t<2>(iq, iq_stride, iq_len, det, det_count, skip, n_frames, st, soft_out, ac, s)
-		: launch_acquire_t<1>(iq, iq_stride, iq_len, det, det_count, skip, n_frames, st, soft_out, ac, s);
+	cudaError_t e = cudaSuccess;
+#define OFDMRX_CALL(R) e = launch_acquire_t<R>(iq, iq_stride, iq_len, det, det_count, skip, n_frames, st, soft_out, ac, s)
+	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
+#undef OFDMRX_CALL
+	return e;
 }
 
 cudaError_t launch_compact(const FrameState *st, int n_frames, int *cw_list, int *n_cw, cudaStream_t s)

@@ -91,26 +91,26 @@ __global__ void __launch_bounds__(kDmThreads) k_demod_fft(const cfx *iq, int64_t
 	for (int sym = tid; sym <= mi.rows; sym += kDmThreads) s.base[sym] = phasor_turns(turns * (double)(kSymLen + kPitch * sym)); // steps since the header symbol
 	__syncthreads();
 	// the samples of symbol sym + 1 are loaded into registers while symbol sym goes through its FFT passes
-	constexpr int kPerThread = kSymLen / kDmThreads; // 4 (8 at 16 kHz)
+	constexpr int kPerThread = (kSymLen + kDmThreads - 1) / kDmThreads; // 4 (8 / 23 / 24 at 16 / 44.1 / 48 kHz)
 	cfx nxt[kPerThread];
 #pragma unroll
 	for (int k = 0; k < kPerThread; ++k) {
-		const int idx = p0 + tid + k * kDmThreads;
-		nxt[k] = (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
+		const int i = tid + k * kDmThreads, idx = p0 + i;
+		nxt[k] = (i < kSymLen && idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
 	}
 	for (int sym = 0; sym <= mi.rows; ++sym) {
 		const cfx base = s.base[sym];
 #pragma unroll
 		for (int k = 0; k < kPerThread; ++k) {
 			const int i = tid + k * kDmThreads;
-			s.buf0[i] = cmul(nxt[k], cmul(base, s.rot[i]));
+			if (i < kSymLen) s.buf0[i] = cmul(nxt[k], cmul(base, s.rot[i]));
 		}
 		if (sym < mi.rows) {
 			const int w1 = p0 + kPitch * (sym + 1);
 #pragma unroll
 			for (int k = 0; k < kPerThread; ++k) {
-				const int idx = w1 + tid + k * kDmThreads;
-				nxt[k] = (idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
+				const int i = tid + k * kDmThreads, idx = w1 + i;
+				nxt[k] = (i < kSymLen && idx >= 0 && idx < iq_len) ? a[idx] : make_float2(0.f, 0.f);
 			}
 		}
 		__syncthreads();
@@ -677,12 +677,13 @@ static void launch_demod_fft_t(const cfx *iq, int64_t iq_stride, int iq_len, con
 	k_demod_fft<S><<<n_frames, kDmThreads, sizeof(FftShared<S>), s>>>(iq, iq_stride, iq_len, st, tw, cons_raw, yph);
 }
 
-cudaError_t launch_demod(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
+cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
 	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	if (rate_scale == 2) launch_demod_fft_t<2>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s);
-	else launch_demod_fft_t<1>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s);
+#define OFDMRX_CALL(R) launch_demod_fft_t<R>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s)
+	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
+#undef OFDMRX_CALL
 	// chains per window: one when there are windows enough to fill the GPU twice over, more (shorter) ones for small batches
 	int ts_smem;
 	theil_sen_grid(1, n_sm, &ts_smem);

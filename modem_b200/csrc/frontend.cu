@@ -132,13 +132,14 @@ __global__ void k_frontend_f32(const cfx *in, int64_t in_stride, const int32_t *
 // P[t] = sum_{k<640} c[t-k], R[t] = max(0.5 sum_{k<1280} e[t-k], 0.064), m[t] = |P|^2/R^2,
 // timing[t] = sum_{k<161} m[t-k]  (decode.cc:86-90 with search_pos = 2880, buffer_len = 8640).
 // Tile of kMtTile outputs; extended index j = t - t0 + kMtHalo addresses a[t0 - 5918 + j].
-constexpr int kMtThreads = 256, kMtTile = 2048;
+constexpr int kMtTile = 2048;
 template <int S>
 struct Mt {
 	using G = Geo<S>;
+	static constexpr int kThreads = G::kSymLen > 4096 ? 1024 : 256;                             // per-thread chunk stays ~11-20 samples
 	static constexpr int kHalo = 2 * G::kHalf + G::kMatchLen - 2, kExt = kMtTile + kHalo;      // 1439, 3487 at 8 kHz
-	static constexpr int kPer = (kExt + kMtThreads - 1) / kMtThreads;                           // 14
-	static constexpr int kPad = kMtThreads * kPer;                                              // 3584
+	static constexpr int kPer = (kExt + kThreads - 1) / kThreads;                               // 14
+	static constexpr int kPad = kThreads * kPer;                                                // 3584
 	// newest sample is buffer tap kBufferLen - 1: the correlator's taps search_pos + half and search_pos + symbol_len
 	// (decode.cc:86) are the stream samples t - kOffOld and t - kOffCur
 	static constexpr int kOffOld = G::kBufferLen - 1 - (G::kSearchPos + G::kHalf);              // 5119
@@ -157,17 +158,17 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane)
 }
 
 template <int S>
-__global__ void __launch_bounds__(kMtThreads) k_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples,
+__global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples,
 	int n_default, float *timing, int64_t timing_stride)
 {
-	constexpr int kMtHalo = Mt<S>::kHalo, kMtExt = Mt<S>::kExt, kMtPer = Mt<S>::kPer, kMtPad = Mt<S>::kPad;
+	constexpr int kMtHalo = Mt<S>::kHalo, kMtExt = Mt<S>::kExt, kMtPer = Mt<S>::kPer, kMtPad = Mt<S>::kPad, kMtThreads = Mt<S>::kThreads;
 	constexpr int kLag = Geo<S>::kHalf, kLen2 = Geo<S>::kSymLen, kBox = Geo<S>::kMatchLen;
 	extern __shared__ float sm[];
 	cfx *sa = reinterpret_cast<cfx *>(sm);              // [kMtPad] samples
 	float *sre = sm + 2 * kMtPad;                       // prefix of c.re, later prefix of m
 	float *sim = sre + kMtPad;                          // prefix of c.im
 	float *se = sim + kMtPad;                           // prefix of e
-	__shared__ float wtot[3][kMtThreads / 32];
+	__shared__ float wtot[3][Mt<S>::kThreads / 32];
 	const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = n_samples ? n_samples[f] : n_default;
 	const int t0 = blockIdx.x * kMtTile;
@@ -337,15 +338,14 @@ __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing,
 
 } // namespace
 
-cudaError_t launch_frontend(int rate_scale, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_frontend(int rate, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
 	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
 	if (format == 0) {
-		if (rate_scale == 2)
-			k_frontend_mono<2><<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc);
-		else
-			k_frontend_mono<1><<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc);
+#define OFDMRX_CALL(R) k_frontend_mono<R><<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc)
+		OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
+#undef OFDMRX_CALL
 	} else if (format == 1) {
 		dim3 g((iq_len + 1023) / 1024, n_frames);
 		k_frontend_iq16<<<g, 256, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len);
@@ -367,24 +367,28 @@ static cudaError_t launch_sync_metric_t(const cfx *iq, int64_t iq_stride, int iq
 		attr = true;
 	}
 	dim3 g((n_max + 1 + kMtTile - 1) / kMtTile, n_frames);
-	k_sync_metric<S><<<g, kMtThreads, smem, s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride);
+	k_sync_metric<S><<<g, Mt<S>::kThreads, smem, s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride);
 	return cudaGetLastError();
 }
 
-cudaError_t launch_sync_metric(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
+cudaError_t launch_sync_metric(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
 	float *timing, int64_t timing_stride, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	return rate_scale == 2 ? launch_sync_metric_t<2>(iq, iq_stride, iq_len, n_samples, n_default, n_max, n_frames, timing, timing_stride, s)
-		: launch_sync_metric_t<1>(iq, iq_stride, iq_len, n_samples, n_default, n_max, n_frames, timing, timing_stride, s);
+	cudaError_t e = cudaSuccess;
+#define OFDMRX_CALL(R) e = launch_sync_metric_t<R>(iq, iq_stride, iq_len, n_samples, n_default, n_max, n_frames, timing, timing_stride, s)
+	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
+#undef OFDMRX_CALL
+	return e;
 }
 
-cudaError_t launch_sync_detect(int rate_scale, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
 	Detection *det, int32_t *det_count, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-	if (rate_scale == 2) k_sync_detect<2><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count);
-	else k_sync_detect<1><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count);
+#define OFDMRX_CALL(R) k_sync_detect<R><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count)
+	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
+#undef OFDMRX_CALL
 	return cudaGetLastError();
 }
 

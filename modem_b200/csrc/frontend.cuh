@@ -15,7 +15,7 @@ struct Detection {
 
 struct FrontendConsts {
 	float dc_a, dc_b;  // BlockDC for 2*(1280+160) samples (decode.cc:386)
-	float reco, imco[kMaxHilbertCoeffs]; // Hilbert<21>: 5 coefficients, Hilbert<41>: 10
+	float reco, imco[kMaxHilbertCoeffs]; // Hilbert<21>: 5 coefficients ... Hilbert<125>: 31
 };
 
 struct AcquireConsts {
@@ -25,17 +25,17 @@ struct AcquireConsts {
 	const uint32_t *bch_rows;  // 71 x 8 words, systematic generator (decode.cc:378-384)
 };
 
-cudaError_t launch_frontend(int rate_scale, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_frontend(int rate, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
 	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s);
-cudaError_t launch_sync_metric(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
+cudaError_t launch_sync_metric(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
 	float *timing, int64_t timing_stride, cudaStream_t s);
-cudaError_t launch_sync_detect(int rate_scale, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
+cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
 	Detection *det, int32_t *det_count, cudaStream_t s);
-cudaError_t launch_acquire(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s);
 // three kernels: FFT + differential demodulation (cons_raw, phase errors yph), Theil-Sen per row (ts[row] = slope, yint,
 // precision), soft demapping (llr; cons = derotated constellation, optional)
-cudaError_t launch_demod(int rate_scale, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
+cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
 	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s);
 cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float *ts, int n_sm, cudaStream_t s);
 cudaError_t launch_compact(const FrameState *st, int n_frames, int *cw_list, int *n_cw, cudaStream_t s);

@@ -86,7 +86,7 @@ int main(int argc, char **argv)
 	}
 	int skip = argc > 3 ? std::atoi(argv[3]) : 0;
 	if (skip < 0) skip = 0;
-	if (w.rate != 8000 && w.rate != 16000) { // 44100/48000 are valid for the reference (decode.cc:590-606) but not built here yet
+	if (w.rate != 8000 && w.rate != 16000 && w.rate != 44100 && w.rate != 48000) { // decode.cc:590-606
 		std::cerr << "Unsupported sample rate." << std::endl;
 		return 1;
 	}

@@ -5,6 +5,9 @@
 // node schedule derived from it, MLS sequences (decode.cc:184,187,238,407), the BCH(255,71) generator
 // (decode.cc:378-384), Hilbert coefficients (decode.cc:172,193), FFT twiddles, CRC tables (decode.cc:197-198).
 #pragma once
+// run CALL(RATE) for the sample rate `rate` (one of the four the reference instantiates, decode.cc:590-606)
+#define OFDMRX_FOR_RATE(rate, CALL) \
+	switch (rate) { case 16000: CALL(16000); break; case 44100: CALL(44100); break; case 48000: CALL(48000); break; default: CALL(8000); break; }
 #include <cstdint>
 #include <vector>
 #ifndef __CUDACC__
@@ -16,23 +19,23 @@
 
 namespace ofdmrx {
 
-// ---- sample-rate geometry (decode.cc:171-173,188-189,196; SchmidlCox template arguments decode.cc:41-42) -------------
-// S = rate / 8000.  Built: S = 1 (8000 Hz) and S = 2 (16000 Hz); 44100 / 48000 Hz need radix-3/7 FFT passes (7056, 7680).
-template <int S>
+// ---- sample-rate geometry (decode.cc:171-173,188-189,196,590-606; SchmidlCox template arguments decode.cc:41-42) ---
+// RATE in {8000, 16000, 44100, 48000}: symbol lengths 1280, 2560, 7056 (= 2^4 3^2 7^2), 7680 (= 2^9 3 5).
+template <int RATE>
 struct Geo {
-	static constexpr int kRate = 8000 * S;
-	static constexpr int kSymLen = 1280 * S, kGuardLen = kSymLen / 8, kPitch = kSymLen + kGuardLen, kHalf = kSymLen / 2;
+	static constexpr int kRate = RATE;
+	static constexpr int kSymLen = (1280 * RATE) / 8000, kGuardLen = kSymLen / 8, kPitch = kSymLen + kGuardLen, kHalf = kSymLen / 2;
 	static constexpr int kBufferLen = 6 * kPitch;               // 8640 at 8 kHz
 	static constexpr int kSearchPos = kBufferLen - 4 * kPitch;  // 2880
 	static constexpr int kMatchLen = kGuardLen | 1, kMatchDel = (kMatchLen - 1) / 2; // 161, 80
-	static constexpr int kFilterLen = ((21 * S) & ~3) | 1;      // 21 (41 at 16 kHz)
+	static constexpr int kFilterLen = (((21 * RATE) / 8000) & ~3) | 1; // 21, 41, 113, 125
 };
-constexpr int kRate = Geo<1>::kRate;
-constexpr int kSymLen = Geo<1>::kSymLen, kGuardLen = Geo<1>::kGuardLen, kPitch = Geo<1>::kPitch, kHalf = Geo<1>::kHalf;
-constexpr int kBufferLen = Geo<1>::kBufferLen, kSearchPos = Geo<1>::kSearchPos;
-constexpr int kMatchLen = Geo<1>::kMatchLen, kMatchDel = Geo<1>::kMatchDel;
-constexpr int kFilterLen = Geo<1>::kFilterLen;
-constexpr int kMaxHilbertCoeffs = 10; // (41 - 1) / 4
+constexpr int kRate = Geo<8000>::kRate;
+constexpr int kSymLen = Geo<8000>::kSymLen, kGuardLen = Geo<8000>::kGuardLen, kPitch = Geo<8000>::kPitch, kHalf = Geo<8000>::kHalf;
+constexpr int kBufferLen = Geo<8000>::kBufferLen, kSearchPos = Geo<8000>::kSearchPos;
+constexpr int kMatchLen = Geo<8000>::kMatchLen, kMatchDel = Geo<8000>::kMatchDel;
+constexpr int kFilterLen = Geo<8000>::kFilterLen;
+constexpr int kMaxHilbertCoeffs = 31; // (125 - 1) / 4
 constexpr int kConsCols = 432, kConsRows = 50, kModBits = 3, kConsCnt = 21600, kConsBits = 64800;
 constexpr int kCodeOrder = 16, kCodeLen = 65536, kMesgBits = 43808, kDataBits = 43040, kCrcBits = 43072, kDataBytes = 5380;
 constexpr int kHdrBits = 255, kHdrK = 71;

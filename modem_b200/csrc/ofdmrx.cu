@@ -22,7 +22,7 @@ static_assert(sizeof(ofdmrx_frame_status) == sizeof(FrameState), "ABI status str
 
 struct ofdmrx_handle {
 	int device = 0, n_sm = 0;
-	int rate_scale = 1; // sample rate / 8000 (1 or 2)
+	int rate = 8000;    // 8000, 16000, 44100 or 48000 (decode.cc:590-606)
 	int max_frames = 0, max_samples = 0, iq_len = 0;
 	bool keep_taps = false;
 	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0, scl_stream_level = 17;
@@ -98,11 +98,11 @@ int ensure_scl_scratch(ofdmrx_handle *h)
 
 extern "C" {
 
-const char *ofdmrx_version(void) { return "ofdmrx 0.2 (sm_100a; modes 6-13 @ 8 kHz; SCL L=8)"; }
+const char *ofdmrx_version(void) { return "ofdmrx 0.3 (sm_100a; modes 6-13 @ 8/16/44.1/48 kHz; SCL L=8)"; }
 
 int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int max_samples)
 {
-	if (!out || (rate_hz != 8000 && rate_hz != 16000) || max_frames < 1 || max_samples < 1) return -22; // 44100 / 48000: not built
+	if (!out || (rate_hz != 8000 && rate_hz != 16000 && rate_hz != 44100 && rate_hz != 48000) || max_frames < 1 || max_samples < 1) return -22;
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) {
 		std::fprintf(stderr, "ofdmrx: no CUDA device %d (there is no CPU fallback)\n", device);
@@ -118,7 +118,7 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	ofdmrx_handle *h = new (std::nothrow) ofdmrx_handle;
 	if (!h) return -12;
 	h->device = device;
-	h->rate_scale = rate_hz / 8000;
+	h->rate = rate_hz;
 	h->n_sm = prop.multiProcessorCount;
 	h->max_frames = max_frames;
 	h->max_samples = max_samples;
@@ -148,8 +148,8 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	}
 	std::vector<uint32_t> bch = bch_generator_rows();
 	std::vector<uint8_t> mls1 = mls_bits(0b100101011, 255);
-	const int sym_len = kSymLen * h->rate_scale, half = sym_len / 2, pitch = kPitch * h->rate_scale;
-	const int filter_len = h->rate_scale == 2 ? Geo<2>::kFilterLen : Geo<1>::kFilterLen;
+	const int sym_len = (1280 * rate_hz) / 8000, half = sym_len / 2, pitch = sym_len + sym_len / 8;
+	const int filter_len = (((21 * rate_hz) / 8000) & ~3) | 1;
 	std::vector<float> tw1280 = twiddles(sym_len, -1), tw640 = twiddles(half, -1), kern = mls0_kernel(half);
 	float reco;
 	std::vector<float> imco = hilbert_coeffs(filter_len, &reco);
@@ -272,17 +272,17 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 	float *timing = h->d_timing + (size_t)f0 * L;
 	const int32_t *ns = d_ns ? d_ns + f0 : nullptr;
 	if (record) cudaEventRecord(h->ev[0], s);
-	OFDMRX_CUDA_TRY(launch_frontend(h->rate_scale, format, d_samples, stride, ns, n_default, nf, iq, h->iq_len, h->iq_len, h->fc, s));
+	OFDMRX_CUDA_TRY(launch_frontend(h->rate, format, d_samples, stride, ns, n_default, nf, iq, h->iq_len, h->iq_len, h->fc, s));
 	if (record) cudaEventRecord(h->ev[1], s);
-	OFDMRX_CUDA_TRY(launch_sync_metric(h->rate_scale, iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, s));
+	OFDMRX_CUDA_TRY(launch_sync_metric(h->rate, iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, s));
 	if (record) cudaEventRecord(h->ev[2], s);
-	OFDMRX_CUDA_TRY(launch_sync_detect(h->rate_scale, timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, s));
+	OFDMRX_CUDA_TRY(launch_sync_detect(h->rate, timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, s));
 	if (record) cudaEventRecord(h->ev[3], s);
 	AcquireConsts ac{h->d_tw1280, h->d_tw640, h->d_kern, h->d_mls1, h->d_bch};
-	OFDMRX_CUDA_TRY(launch_acquire(h->rate_scale, iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
+	OFDMRX_CUDA_TRY(launch_acquire(h->rate, iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
 		h->d_soft + (size_t)f0 * 256, ac, s));
 	if (record) cudaEventRecord(h->ev[4], s);
-	OFDMRX_CUDA_TRY(launch_demod(h->rate_scale, iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kMaxCons,
+	OFDMRX_CUDA_TRY(launch_demod(h->rate, iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kMaxCons,
 		h->d_y + (size_t)f0 * kMaxCons, h->keep_taps ? h->d_cons + (size_t)f0 * kMaxCons : nullptr, h->d_ts + (size_t)f0 * kMaxRows * 3,
 		h->d_llr + (size_t)f0 * kCodeLen, h->n_sm, s));
 	if (record) cudaEventRecord(h->ev[5], s);

@@ -202,10 +202,10 @@ def test_pipeline_other_modes(oracle, mode):
         rxm.close()
 
 
-def _compare_frames_16k(rxh, oracle, pcm, channels, sent):
+def _compare_frames_rate(rxh, oracle, pcm, channels, sent, rate):
     payload, st = rxh.decode(pcm, channels=channels)
     for i in range(pcm.shape[0]):
-        ost, opay, tp = oracle.decode(pcm[i], channels=channels, rate=16000)
+        ost, opay, tp = oracle.decode(pcm[i], channels=channels, rate=rate)
         s = st[i]
         assert s["status"] == ost, (i, s["status"], ost)
         assert (s["sc_pos"], s["shift"]) == (tp.sc_pos, tp.shift) and abs(int(s["pos_err"]) - tp.pos_err) <= 1
@@ -215,20 +215,21 @@ def _compare_frames_16k(rxh, oracle, pcm, channels, sent):
     return st
 
 
-@pytest.mark.parametrize("mode", [6, 9, 12])
-def test_pipeline_16khz(oracle, mode):
-    """16000 Hz (decode.cc:171-173,594-596): symbol length 2560, guard 320, Hilbert<41>, correlator length 1280,
-    FFT-2560 / FFT-1280 — clean mono and impaired analytic frames against the oracle at the same rate."""
+@pytest.mark.parametrize("rate,mode", [(16000, 6), (16000, 9), (16000, 12), (44100, 6), (44100, 13), (48000, 6), (48000, 10)])
+def test_pipeline_other_sample_rates(oracle, rate, mode):
+    """16000 / 44100 / 48000 Hz (decode.cc:171-173,590-606): symbol lengths 2560 / 7056 / 7680 (FFT radices 2, 3, 4, 5, 7),
+    Hilbert<41/113/125>, correlator lengths 1280 / 3528 / 3840 — clean mono and impaired analytic frames against the
+    oracle at the same rate."""
     import modem_b200 as M
-    stride = oracle.frame_samples(mode, 16000) + 128
-    pcm, ns, sent = oracle.encode_batch(4, seed0=1600 + mode, rate=16000, mode=mode, stride=stride)
-    rxh = M.Receiver(max_frames=4, max_samples=stride, rate=16000)
+    stride = oracle.frame_samples(mode, rate) + 512
+    pcm, ns, sent = oracle.encode_batch(3, seed0=rate // 10 + mode, rate=rate, mode=mode, stride=stride)
+    rxh = M.Receiver(max_frames=3, max_samples=stride, rate=rate)
     try:
-        st = _compare_frames_16k(rxh, oracle, pcm, 1, sent)
+        st = _compare_frames_rate(rxh, oracle, pcm, 1, sent, rate)
         assert (st["status"] == 0).all() and (st["flips"] == 0).all()
         imp = oracle.impair(multipath=True, cfo_hz=91.3, sfo_ppm=80, awgn_db=-28, seed=16 + mode)
-        pcm, ns, sent = oracle.encode_batch(4, seed0=1700 + mode, rate=16000, channels=2, mode=mode, imp=imp, stride=stride)
-        st = _compare_frames_16k(rxh, oracle, pcm, 2, sent)
+        pcm, ns, sent = oracle.encode_batch(3, seed0=rate // 10 + 100 + mode, rate=rate, channels=2, mode=mode, imp=imp, stride=stride)
+        st = _compare_frames_rate(rxh, oracle, pcm, 2, sent, rate)
         assert (st["status"] == 0).all()
     finally:
         rxh.close()
