@@ -389,6 +389,12 @@ def test_decode_cli_matches_reference_contract(oracle, tmp_path):
     q = subprocess.run([ref, str(tmp_path / "cpu.dat"), wav], capture_output=True)
     assert r.returncode == 0 and (tmp_path / "gpu.dat").read_bytes() == (tmp_path / "cpu.dat").read_bytes() == data[1]
     assert b"oper mode: 13" in r.stderr and b"call sign:    N0CALL" in r.stderr and b"bit flips: 0" in r.stderr
+    # another sample rate through the same command line (48 kHz, 2-channel: symbol length 7680)
+    subprocess.run([enc, wav, "48000", "16", "2", "3000", "7", "CQ", str(tmp_path / "in0.dat")], check=True)
+    r = subprocess.run([dec, str(tmp_path / "gpu.dat"), wav], capture_output=True)
+    q = subprocess.run([ref, str(tmp_path / "cpu.dat"), wav], capture_output=True)
+    assert r.returncode == 0 and (tmp_path / "gpu.dat").read_bytes() == (tmp_path / "cpu.dat").read_bytes() == data[0]
+    assert b"oper mode: 7" in r.stderr and b"coarse cfo: 3000" in r.stderr and b"bit flips: 0" in r.stderr
     r = subprocess.run([dec], capture_output=True)
     assert r.returncode == 1 and b"usage:" in r.stderr
     raw = bytearray(open(wav, "rb").read())
