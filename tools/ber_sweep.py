@@ -20,18 +20,22 @@ import oracle_lib as O  # noqa: E402
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     n = int(os.environ.get("N_PER_POINT", "1000"))
+    mode, rate = int(os.environ.get("MODE", "6")), int(os.environ.get("RATE", "8000"))
     lo, hi, step = float(os.environ.get("DB_LO", "-40")), float(os.environ.get("DB_HI", "-10")), float(os.environ.get("DB_STEP", "1"))
     levels = list(np.arange(lo, hi + 1e-9, step))
-    fine = [x for x in np.arange(-17.0, -12.99, 0.25) if x not in levels]   # resolve the waterfall
-    levels = sorted(set(levels) | set(fine))
-    rx = M.Receiver(max_frames=n)
+    if os.environ.get("FINE", "1") != "0":
+        fine = [x for x in np.arange(-17.0, -12.99, 0.25) if x not in levels]   # resolve the waterfall (mode 6)
+        levels = sorted(set(levels) | set(fine))
+    stride = O.frame_samples(mode, rate)
+    rx = M.Receiver(max_frames=n, max_samples=stride, rate=rate)
     cores = os.cpu_count() or 1
     rows = []
     for db in levels:
         t0 = time.time()
-        pcm, ns, sent = O.encode_batch(n, seed0=int(1e6 + 1000 * (db + 100)), channels=2, imp=O.impair(awgn_db=float(db), seed=int(7e5 + 100 * (db + 100))))
+        pcm, ns, sent = O.encode_batch(n, seed0=int(1e6 + 1000 * (db + 100)), channels=2, rate=rate, mode=mode, stride=stride,
+                                       imp=O.impair(awgn_db=float(db), seed=int(7e5 + 100 * (db + 100))))
         gp, gs = rx.decode(pcm, channels=2)
-        ost, op = O.decode_batch(pcm, channels=2, nthreads=cores)
+        ost, op = O.decode_batch(pcm, channels=2, rate=rate, nthreads=cores)
         bits = n * 43040
         g_err = int(np.unpackbits(gp ^ sent, axis=1).sum())
         o_err = int(np.unpackbits(op ^ sent, axis=1).sum())
@@ -47,7 +51,7 @@ def main():
     os.makedirs(out, exist_ok=True)
     json.dump({"n_per_point": n, "rows": rows}, open(os.path.join(out, "ber_sweep_%s.json" % tag), "w"), indent=1)
     with open(os.path.join(out, "ber_sweep_%s.md" % tag), "w") as f:
-        f.write("# AWGN sweep (BASELINE configs[3]): B200 path vs CPU oracle on identical windows, %d windows/point\n\n" % n)
+        f.write("# AWGN sweep (BASELINE configs[3]): B200 path vs CPU oracle on identical windows, mode %d at %d Hz, %d windows/point\n\n" % (mode, rate, n))
         f.write("| AWGN dB | GPU FER | CPU FER | GPU BER | CPU BER | both decode but differ | only GPU | only CPU |\n|---|---|---|---|---|---|---|---|\n")
         for r in rows:
             f.write("| %.2f | %.4f | %.4f | %.3e | %.3e | %d | %d | %d |\n" % (r["awgn_db"], r["gpu_fer"], r["cpu_fer"], r["gpu_ber"], r["cpu_ber"],

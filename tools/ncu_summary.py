@@ -41,7 +41,7 @@ def full(rep, out, frames):
     with open(out, "w") as f:
         f.write("# ncu --set full --clock-control none summary of %s (%d windows in the captured batch)\n\n" % (os.path.basename(rep), frames))
         for r in rows[2:]:
-            name = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
+            name = r[idx["Kernel Name"]].split("(")[0].split("::")[-1].split("<")[0]
             f.write("## %s\n\n| metric | value | unit |\n|---|---|---|\n" % name)
             for k in KEYS:
                 if k in idx:
@@ -60,7 +60,7 @@ def launches(csvf, out):
     agg = {}
     for r in rows[1:]:
         try:
-            name = r[idx["Kernel Name"]].split("(")[0].split("::")[-1]
+            name = r[idx["Kernel Name"]].split("(")[0].split("::")[-1].split("<")[0]
             v = float(r[idx["Metric Value"]])
             unit = r[idx["Metric Unit"]]
         except (ValueError, KeyError, IndexError):
