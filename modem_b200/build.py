@@ -14,6 +14,7 @@ OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libofdmrx.so")
 DECODE = os.path.join(PKG, "decode")
 HOSTTEST = os.path.join(OBJ, "libhosttest.so")
+FFTHOST = os.path.join(OBJ, "libffthost.so")   # test helper: the product's FFT plans compiled for the host
 
 CU = ["polar.cu", "frontend.cu", "acquire.cu", "demod.cu", "ofdmrx.cu"]
 CC = ["host_tables.cc"]
@@ -65,6 +66,10 @@ def build(force=False, verbose=False):
     emu = os.path.join(ROOT, "tests", "scl_emulator.cc")
     if os.path.exists(emu) and (force or _stale(HOSTTEST, [emu, os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "host_tables.h")])):
         _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", emu, os.path.join(CSRC, "host_tables.cc"), "-o", HOSTTEST], log)
+    ffth = os.path.join(ROOT, "tests", "fft_host.cu")
+    if os.path.exists(ffth) and (force or _stale(FFTHOST, [ffth, os.path.join(CSRC, "fft.cuh"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "host_tables.cc")])):
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC", "-shared", ffth,
+              os.path.join(CSRC, "host_tables.cc"), "-o", FFTHOST], log)
     with open(os.path.join(OBJ, "build.log"), "a") as f:
         f.write("\n".join(log))
     if verbose:

@@ -17,10 +17,10 @@ namespace ofdmrx {
 	} while (0)
 
 typedef float2 cfx;
-__device__ __forceinline__ cfx cmul(cfx a, cfx b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ cfx cmulc(cfx a, cfx b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a * conj(b)
-__device__ __forceinline__ cfx cadd(cfx a, cfx b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cfx csub(cfx a, cfx b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cfx cmul(cfx a, cfx b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__host__ __device__ __forceinline__ cfx cmulc(cfx a, cfx b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a * conj(b)
+__host__ __device__ __forceinline__ cfx cadd(cfx a, cfx b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cfx csub(cfx a, cfx b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float cnorm(cfx a) { return a.x * a.x + a.y * a.y; }
 // decode.cc:62-70 / 227-235: differential demodulation with erasure
 __device__ __forceinline__ cfx demod_or_erase(cfx curr, cfx prev)

@@ -8,14 +8,20 @@
 
 namespace ofdmrx {
 
-template <int R> __device__ __forceinline__ void bfly(cfx *v);
-template <> __device__ __forceinline__ void bfly<2>(cfx *v)
+#ifdef __CUDACC__
+#define OFDMRX_HD __host__ __device__ __forceinline__
+#else
+#define OFDMRX_HD inline
+#endif
+
+template <int R> OFDMRX_HD void bfly(cfx *v);
+template <> OFDMRX_HD void bfly<2>(cfx *v)
 {
 	const cfx a = v[0], b = v[1];
 	v[0] = cadd(a, b);
 	v[1] = csub(a, b);
 }
-template <> __device__ __forceinline__ void bfly<4>(cfx *v)
+template <> OFDMRX_HD void bfly<4>(cfx *v)
 {
 	const cfx t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
 	const cfx t3 = make_float2(d.y, -d.x); // d * (-j)
@@ -24,7 +30,7 @@ template <> __device__ __forceinline__ void bfly<4>(cfx *v)
 	v[2] = csub(t0, t2);
 	v[3] = csub(t1, t3);
 }
-template <> __device__ __forceinline__ void bfly<5>(cfx *v)
+template <> OFDMRX_HD void bfly<5>(cfx *v)
 {
 	const float c1 = 0.30901699437494742f, s1 = 0.95105651629515357f, c2 = -0.80901699437494742f, s2 = 0.58778525229247313f;
 	const cfx a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]), b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
@@ -40,7 +46,7 @@ template <> __device__ __forceinline__ void bfly<5>(cfx *v)
 	v[3] = make_float2(r2.x - i2.y, r2.y + i2.x);
 }
 
-template <> __device__ __forceinline__ void bfly<3>(cfx *v)
+template <> OFDMRX_HD void bfly<3>(cfx *v)
 {
 	const float h = 0.86602540378443864676f; // sin(2 pi / 3)
 	const cfx t1 = cadd(v[1], v[2]), d = csub(v[1], v[2]);
@@ -50,7 +56,7 @@ template <> __device__ __forceinline__ void bfly<3>(cfx *v)
 	v[1] = cadd(t2, sd);
 	v[2] = csub(t2, sd);
 }
-template <> __device__ __forceinline__ void bfly<7>(cfx *v)
+template <> OFDMRX_HD void bfly<7>(cfx *v)
 {
 	// cos / sin of 2 pi k / 7, k = 1, 2, 3
 	const float c1 = 0.62348980185873353053f, c2 = -0.22252093395631440429f, c3 = -0.90096886790241912624f;
@@ -72,7 +78,7 @@ template <> __device__ __forceinline__ void bfly<7>(cfx *v)
 
 // one decimation-in-time Stockham pass: combines R sub-transforms of length m into length m*R
 template <int N, int R>
-__device__ __forceinline__ void fft_pass(const cfx *src, cfx *dst, int m, const cfx *tw, int tid, int nthr)
+OFDMRX_HD void fft_pass(const cfx *src, cfx *dst, int m, const cfx *tw, int tid, int nthr)
 {
 	const int l = N / (m * R);
 	for (int b = tid; b < N / R; b += nthr) {
@@ -99,14 +105,16 @@ template <> struct FftPlan<3840> { static constexpr int n = 6; static constexpr 
 template <> struct FftPlan<7680> { static constexpr int n = 7; static constexpr int r[7] = {4, 4, 4, 4, 2, 3, 5}; };
 
 template <int N, int P, int M>
-__device__ __forceinline__ cfx *fft_run(cfx *src, cfx *dst, const cfx *tw, int tid, int nthr)
+OFDMRX_HD cfx *fft_run(cfx *src, cfx *dst, const cfx *tw, int tid, int nthr)
 {
 	if constexpr (P == FftPlan<N>::n) {
 		return src;
 	} else {
 		constexpr int R = FftPlan<N>::r[P];
 		fft_pass<N, R>(src, dst, M, tw, tid, nthr);
+#ifdef __CUDA_ARCH__
 		__syncthreads();
+#endif
 		return fft_run<N, P + 1, M * R>(dst, src, tw, tid, nthr);
 	}
 }
@@ -114,7 +122,7 @@ __device__ __forceinline__ cfx *fft_run(cfx *src, cfx *dst, const cfx *tw, int t
 // in: buf0 (N values), scratch buf1; returns the buffer holding the result (buf1 after an odd number of passes, else buf0).
 // All threads of the CTA must call.
 template <int N>
-__device__ __forceinline__ cfx *fft_fwd(cfx *buf0, cfx *buf1, const cfx *tw, int tid, int nthr)
+OFDMRX_HD cfx *fft_fwd(cfx *buf0, cfx *buf1, const cfx *tw, int tid, int nthr)
 {
 	return fft_run<N, 0, 1>(buf0, buf1, tw, tid, nthr);
 }

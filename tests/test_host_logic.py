@@ -43,6 +43,23 @@ def test_schedule_structure(hostlib):
     assert (depth[(op != 0) & (op != 1) & ~top] == 1).all()
 
 
+def test_fft_plans_of_all_sample_rates():
+    """The product's Stockham passes and radix-2/3/4/5/7 butterflies (modem_b200/csrc/fft.cuh, compiled for the host by
+    tests/fft_host.cu) against numpy for the symbol and half-symbol lengths of 8 / 16 / 44.1 / 48 kHz."""
+    import os
+    from modem_b200 import build
+    build.build()
+    lib = C.CDLL(build.FFTHOST)
+    rng = np.random.default_rng(1)
+    for n in (640, 1280, 2560, 3528, 3840, 7056, 7680):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        out = np.zeros(n, np.complex64)
+        assert lib.fft_host(n, _p(x), _p(out)) == 0
+        ref = np.fft.fft(x.astype(np.complex128))
+        assert np.abs(out - ref).max() / np.abs(ref).max() < 1e-6, n
+    assert lib.fft_host(1000, _p(x), _p(out)) == -1
+
+
 def test_tables_match_oracle(oracle, hostlib):
     rows = np.zeros(71 * 8, np.uint32)
     hostlib.host_bch_rows(_p(rows))
