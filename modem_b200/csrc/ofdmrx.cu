@@ -30,6 +30,8 @@ struct ofdmrx_handle {
 	// constants
 	uint32_t *d_tbl[2] = {}, *d_scr = nullptr, *d_bch = nullptr; // [code table]: frozen set | message offsets | SCL schedule
 	int polar_table = 0; // table used by ofdmrx_polar_decode (option "polar_table")
+	bool scl_top = true;  // schedules use TOP ops: alpha levels 14 and 15 are never stored
+	size_t scl_a_stride = 0; // floats of alpha scratch per resident warp
 	uint8_t *d_mls1 = nullptr;
 	cfx *d_tw1280 = nullptr, *d_tw640 = nullptr, *d_kern = nullptr;
 	FrontendConsts fc;
@@ -89,7 +91,10 @@ int ensure_scl_scratch(ofdmrx_handle *h)
 	while (h->scl_grid > 1 && (h->scl_grid - 1) * (kSclThreads / 32) >= need_warps) { --h->scl_grid; }
 	warps = h->scl_grid * (kSclThreads / 32);
 	h->scl_warps = warps;
-	if (int r = dev_alloc(&h->d_A, (size_t)warps * kSclWarpFloats)) return r;
+	// per warp: alpha levels 5.. back to back ([quad][lane] float4); with TOP ops levels 14 and 15 are never touched, so a
+	// warp needs 2.1 MB instead of 8.4 MB
+	h->scl_a_stride = h->scl_top ? scl_off(14) : kSclWarpFloats;
+	if (int r = dev_alloc(&h->d_A, (size_t)warps * h->scl_a_stride)) return r;
 	if (int r = dev_alloc(&h->d_B, (size_t)warps * kSclWarpWords)) return r;
 	return 0;
 }
@@ -130,6 +135,7 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (const char *e = std::getenv("OFDMRX_SCL_STREAM_LEVEL")) h->scl_stream_level = std::atoi(e);
 	bool top = true; // levels 16..14 recomputed from the channel LLRs (OP_TOP); OFDMRX_SCL_TOP=0 stores them instead
 	if (const char *e = std::getenv("OFDMRX_SCL_TOP")) top = std::atoi(e) != 0;
+	h->scl_top = top;
 	std::vector<uint32_t> msg_off[2];
 	for (int tb = 0; tb < 2; ++tb) { // code tables of modes 6..9 and 10..13 (decode.cc:310-311,342-343)
 		h->h_frozen[tb] = make_frozen(kCodeOrder, tb ? 64512 : 64800, kCrcBits);
@@ -137,6 +143,9 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 		msg_off[tb].resize(2048);
 		uint32_t acc = 0;
 		for (int w = 0; w < 2048; ++w) { msg_off[tb][w] = acc; acc += 32 - __builtin_popcount(h->h_frozen[tb][w]); }
+		bool has_top = false; // the generator falls back to stored levels if a rate-0 node reached the top level
+		for (uint32_t op : h->h_ops[tb]) has_top |= scl_op(op) == OP_TOP;
+		if (!has_top) h->scl_top = false;
 	}
 	std::vector<uint32_t> scr(kDataBytes / 4, 0);
 	{
@@ -299,7 +308,7 @@ static int run_scl(ofdmrx_handle *h, int nf, cudaStream_t s)
 	cudaEventRecord(h->ev[6], s);
 	SclParams p{};
 	p.llr = h->d_llr; p.cw_list = h->d_cwlist; p.n_cw_ptr = h->d_ncw; p.A = h->d_A; p.B = h->d_B;
-	p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1];
+	p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1]; p.a_stride = h->scl_a_stride;
 	p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr; p.stream_level = h->scl_stream_level;
 	OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
 	cudaEventRecord(h->ev[7], s);
@@ -385,7 +394,7 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
 		SclParams p{};
 		p.llr = h->d_llr; p.cw_list = nullptr; p.n_cw_ptr = nullptr; p.A = h->d_A; p.B = h->d_B;
 		p.n_cw[h->polar_table] = nf; p.n_cw[1 - h->polar_table] = 0;
-		p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1];
+		p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1]; p.a_stride = h->scl_a_stride;
 		p.payload = h->d_payload; p.st = h->d_st;
 		p.xbits = xbits ? h->d_xbits : nullptr;
 		p.stream_level = h->scl_stream_level;

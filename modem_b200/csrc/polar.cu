@@ -5,10 +5,12 @@
 //   * one list lane per THREAD, one codeword per 8 threads, four codewords per warp.  Every codeword walks the
 //     same precomputed op schedule (host_tables.cc: the frozen set is fixed), so a warp never diverges and the
 //     only cross-thread traffic is 8-wide shuffles (lane permutation after a fork, fork ranking).
-//   * alpha (LLR) buffers of tree levels 5..15 live in a per-warp HBM/L2 scratch laid out [quad][warp lane][4]
+//   * alpha (LLR) buffers of tree levels 6..13 live in a per-warp HBM/L2 scratch laid out [quad][warp lane][4]
 //     (a quad = 4 consecutive tree positions) so that every warp access is 512 coalesced bytes of 128-bit loads,
-//     also when a thread reads through the lane map;
-//     levels 0..4 (a 32-leaf "word") are fully unrolled and live in registers.
+//     also when a thread reads through the lane map; level 5 lives in shared memory; levels 14..16 are never stored
+//     (TOP ops recompute level 13 from the lane-shared channel LLRs); levels 0..4 (a 32-leaf "word") are fully
+//     unrolled and live in registers.
+//   * two code tables (modes 6..9 / 10..13): one op schedule each; the four codewords of a warp share a table.
 //   * partial sums (beta) are bit-packed, 32 tree positions per word; at the root they ARE the re-encoded
 //     codeword, whose non-frozen positions are the systematic message (decode.cc:254-261) — no message/map
 //     trace-back is stored.
@@ -215,20 +217,15 @@ __device__ __forceinline__ void word32(SclCtx &c)
 	c.ret = __shfl_sync(FULL, l.ret, srcr);
 }
 
-// L2 cache policy per tree level: the big alpha levels stream through (evict-first) so that they do not push the small,
-// frequently re-read levels out of the 126 MB L2; the policy is a runtime operand, so the code is not duplicated.
+// L2 cache policy for the stores of the TOP ops (levels 13 and 12 stream through: evict-first keeps them from pushing
+// the small, frequently re-read levels out of the 126 MB L2); the policy is a runtime operand.  The F/G ops use plain
+// generic accesses (their lowest level lives in shared memory; hints measured no gain there).
 __device__ __forceinline__ uint64_t l2_policy(bool stream)
 {
 	uint64_t p;
 	if (stream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
 	else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
 	return p;
-}
-__device__ __forceinline__ float4 ld_pol(const float4 *ptr, uint64_t pol)
-{
-	float4 v;
-	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol) : "memory");
-	return v;
 }
 __device__ __forceinline__ void st_pol(float4 *ptr, float4 v, uint64_t pol)
 {
@@ -272,7 +269,8 @@ constexpr int kSclPairsInFlight = OFDMRX_SCL_PAIRS; // quad pairs loaded per thr
 // F or G at level l fused with the D-1 F steps that follow it down the left spine (host_tables.cc: depth field).
 // One iteration takes the 2^(D-1) quad pairs of the parent whose results meet again in the chained F steps, so the
 // intermediate levels are produced in registers, written once (the later G needs them) and never re-read by an F.
-// 8 x 128-bit loads are in flight per thread for every D.
+// 8 x 128-bit loads are in flight per thread for every D (D <= kSclMaxFuse = 2: deeper chains cost registers and
+// instruction-cache footprint and measured slower).
 template <int D, bool IS_G>
 __device__ __forceinline__ void fused_op(float4 *A, float4 *S, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32)
 {
@@ -281,7 +279,6 @@ __device__ __forceinline__ void fused_op(float4 *A, float4 *S, const float4 *C4,
 	const float4 *P = lvl_ptr(A, S, l > 15 ? 15 : l);
 	float4 *D1 = lvl_ptr(A, S, l - 1);
 	float4 *D2 = lvl_ptr(A, S, D >= 2 ? l - 2 : l - 1);
-	float4 *D3 = lvl_ptr(A, S, D >= 3 ? l - 3 : l - 1);
 	const bool root = l == 16;
 	for (int q0 = 0; q0 < step; q0 += 8) {
 		uint32_t bw[M];
@@ -317,7 +314,6 @@ __device__ __forceinline__ void fused_op(float4 *A, float4 *S, const float4 *C4,
 						v2[m] = f_op4(v1[m], v1[m + M / 2]);
 						D2[(q0 + k + u + m * step) * 32 + lane32] = v2[m];
 					}
-					if constexpr (D >= 3) D3[(q0 + k + u) * 32 + lane32] = f_op4(v2[0], v2[1]);
 				}
 			}
 		}
@@ -392,7 +388,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 	const int lane32 = threadIdx.x & 31;
 	const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const int n_warps = (gridDim.x * blockDim.x) >> 5;
-	float4 *A = reinterpret_cast<float4 *>(p.A + (size_t)warp_global * kSclWarpFloats);
+	float4 *A = reinterpret_cast<float4 *>(p.A + (size_t)warp_global * p.a_stride);
 	uint32_t *B = p.B + (size_t)warp_global * kSclWarpWords;
 	SclCtx c;
 	c.t = lane32 & 7;

@@ -20,7 +20,8 @@ struct SclParams {
 	                         // multiple of 4 on those of table 1 (modes 10..13); nullptr = identity (one table)
 	int n_cw[2];             // codewords per code table, or read from n_cw_ptr (device, 2 ints) when that is set
 	const int *n_cw_ptr;
-	float *A;                // scratch: resident warps x kSclWarpFloats
+	float *A;                // scratch: resident warps x a_stride floats
+	size_t a_stride;         // kSclWarpFloats, or scl_off(14) when the schedules use TOP ops (levels 14, 15 never stored)
 	uint32_t *B;             // scratch: resident warps x kSclWarpWords
 	const uint32_t *tbl[2];  // per code table, one array: frozen set (2048 words), number of non-frozen indices before each
 	                         // word (2048), op schedule (host_tables.cc) — one base pointer keeps the kernel's registers down
