@@ -140,11 +140,10 @@ constexpr int kTsLaneCap = kTsCap / 32; // ... as 32 private sub-queues
 constexpr int kTsPad = kMaxCols;       // 16 x 32 columns, the tail beyond the mode's carrier count holds +inf
 constexpr int kTsRows = kTsPad / 32;   // up to 16 row blocks: lane L owns carriers i = 32 R + L
 
-constexpr int kTsCandCap = 1536;       // in-bracket quotients kept for the final select
+constexpr int kTsCandCap = 1280;       // in-bracket quotients kept for the final select
 
 struct TsSweep {                       // per sweep: every 32-column chunk sorted by u
 	float2 suv[kTsPad];                // (u, v) of the chunk's columns in ascending u
-	uint32_t pm[kTsRows * 33 + 2];     // pm[33 K + p]: set of in-chunk column offsets among the first p sorted entries
 	uint16_t sj[kTsPad];               // original column of each sorted entry
 };
 struct TsShared {
@@ -159,6 +158,7 @@ struct TsShared {
 	};
 };
 static_assert(sizeof(TsSweep) >= kTsCandCap * sizeof(int) && sizeof(TsSweep) >= kTsPad * sizeof(int), "candidate / intercept scratch");
+static_assert(sizeof(TsShared) == 11264, "11 KB per row: five 4-warp CTAs (20 rows in flight) per SM");
 
 // k-th smallest (0-based) of the n values v[] (shared memory of this warp; order-preserving integer images of
 // floats, see f2ord), exact: radix select, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
@@ -213,7 +213,8 @@ __device__ __noinline__ int warp_select_kth(const int *v, int n, int k, int *his
 // sorted by u inside every chunk of 32 (one warp bitonic sort per chunk), so for a row i and a chunk the count below
 // is a 6-step binary search instead of 32 compares, and the in-bracket columns are the few sorted entries that follow:
 // v_j < c_i needs u_j < c_i + w x_j <= c_i + w x_max(chunk), w = bhi - blo >= 0, which bounds the scan.  The chunk
-// holding i itself only counts columns j > i: the prefix sets pm[] turn that into one popcount.
+// holding i itself only counts columns j > i: a prefix bit-set over the sorted order (one warp scan per row block, kept
+// in registers) turns that into a shuffle and a popcount.
 // Lane L owns the rows i = 32 R + L; in-bracket pairs go to the lane's private sub-queue s.q[32 n + L].
 __device__ __forceinline__ void ts_sort_chunks(TsShared &s, const TsDims &d, int lane, float blo, float bhi)
 {
@@ -240,11 +241,6 @@ __device__ __forceinline__ void ts_sort_chunks(TsShared &s, const TsDims &d, int
 		const float vs = __shfl_sync(FULL, v, idx);
 		s.sw.suv[j] = make_float2(key, vs);
 		s.sw.sj[j] = (uint16_t)(32 * K + idx);
-		uint32_t m = 1u << idx; // inclusive prefix union over the sorted order
-#pragma unroll
-		for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULL, m, dd); if (lane >= dd) m |= o; }
-		s.sw.pm[33 * K + lane + 1] = m;
-		if (lane == 0) s.sw.pm[33 * K] = 0u;
 	}
 	__syncwarp();
 }
@@ -273,11 +269,20 @@ __device__ __forceinline__ int sweep_pairs(TsShared &s, const TsDims &d, int lan
 		const float yi = s.y[i], x = (float)(i - d.half);
 		const float a = i < d.n ? fmaf(-blo, x, yi) - eps : ninf;
 		const float c = i < d.n ? fmaf(-bhi, x, yi) + eps : ninf;
+		// own chunk: set of in-chunk column offsets among the first p sorted entries, p = lane + 1 (inclusive scan)
+		uint32_t pm = 1u << (s.sw.sj[32 * R + lane] & 31);
+#pragma unroll
+		for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULL, pm, dd); if (lane >= dd) pm |= o; }
 #pragma unroll 1
 		for (int K = R; K < d.nblk; ++K) {
 			const float2 *chunk = s.sw.suv + 32 * K;
 			int p = ts_lower_bound(chunk, a);
-			cb += K == R ? __popc(s.sw.pm[33 * K + p] & above) : p;
+			if (K == R) {
+				const uint32_t first_p = __shfl_sync(FULL, pm, max(p - 1, 0)); // every lane takes part; p = 0 -> empty set
+				cb += __popc((p > 0 ? first_p : 0u) & above);
+			} else {
+				cb += p;
+			}
 			// in-bracket candidates: sorted entries from p on while u < c + w x_max(K) (+ eps for the roundings of u and v)
 			const float t = c + fmaf(w, (float)(32 * K + 31 - d.half), eps);
 			while (p < 32) {
@@ -411,7 +416,10 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 	const float yabs = fmaxf(fabsf(ymin), fabsf(ymax));
 	// +-1.35e-4 sigma around the pilot holds rank 46 548 in ~99 % of the rows and ~1100 of the 93 096 quotients
 	// (~35 per lane's sub-queue).
-	float half = fmaxf(1.35e-4f * sigma, fmaxf(fabsf(c0) * 4e-6f, 1e-12f));
+	// (more carriers than 432: the quotient count inside a bracket of given relative width grows like n^1.5; shrink it to
+	// keep ~1100 candidates, which is what the per-row scratch is sized for)
+	const float shrink = d.n > 432 ? scale * sqrtf(scale) : 1.f;
+	float half = fmaxf(1.35e-4f * sigma * shrink, fmaxf(fabsf(c0) * 4e-6f, 1e-12f));
 	pilot_out = c0; half_out = half;
 	float blo = c0 + hint - half, bhi = c0 + hint + half;
 	// enclosure of the answer established so far: #(q < L) = cL <= rank < cU = #(q < U)  (exact counts; +-inf = unknown)
