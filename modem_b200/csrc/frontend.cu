@@ -164,10 +164,9 @@ __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, 
 	constexpr int kMtHalo = Mt<S>::kHalo, kMtExt = Mt<S>::kExt, kMtPer = Mt<S>::kPer, kMtPad = Mt<S>::kPad, kMtThreads = Mt<S>::kThreads;
 	constexpr int kLag = Geo<S>::kHalf, kLen2 = Geo<S>::kSymLen, kBox = Geo<S>::kMatchLen;
 	extern __shared__ float sm[];
-	cfx *sa = reinterpret_cast<cfx *>(sm);              // [kMtPad] samples
-	float *sre = sm + 2 * kMtPad;                       // prefix of c.re, later prefix of m
-	float *sim = sre + kMtPad;                          // prefix of c.im
-	float *se = sim + kMtPad;                           // prefix of e
+	float *sre = sm;                                    // c.re, then its prefix, later the prefix of m   [kMtPad]
+	float *sim = sre + kMtPad;                          // c.im, then its prefix
+	float *se = sim + kMtPad;                           // e, then its prefix
 	__shared__ float wtot[3][Mt<S>::kThreads / 32];
 	const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = n_samples ? n_samples[f] : n_default;
@@ -175,15 +174,22 @@ __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, 
 	if (t0 > n) return; // stream has n+1 steps: t = 0..n
 	const cfx *a = iq + (size_t)f * iq_stride;
 	const int base = t0 - (Mt<S>::kOffCur + kMtHalo); // extended index j <-> a[t - kOffCur], t = t0 + j - kMtHalo
-	{ // all kMtPer loads of a thread are issued before the first shared-memory store (memory-level parallelism)
-		cfx v[kMtPer];
+	{ // c[j] = a[j - lag] conj(a[j]) and e[j] = |a[j]|^2 straight from coalesced global loads (the lagged stream comes from
+	  // L1/L2); all loads of a thread are issued before the first shared-memory store
+		cfx cur[kMtPer], old[kMtPer];
 #pragma unroll
 		for (int k = 0; k < kMtPer; ++k) {
 			const int j = tid + k * kMtThreads, idx = base + j;
-			v[k] = (j < kMtExt && idx >= 0 && idx < iq_len) ? __ldg(&a[idx]) : make_float2(0.f, 0.f);
+			cur[k] = (j < kMtExt && idx >= 0 && idx < iq_len) ? __ldg(&a[idx]) : make_float2(0.f, 0.f);
+			const int io = idx - kLag;
+			old[k] = (j >= kLag && j < kMtExt && io >= 0 && io < iq_len) ? __ldg(&a[io]) : make_float2(0.f, 0.f);
 		}
 #pragma unroll
-		for (int k = 0; k < kMtPer; ++k) sa[tid + k * kMtThreads] = v[k];
+		for (int k = 0; k < kMtPer; ++k) {
+			const int j = tid + k * kMtThreads;
+			const cfx c = cmulc(old[k], cur[k]);
+			sre[j] = c.x; sim[j] = c.y; se[j] = cnorm(cur[k]);
+		}
 	}
 	__syncthreads();
 	// per-thread chunk [j0, j0+kMtPer): local sums of c and e, then block scan
@@ -193,10 +199,7 @@ __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, 
 #pragma unroll
 	for (int k = 0; k < kMtPer; ++k) {
 		const int j = j0 + k;
-		const cfx cur = sa[j];
-		const cfx old = j >= kLag ? sa[j - kLag] : make_float2(0.f, 0.f);
-		const cfx c = cmulc(old, cur);
-		s0 += c.x; s1 += c.y; s2 += cnorm(cur);
+		s0 += sre[j]; s1 += sim[j]; s2 += se[j];
 		cre[k] = s0; cim[k] = s1; ce[k] = s2;
 	}
 	float w0 = warp_incl_scan(s0, lane), w1 = warp_incl_scan(s1, lane), w2 = warp_incl_scan(s2, lane);
@@ -361,7 +364,7 @@ static cudaError_t launch_sync_metric_t(const cfx *iq, int64_t iq_stride, int iq
 	float *timing, int64_t timing_stride, cudaStream_t s)
 {
 	static bool attr = false;
-	const size_t smem = (size_t)5 * Mt<S>::kPad * sizeof(float);
+	const size_t smem = (size_t)3 * Mt<S>::kPad * sizeof(float);
 	if (!attr) {
 		cudaFuncSetAttribute(k_sync_metric<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		attr = true;
