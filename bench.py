@@ -9,7 +9,10 @@ decoding, CRC, de-scramble) over one batch of F synthetic windows per GPU — BA
 frames, 8000 Hz 16-bit real, clean channel, produced by the oracle's restatement of the reference encoder.
 `value`: inputs resident in HBM, CUDA-event timed, max over ranks, one NCCL all-gather of the payload bytes per step
 when N > 1.  `e2e`: the same batch through the reference-facing C-ABI with HOST (pinned) buffers: H2D of the int16
-windows and D2H of payload + status inside the timed region.  `--impl reference` times the CPU oracle port
+windows and D2H of payload + status inside the timed region of every step — with one handle and with two handles on two
+host threads (the copy of one batch overlaps the decode of the other); the better one is reported, both are in the line.
+`config3`: a secondary number on BASELINE configs[2]-type windows (README impairment chain) with its own parity gate.
+`--impl reference` times the CPU oracle port
 (oracle/, "-Ofast -march=native" like the reference Makefile) on a bounded sample with all host threads.
 """
 import argparse
