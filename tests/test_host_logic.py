@@ -60,6 +60,18 @@ def test_fft_plans_of_all_sample_rates():
     assert lib.fft_host(1000, _p(x), _p(out)) == -1
 
 
+def test_mode_geometry_is_consistent(oracle):
+    """Mode table of the Python mirror (decode.cc:302-374) against the oracle's row counts and the code lengths."""
+    import modem_b200 as M
+    bits = {6: 3, 7: 3, 8: 2, 9: 2, 10: 3, 11: 3, 12: 2, 13: 2}
+    for mode, (rows, cols) in M.MODE_GEOMETRY.items():
+        assert rows == oracle.MODE_ROWS[mode]
+        assert rows * cols * bits[mode] == (64800 if mode < 10 else 64512)
+        assert rows <= 126 and cols <= 512 and rows * cols <= 32400
+    for rate, sym in ((8000, 1280), (16000, 2560), (44100, 7056), (48000, 7680)):
+        assert oracle.frame_samples(6, rate) == 2 * rate + 55 * (sym + sym // 8)
+
+
 def test_tables_match_oracle(oracle, hostlib):
     rows = np.zeros(71 * 8, np.uint32)
     hostlib.host_bch_rows(_p(rows))
