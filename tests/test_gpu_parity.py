@@ -344,6 +344,22 @@ def test_full_size_round_trip_and_determinism(rx, oracle):
         assert ost == 0 and (opay == p1[i]).all()
 
 
+def test_batches_larger_than_the_handle_are_chunked(oracle):
+    """n_frames > max_frames: the call walks the batch in chunks of max_frames; results equal the one-shot decode."""
+    import modem_b200 as M
+    pcm, ns, sent = oracle.encode_batch(21, seed0=8100)
+    small = M.Receiver(max_frames=8)
+    try:
+        payload, st = small.decode(pcm)
+        assert (st["status"] == 0).all() and (payload == sent).all()
+        ns2 = np.full(21, 95200, np.int32)
+        ns2[5] = 40000                      # one ragged window in the second chunk's neighbourhood
+        payload, st = small.decode(pcm, n_samples=ns2)
+        assert st["status"][5] != 0 and (np.delete(st["status"], 5) == 0).all() and (np.delete(payload, 5, 0) == np.delete(sent, 5, 0)).all()
+    finally:
+        small.close()
+
+
 def test_device_memory_interface(rx, oracle):
     import torch
     import modem_b200 as M
