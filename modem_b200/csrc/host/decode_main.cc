@@ -67,8 +67,15 @@ void base37(char *str, long long val, int len)
 
 int main(int argc, char **argv)
 {
-	bool batch = argc > 1 && !std::strcmp(argv[1], "--batch");
-	if (batch) { --argc; ++argv; }
+	// extension: --batch[=STRIDE] decodes N consecutive windows of STRIDE sample frames (default 95200: a single mode-6 frame
+	// recording at 8 kHz) and writes N x 5380 bytes
+	bool batch = argc > 1 && !std::strncmp(argv[1], "--batch", 7) && (argv[1][7] == 0 || argv[1][7] == '=');
+	int64_t batch_stride = 95200;
+	if (batch) {
+		if (argv[1][7] == '=') batch_stride = std::atoll(argv[1] + 8);
+		if (batch_stride < 1) { std::cerr << "usage: " << argv[0] << " [--batch[=STRIDE]] OUTPUT INPUT [SKIP]" << std::endl; return 1; }
+		--argc; ++argv;
+	}
 	if (argc < 3 || argc > 4) {
 		std::cerr << "usage: " << argv[0] << " OUTPUT INPUT [SKIP]" << std::endl;
 		return 1;
@@ -91,7 +98,7 @@ int main(int argc, char **argv)
 		return 1;
 	}
 	const int64_t total = (int64_t)w.pcm.size() / w.channels;
-	const int64_t stride = batch ? 95200 : std::max<int64_t>(total, 1);
+	const int64_t stride = batch ? batch_stride : std::max<int64_t>(total, 1);
 	const int n_frames = batch ? (int)(total / stride) : 1;
 	if (n_frames < 1) { std::cerr << "input shorter than one window" << std::endl; return 1; }
 	ofdmrx_t *h = nullptr;
