@@ -467,11 +467,10 @@ template <int S>
 static cudaError_t launch_acquire_t(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s)
 {
-	static bool attr = false;
+	static bool attr[64] = {};
 	const size_t smem = kAcqBufOff + 2 * (size_t)Geo<S>::kSymLen * sizeof(cfx);
-	if (!attr) {
+	if (first_use_on_device(attr)) {
 		cudaFuncSetAttribute(k_acquire<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr = true;
 	}
 	k_acquire<S><<<n_frames, kAcqThreads, smem, s>>>(iq, iq_stride, iq_len, det, det_count, skip, st, soft_out, ac);
 	return cudaGetLastError();

@@ -16,6 +16,17 @@ namespace ofdmrx {
 		}                                                                                            \
 	} while (0)
 
+// Function attributes (dynamic shared memory limits) are per device: launchers set them once per device, not per process.
+inline bool first_use_on_device(bool (&seen)[64])
+{
+	int d = 0;
+	cudaGetDevice(&d);
+	d &= 63;
+	if (seen[d]) return false;
+	seen[d] = true;
+	return true;
+}
+
 typedef float2 cfx;
 __host__ __device__ __forceinline__ cfx cmul(cfx a, cfx b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __host__ __device__ __forceinline__ cfx cmulc(cfx a, cfx b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a * conj(b)

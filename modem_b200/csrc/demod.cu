@@ -651,11 +651,10 @@ __global__ void __launch_bounds__(kSdThreads) k_soft_demap(const cfx *cons_raw, 
 
 static int theil_sen_grid(int rows, int n_sm, int *smem)
 {
-	static bool attr = false;
+	static bool attr[64] = {};
 	*smem = (int)(kTsWarps * sizeof(TsShared));
-	if (!attr) {
+	if (first_use_on_device(attr)) {
 		cudaFuncSetAttribute(k_theil_sen, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem);
-		attr = true;
 	}
 	int grid = (rows + kTsWarps - 1) / kTsWarps;
 	const int resident = n_sm * (int)((227 * 1024) / (*smem + 1024));
@@ -677,10 +676,9 @@ template <int S>
 static void launch_demod_fft_t(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *st, int n_frames, const cfx *tw,
 	cfx *cons_raw, float *yph, cudaStream_t s)
 {
-	static bool attr = false;
-	if (!attr) {
+	static bool attr[64] = {};
+	if (first_use_on_device(attr)) {
 		cudaFuncSetAttribute(k_demod_fft<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FftShared<S>));
-		attr = true;
 	}
 	k_demod_fft<S><<<n_frames, kDmThreads, sizeof(FftShared<S>), s>>>(iq, iq_stride, iq_len, st, tw, cons_raw, yph);
 }

@@ -363,11 +363,10 @@ template <int S>
 static cudaError_t launch_sync_metric_t(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
 	float *timing, int64_t timing_stride, cudaStream_t s)
 {
-	static bool attr = false;
+	static bool attr[64] = {};
 	const size_t smem = (size_t)3 * Mt<S>::kPad * sizeof(float);
-	if (!attr) {
+	if (first_use_on_device(attr)) {
 		cudaFuncSetAttribute(k_sync_metric<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr = true;
 	}
 	dim3 g((n_max + 1 + kMtTile - 1) / kMtTile, n_frames);
 	k_sync_metric<S><<<g, Mt<S>::kThreads, smem, s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride);
