@@ -105,7 +105,7 @@ def call_sign(status_row):
 
 
 class Receiver:
-    """Batched stand-in for the reference's Decoder<float, Complex<float>, 8000> (decode.cc:161-557)."""
+    """Batched stand-in for the reference's Decoder<float, Complex<float>, RATE> (decode.cc:161-557, instantiated at :590-606)."""
 
     def __init__(self, device=0, max_frames=1024, max_samples=FRAME_SAMPLES, rate=8000, keep_taps=False, scl_ctas_per_sm=None):
         self._lib = load()
@@ -231,11 +231,11 @@ def read_wav(path_or_bytes):
 def decode_wav(path, skip=0, device=0):
     """`decode OUTPUT INPUT [SKIP]` for one file: returns (5380 payload bytes, status record)."""
     rate, ch, pcm = read_wav(path)
-    if rate != 8000:
-        raise OfdmrxError("Unsupported sample rate.")  # decode.cc:603-605 (16/44.1/48 kHz: not built yet)
+    if rate not in (8000, 16000, 44100, 48000):
+        raise OfdmrxError("Unsupported sample rate.")  # decode.cc:590-606
     if ch < 1 or ch > 2:
         raise OfdmrxError("Only real or analytic signal (one or two channels) supported.")  # decode.cc:578-581
-    rx = Receiver(device=device, max_frames=1, max_samples=max(pcm.shape[0], 1))
+    rx = Receiver(device=device, max_frames=1, max_samples=max(pcm.shape[0], 1), rate=rate)
     try:
         payload, status = rx.decode(pcm.reshape(1, -1), channels=ch, skip=skip)
     finally:
