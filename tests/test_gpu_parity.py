@@ -420,3 +420,29 @@ def test_decode_cli_matches_reference_contract(oracle, tmp_path):
     q = subprocess.run([ref, str(tmp_path / "cpu.dat"), wav], capture_output=True)
     assert r.returncode == 0 and (tmp_path / "gpu.dat").read_bytes() == (tmp_path / "cpu.dat").read_bytes()
     assert len((tmp_path / "gpu.dat").read_bytes()) == 5380
+
+
+def test_against_committed_golden_vectors(rx, oracle):
+    """tests/golden/oracle_vectors.npz (made by tests/golden/make_golden.py from the CPU oracle; the CPU suite checks that the
+    oracle still reproduces it): the CUDA path against the committed numbers themselves, clean and through the README chain."""
+    import os
+    import modem_b200 as M
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_vectors.npz"))
+    pl = g["payload"]
+    payload, st = rx.decode(oracle.encode(pl).reshape(1, -1), channels=1)
+    s = st[0]
+    assert s["status"] == 0 and (payload[0] == pl).all() and s["flips"] == 0
+    assert s["sc_pos"] == int(g["sc_pos"]) and abs(s["cfo_rad"] - float(g["cfo_rad"])) < 1e-5
+    dsoft = np.abs(rx.taps(M.TAP_SOFT, 0, 1)[0][:255].astype(int) - g["soft"].astype(int))
+    assert dsoft.max() <= 1 and (dsoft != 0).sum() <= 8
+    prec = rx.taps(M.TAP_TS, 0, 1)[0][:, 2]
+    assert (np.abs(prec - g["precision"]) / g["precision"]).max() < TOL_PRECISION
+    head = g["llr_head"]
+    assert np.abs(rx.taps(M.TAP_LLR, 0, 1)[0][:256] - head).max() / np.abs(head).mean() < TOL_LLR
+    imp = oracle.impair(multipath=True, cfo_hz=234.567, sfo_ppm=147, awgn_db=-30, seed=9)
+    payload, st = rx.decode(oracle.encode(pl, channels=2, imp=imp).reshape(1, -1), channels=2)
+    s = st[0]
+    assert s["status"] == 0 and (payload[0] == pl).all()
+    assert s["sc_pos"] == int(g["imp_sc_pos"]) and abs(s["cfo_rad"] - float(g["imp_cfo_rad"])) < 1e-5
+    slope = rx.taps(M.TAP_TS, 0, 1)[0][:, 0]
+    assert np.abs(slope - g["imp_slope"]).max() <= TOL_SLOPE_REL * np.abs(g["imp_slope"]).max() + 1e-7
