@@ -35,20 +35,8 @@ int main(int argc, char **argv)
 	std::memset(out, 0, sizeof(out));
 	int st = rx.run(out, w.samples.data(), w.frames(), w.channels, skip, opt);
 	const Taps &t = rx.taps;
-	if (t.detections && t.t_fire >= 0) {
-		std::cerr << "symbol pos: " << t.symbol_pos << std::endl;
-		std::cerr << "coarse cfo: " << t.cfo_rad * (w.rate / kTwoPi) << " Hz " << std::endl;
-	}
-	switch (st) {
-	case ST_OSD_FAIL: std::cerr << "OSD error." << std::endl; break;
-	case ST_HDR_CRC: std::cerr << "header CRC error." << std::endl; break;
-	case ST_BAD_MODE: std::cerr << "operation mode " << t.mode << " unsupported." << std::endl; break;
-	case ST_BAD_CALL: std::cerr << "oper mode: " << t.mode << std::endl << "call sign unsupported." << std::endl; break;
-	default: break;
-	}
+	std::cerr << rx.header_log; // per consumed detection: symbol pos, coarse cfo, header outcome (decode.cc:400-446)
 	if (st == ST_OK || st == ST_PAYLOAD_CRC) {
-		std::cerr << "oper mode: " << t.mode << std::endl;
-		std::cerr << "call sign: " << t.call_sign << std::endl;
 		std::cerr << "demod ";
 		for (size_t j = 0; j < t.slope.size(); ++j) std::cerr << ".";
 		std::cerr << " done" << std::endl;

@@ -3,8 +3,10 @@
 // CPU restatement of the reference transmitter (/root/reference/encode.cc) and receiver
 // (/root/reference/decode.cc) for all modes 6..13 at 8/16/44.1/48 kHz, plus a re-specified impairment
 // chain standing in for the absent aicodix/disorders tools (README.md:49).  The receiver exposes STAGE
-// TAPS so each CUDA kernel can be compared at its own output.  PARITY UNPINNED: the reference cannot be
-// compiled here (aicodix/dsp + aicodix/code absent); what pins this file is
+// TAPS so each CUDA kernel can be compared at its own output.  PARITY UNPINNED for the third-party arithmetic:
+// a stock reference cannot be compiled here (aicodix/dsp + aicodix/code absent).  What pins this file is
+//   (0) the reference's OWN decode.cc / encode.cc compiled against shim/ (the primitives of ref_dsp.hh / ref_code.hh behind
+//       the absent headers' API): same WAV bytes, same payloads, same stderr as this restatement (tests/test_reference_tu.py),
 //   (1) polar_tables.hh regenerated bit-exactly by ref_freezer.hh (the one real golden vector),
 //   (2) SURVEY.md Appendix B known answers (tests/test_oracle_kat.py),
 //   (3) encode -> decode loop-back returning the exact payload.
@@ -384,6 +386,7 @@ class Receiver {
 	long long stream_count_ = 0; // samples pushed so far
 public:
 	Taps taps;
+	std::string header_log; // what decode.cc:400-446 prints on stderr, one block per consumed detection (SKIP walks several)
 	explicit Receiver(int rate) : rate_(rate), symbol_len_(1280 * rate / 8000), guard_len_(symbol_len_ / 8),
 		filter_len_((((21 * rate) / 8000) & ~3) | 1), buffer_len_(6 * (symbol_len_ + guard_len_)),
 		search_pos_(buffer_len_ - 4 * (symbol_len_ + guard_len_)), half_(symbol_len_ / 2),
@@ -468,6 +471,7 @@ public:
 	int run(uint8_t *out, const float *pcm, size_t n_frames, int channels, int skip_count, const RxOptions &opt = RxOptions())
 	{
 		taps = Taps();
+		header_log.clear();
 		pcm_ = pcm; n_frames_ = n_frames; channels_ = channels; pos_ = 0; good_ = true; stream_count_ = 0;
 		blockdc_ = BlockDC();
 		blockdc_.samples(2 * (symbol_len_ + guard_len_));
@@ -497,6 +501,11 @@ public:
 			cfo_rad = taps.cfo_rad;
 			taps.t_fire = (int)(stream_count_ - 1);
 			taps.sc_pos = taps.t_fire - (buffer_len_ - 1) + symbol_pos;
+			{
+				char line[96]; // operator<<(float) prints like %.6g
+				std::snprintf(line, sizeof(line), "symbol pos: %d\ncoarse cfo: %.6g Hz \n", symbol_pos, (double)(cfo_rad * (rate_ / kTwoPi)));
+				header_log += line;
+			}
 			osc.omega(-cfo_rad);
 			for (int i = 0; i < symbol_len_; ++i) tdom[i] = buf[i + symbol_pos + (symbol_len_ + guard_len_)] * osc();
 			fwd_(fdom.data(), tdom.data());
@@ -510,19 +519,21 @@ public:
 			bool unique = opt.osd_literal ? osd.decode_full(taps.hdr, taps.soft, genmat_) : osd.decode_pruned(taps.hdr, taps.soft, genmat_);
 			taps.osd_unique = unique;
 			taps.osd_visited = osd.visited;
-			if (!unique) { taps.status = ST_OSD_FAIL; continue; }
+			if (!unique) { taps.status = ST_OSD_FAIL; header_log += "OSD error.\n"; continue; }
 			uint64_t md = 0;
 			for (int i = 0; i < 55; ++i) md |= (uint64_t)get_be_bit(taps.hdr, i) << i;
 			uint16_t cs = 0;
 			for (int i = 0; i < 16; ++i) cs |= (uint16_t)get_be_bit(taps.hdr, i + 55) << i;
 			CRC<uint16_t> crc0(0xA8F4);
 			taps.md = md;
-			if (crc0.u64(md << 9) != cs) { taps.status = ST_HDR_CRC; continue; }
+			if (crc0.u64(md << 9) != cs) { taps.status = ST_HDR_CRC; header_log += "header CRC error.\n"; continue; }
 			taps.mode = md & 255;
-			if (!mode_params(taps.mode, mp)) { taps.status = ST_BAD_MODE; continue; }
-			if ((md >> 8) == 0 || (long long)(md >> 8) >= kCallSignLimit) { taps.status = ST_BAD_CALL; continue; }
+			if (!mode_params(taps.mode, mp)) { taps.status = ST_BAD_MODE; header_log += "operation mode " + std::to_string(taps.mode) + " unsupported.\n"; continue; }
+			header_log += "oper mode: " + std::to_string(taps.mode) + "\n";
+			if ((md >> 8) == 0 || (long long)(md >> 8) >= kCallSignLimit) { taps.status = ST_BAD_CALL; header_log += "call sign unsupported.\n"; continue; }
 			base37_decode(taps.call_sign, md >> 8, 9);
 			taps.call_sign[9] = 0;
+			header_log += std::string("call sign: ") + taps.call_sign + "\n";
 			okay = true;
 		} while (skip_count--);
 		if (!okay) return taps.status;
