@@ -17,6 +17,7 @@ ENCODE = os.path.join(PKG, "encode")
 HOSTTEST = os.path.join(OBJ, "libhosttest.so")
 FFTHOST = os.path.join(OBJ, "libffthost.so")   # test helper: the product's FFT plans compiled for the host
 STIMHOST = os.path.join(OBJ, "libstimhost.so") # test helper: the stimulus routines (stimulus.cuh) compiled for the host
+STIMTSAN = os.path.join(OBJ, "stimulus_cta_tsan") # test helper: the CTA-cooperative routines on host threads under ThreadSanitizer
 
 CU = ["polar.cu", "frontend.cu", "acquire.cu", "demod.cu", "ofdmrx.cu", "stimulus.cu"]
 CC = ["host_tables.cc", "tx_tables.cc"]
@@ -82,6 +83,10 @@ def build(force=False, verbose=False):
     if os.path.exists(stim) and (force or _stale(STIMHOST, stim_deps)):
         _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", stim,
               os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMHOST], log)
+    tsan = os.path.join(ROOT, "tests", "stimulus_cta_tsan.cu")
+    if os.path.exists(tsan) and (force or _stale(STIMTSAN, [tsan] + stim_deps[1:])):
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O1", "-g", "-Xcompiler", "-fsanitize=thread,-ffp-contract=off,-pthread", tsan,
+              os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMTSAN], log)
     with open(os.path.join(OBJ, "build.log"), "a") as f:
         f.write("\n".join(log))
     if verbose:

@@ -20,11 +20,7 @@
 
 namespace ofdmrx {
 
-#ifdef __CUDA_ARCH__
-#define OFDMRX_TX_SYNC() __syncthreads()
-#else
-#define OFDMRX_TX_SYNC() ((void)0)
-#endif
+#define OFDMRX_TX_SYNC() OFDMRX_CTA_SYNC()
 
 constexpr int kTxMaxCarriers = 512;                        // widest occupied band (mode 10), encode.cc:232
 constexpr int kTxSymPilot = 0, kTxSymSc = 1, kTxSymMeta = 2; // frame-constant symbols

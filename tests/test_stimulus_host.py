@@ -121,3 +121,13 @@ def test_argument_rules(stim, oracle):
     assert rc(off=2700) == -22                                # above rate/2 - bw/2
     assert rc(off=-1000, fmt=1) == 95200                      # analytic output may sit at negative offsets
     assert rc(rate=22050) == -22
+
+
+def test_no_barrier_is_missing(stim):
+    """the CTA-cooperative routines (payload -> code bits, one OFDM symbol, the shared Stockham FFT) on six host threads with
+    OFDMRX_CTA_SYNC() as a real barrier, under ThreadSanitizer (tests/stimulus_cta_tsan.cu): no data race, and the same bits
+    as the one-thread run.  (Dropping any one barrier from stimulus.cuh makes this fail — tried.)"""
+    import subprocess
+    from modem_b200 import build as B
+    r = subprocess.run([B.STIMTSAN, "6"], capture_output=True, text=True)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr and "0 mismatching" in r.stdout, (r.stdout, r.stderr[-2000:])
