@@ -271,12 +271,27 @@ def main():
         import oracle_lib as O
         uniq = 148
         imp = O.impair(multipath=True, cfo_hz=234.567, sfo_ppm=147, awgn_db=-30, seed=4242 + rank)
-        ipcm, ins, isent = O.encode_batch(uniq, seed0=777 + 1000 * rank, channels=2, imp=imp, nthreads=max(1, cores // world))
-        sel = torch.arange(n) % uniq
-        dev_imp = torch.from_numpy(ipcm)[sel].cuda()
+        if os.environ.get("BENCH_STIM", "cpu") == "device":
+            # every window distinct: payloads, noise and all generated on the GPU (include/ofdmtx.h), nothing replicated
+            uniq = n
+            isent = np.random.default_rng(777 + rank).integers(0, 256, (n, M.PAYLOAD_BYTES), dtype=np.uint8)
+            tx = M.Transmitter(device=local_rank, max_windows=min(n, 2048))
+            c3_stride = tx.window_samples(6)
+            dev_imp = torch.zeros((n, c3_stride * 2), dtype=torch.int16, device="cuda")
+            tx.encode_raw(isent.ctypes.data, M.MEM_HOST, n, 6, int(M.load().ofdmtx_call_sign(b"CALLSIGN")), 2000,
+                          M.impairments(multipath=True, cfo_hz=234.567, sfo_ppm=147.0, awgn_db=-30.0, seed=4242 + 1000003 * rank),
+                          dev_imp.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, c3_stride, None, stream)
+            torch.cuda.synchronize()
+            tx.close()
+            sel = torch.arange(n)
+        else:
+            ipcm, ins, isent = O.encode_batch(uniq, seed0=777 + 1000 * rank, channels=2, imp=imp, nthreads=max(1, cores // world))
+            c3_stride = ipcm.shape[1] // 2
+            sel = torch.arange(n) % uniq
+            dev_imp = torch.from_numpy(ipcm)[sel].cuda()
 
         def step_cfg3():
-            rx.decode_raw(dev_imp.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, n, ipcm.shape[1] // 2, None, 0, payload.data_ptr(), status.data_ptr(), stream)
+            rx.decode_raw(dev_imp.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, n, c3_stride, None, 0, payload.data_ptr(), status.data_ptr(), stream)
 
         for _ in range(2):
             step_cfg3()

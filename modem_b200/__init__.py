@@ -48,6 +48,8 @@ MODE_GEOMETRY = {6: (50, 432), 7: (54, 400), 8: (81, 400), 9: (90, 360), 10: (42
 EXPORTS = ["ofdmrx_create", "ofdmrx_destroy", "ofdmrx_set_option", "ofdmrx_decode_batch", "ofdmrx_polar_decode",
            "ofdmrx_get_taps", "ofdmrx_tap_elems", "ofdmrx_last_launches", "ofdmrx_stage_times", "ofdmrx_get_table",
            "ofdmrx_version", "ofdmrx_theil_sen"]
+TX_EXPORTS = ["ofdmtx_create", "ofdmtx_destroy", "ofdmtx_call_sign", "ofdmtx_window_samples", "ofdmtx_encode_batch",
+              "ofdmtx_get_code", "ofdmtx_last_launches"]
 STAGES = ["frontend", "sync_metric", "sync_detect", "acquire", "demod", "compact_init", "polar_scl"]
 
 _lib = None
@@ -80,6 +82,17 @@ def load():
     L.ofdmrx_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.ofdmrx_get_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.ofdmrx_version.restype = C.c_char_p
+    L.ofdmtx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.ofdmtx_destroy.argtypes = [C.c_void_p]
+    L.ofdmtx_destroy.restype = None
+    L.ofdmtx_call_sign.argtypes = [C.c_char_p]
+    L.ofdmtx_call_sign.restype = C.c_int64
+    L.ofdmtx_window_samples.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ofdmtx_window_samples.restype = C.c_int64
+    L.ofdmtx_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.ofdmtx_get_code.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ofdmtx_last_launches.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -199,6 +212,67 @@ class Receiver:
     @property
     def last_launches(self):
         return int(self._lib.ofdmrx_last_launches(self._h))
+
+
+class Impairments(C.Structure):
+    """ofdmtx_impairments (include/ofdmtx.h): the README.md:49 chain as the oracle re-specifies it."""
+    _fields_ = [("multipath", C.c_int32), ("cfo_hz", C.c_float), ("sfo_ppm", C.c_float), ("awgn", C.c_int32),
+                ("awgn_db", C.c_float), ("seed", C.c_uint64)]
+
+
+def impairments(multipath=False, cfo_hz=0.0, sfo_ppm=0.0, awgn_db=None, seed=1):
+    return Impairments(int(multipath), cfo_hz, sfo_ppm, int(awgn_db is not None), awgn_db if awgn_db is not None else 0.0, seed)
+
+
+class Transmitter:
+    """Batched stand-in for the reference's Encoder<float, Complex<float>, RATE> (encode.cc:27-318) plus the impairment
+    chain of README.md:49 — the device-side stimulus generator."""
+
+    def __init__(self, device=0, max_windows=1024, rate=8000, frames_per_window=1):
+        self._lib = load()
+        self._h = C.c_void_p()
+        self.rate, self.frames_per_window = rate, frames_per_window
+        _check(self._lib.ofdmtx_create(C.byref(self._h), device, rate, max_windows, frames_per_window), "ofdmtx_create")
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.ofdmtx_destroy(h)
+            h.value = None
+
+    __del__ = close
+
+    def window_samples(self, mode=6):
+        return int(self._lib.ofdmtx_window_samples(self.rate, mode, self.frames_per_window))
+
+    def encode(self, payloads, mode=6, call_sign=b"CALLSIGN", freq_off=2000, channels=1, imp=None, stride=None, fmt=None):
+        """payloads: uint8 [n_windows (x frames_per_window), 5380] (host).  Returns (samples, n_samples): int16
+        [n, stride * channels] like `encode - RATE 16 CHANNELS ...` would write them (fmt=FMT_F32_IQ: complex64 [n, stride])."""
+        payloads = np.ascontiguousarray(payloads, np.uint8).reshape(-1, self.frames_per_window * PAYLOAD_BYTES)
+        n = payloads.shape[0]
+        fmt = (FMT_S16_MONO if channels == 1 else FMT_S16_IQ) if fmt is None else fmt
+        stride = stride or self.window_samples(mode) + (64 if imp is not None and imp.sfo_ppm < 0 else 0)
+        out = np.zeros((n, stride), np.complex64) if fmt == FMT_F32_IQ else np.zeros((n, stride * (1 if fmt == FMT_S16_MONO else 2)), np.int16)
+        ns = np.zeros(n, np.int32)
+        cs = int(self._lib.ofdmtx_call_sign(call_sign))
+        self.encode_raw(payloads.ctypes.data, MEM_HOST, n, mode, cs, freq_off, imp, out.ctypes.data, MEM_HOST, fmt, stride, ns, None)
+        return out, ns
+
+    def encode_raw(self, payload_ptr, payload_mem, n_windows, mode, call_sign, freq_off, imp, samples_ptr, mem_kind, fmt, stride,
+                   n_samples, stream):
+        _check(self._lib.ofdmtx_encode_batch(self._h, payload_ptr, payload_mem, n_windows, mode, call_sign, freq_off,
+                                             C.byref(imp) if imp is not None else None, samples_ptr, mem_kind, fmt, stride,
+                                             n_samples.ctypes.data if n_samples is not None else None, stream), "ofdmtx_encode_batch")
+
+    def code_bits(self, first=0, count=1):
+        """transmitted code words of the last chunk: uint32 [count, 2048]"""
+        out = np.zeros((count, 2048), np.uint32)
+        _check(self._lib.ofdmtx_get_code(self._h, first, count, out.ctypes.data), "ofdmtx_get_code")
+        return out
+
+    @property
+    def last_launches(self):
+        return int(self._lib.ofdmtx_last_launches(self._h))
 
 
 def read_wav(path_or_bytes):

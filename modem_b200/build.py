@@ -13,12 +13,16 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libofdmrx.so")
 DECODE = os.path.join(PKG, "decode")
+ENCODE = os.path.join(PKG, "encode")
 HOSTTEST = os.path.join(OBJ, "libhosttest.so")
 FFTHOST = os.path.join(OBJ, "libffthost.so")   # test helper: the product's FFT plans compiled for the host
+STIMHOST = os.path.join(OBJ, "libstimhost.so") # test helper: the stimulus routines (stimulus.cuh) compiled for the host
+STIMTSAN = os.path.join(OBJ, "stimulus_cta_tsan") # test helper: the CTA-cooperative routines on host threads under ThreadSanitizer
 
-CU = ["polar.cu", "frontend.cu", "acquire.cu", "demod.cu", "ofdmrx.cu"]
-CC = ["host_tables.cc"]
-HDRS = ["common.cuh", "polar.cuh", "frontend.cuh", "fft.cuh", "host_tables.h", os.path.join("..", "..", "include", "ofdmrx.h")]
+CU = ["polar.cu", "frontend.cu", "acquire.cu", "demod.cu", "ofdmrx.cu", "stimulus.cu"]
+CC = ["host_tables.cc", "tx_tables.cc"]
+HDRS = ["common.cuh", "polar.cuh", "frontend.cuh", "fft.cuh", "host_tables.h", "stimulus.cuh", "tx_tables.h",
+        os.path.join("..", "..", "include", "ofdmrx.h"), os.path.join("..", "..", "include", "ofdmtx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"] + [("-D%s=%s" % (k, os.environ[k])) for k in ("OFDMRX_SCL_PAIRS", "OFDMRX_SCL_SMEM_LEVELS") if os.environ.get(k)]
 
@@ -63,6 +67,10 @@ def build(force=False, verbose=False):
     if os.path.exists(main) and (rebuilt or _stale(DECODE, [main, LIB])):
         _run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), main, "-o", DECODE,
               "-L", PKG, "-lofdmrx", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], log)
+    enc = os.path.join(CSRC, "host", "encode_main.cc")
+    if os.path.exists(enc) and (rebuilt or _stale(ENCODE, [enc, LIB])):
+        _run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), enc, "-o", ENCODE,
+              "-L", PKG, "-lofdmrx", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], log)
     emu = os.path.join(ROOT, "tests", "scl_emulator.cc")
     if os.path.exists(emu) and (force or _stale(HOSTTEST, [emu, os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "host_tables.h")])):
         _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", emu, os.path.join(CSRC, "host_tables.cc"), "-o", HOSTTEST], log)
@@ -70,6 +78,15 @@ def build(force=False, verbose=False):
     if os.path.exists(ffth) and (force or _stale(FFTHOST, [ffth, os.path.join(CSRC, "fft.cuh"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "host_tables.cc")])):
         _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC", "-shared", ffth,
               os.path.join(CSRC, "host_tables.cc"), "-o", FFTHOST], log)
+    stim = os.path.join(ROOT, "tests", "stimulus_host.cu")
+    stim_deps = [stim] + [os.path.join(CSRC, f) for f in ("stimulus.cuh", "fft.cuh", "common.cuh", "host_tables.cc", "tx_tables.cc", "tx_tables.h")]
+    if os.path.exists(stim) and (force or _stale(STIMHOST, stim_deps)):
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", stim,
+              os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMHOST], log)
+    tsan = os.path.join(ROOT, "tests", "stimulus_cta_tsan.cu")
+    if os.path.exists(tsan) and (force or _stale(STIMTSAN, [tsan] + stim_deps[1:])):
+        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O1", "-g", "-Xcompiler", "-fsanitize=thread,-ffp-contract=off,-pthread", tsan,
+              os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMTSAN], log)
     with open(os.path.join(OBJ, "build.log"), "a") as f:
         f.write("\n".join(log))
     if verbose:

@@ -13,6 +13,17 @@ namespace ofdmrx {
 #else
 #define OFDMRX_HD inline
 #endif
+// CTA-wide barrier of the cooperative routines: __syncthreads() on the device; nothing in the one-"thread" host builds of the
+// CPU tests; a real barrier over host threads when a test harness defines OFDMRX_HOST_CTA (tests/stimulus_cta_tsan.cu runs the
+// routines on several host threads under ThreadSanitizer to prove that no barrier is missing).
+#if defined(__CUDA_ARCH__)
+#define OFDMRX_CTA_SYNC() __syncthreads()
+#elif defined(OFDMRX_HOST_CTA)
+void ofdmrx_host_cta_sync();
+#define OFDMRX_CTA_SYNC() ofdmrx_host_cta_sync()
+#else
+#define OFDMRX_CTA_SYNC() ((void)0)
+#endif
 
 template <int R> OFDMRX_HD void bfly(cfx *v);
 template <> OFDMRX_HD void bfly<2>(cfx *v)
@@ -112,9 +123,7 @@ OFDMRX_HD cfx *fft_run(cfx *src, cfx *dst, const cfx *tw, int tid, int nthr)
 	} else {
 		constexpr int R = FftPlan<N>::r[P];
 		fft_pass<N, R>(src, dst, M, tw, tid, nthr);
-#ifdef __CUDA_ARCH__
-		__syncthreads();
-#endif
+		OFDMRX_CTA_SYNC();
 		return fft_run<N, P + 1, M * R>(dst, src, tw, tid, nthr);
 	}
 }

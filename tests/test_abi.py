@@ -26,6 +26,11 @@ def test_exports_match_header(lib):
     for name in declared:
         assert hasattr(lib, name), name
     assert b"sm_100a" in lib.ofdmrx_version()
+    hdr = open(os.path.join(ROOT, "include", "ofdmtx.h")).read()
+    declared = set(re.findall(r"\b(ofdmtx_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(M.TX_EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
 
 
 def test_status_struct_layout():
@@ -51,6 +56,12 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(M.OfdmrxError):
         M.Receiver(max_frames=4)
     assert lib.ofdmrx_create(C.byref(h), 0, 22050, 4, 95200) == -22    # only the reference's four rates exist (decode.cc:590-606)
+    assert lib.ofdmtx_create(C.byref(h), 0, 8000, 4, 1) == -19
+    assert lib.ofdmtx_create(C.byref(h), 0, 22050, 4, 1) == -22
+    with pytest.raises(M.OfdmrxError):
+        M.Transmitter(max_windows=4)
+    assert lib.ofdmtx_call_sign(b"CALLSIGN") == 1263905687425 and lib.ofdmtx_call_sign(b"no!") == -1
+    assert lib.ofdmtx_window_samples(8000, 6, 1) == 95200
 
 
 def test_sass_is_sm100_only():

@@ -15,6 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import modem_b200 as M  # noqa: E402
 import oracle_lib as O  # noqa: E402
+from _stimulus import windows  # noqa: E402
 
 
 def main():
@@ -32,8 +33,8 @@ def main():
     rows = []
     for db in levels:
         t0 = time.time()
-        pcm, ns, sent = O.encode_batch(n, seed0=int(1e6 + 1000 * (db + 100)), channels=2, rate=rate, mode=mode, stride=stride,
-                                       imp=O.impair(awgn_db=float(db), seed=int(7e5 + 100 * (db + 100))))
+        pcm, ns, sent = windows(n, int(1e6 + 1000 * (db + 100)), channels=2, rate=rate, mode=mode, stride=stride,
+                                imp=dict(awgn_db=float(db), seed=int(7e5 + 100 * (db + 100))))   # STIM=device: generated on the GPU
         gp, gs = rx.decode(pcm, channels=2)
         ost, op = O.decode_batch(pcm, channels=2, rate=rate, nthreads=cores)
         bits = n * 43040
@@ -49,7 +50,7 @@ def main():
         print(rows[-1], flush=True)
     out = os.path.join(ROOT, "profiles")
     os.makedirs(out, exist_ok=True)
-    json.dump({"n_per_point": n, "rows": rows}, open(os.path.join(out, "ber_sweep_%s.json" % tag), "w"), indent=1)
+    json.dump({"n_per_point": n, "stimulus": os.environ.get("STIM", "cpu"), "rows": rows}, open(os.path.join(out, "ber_sweep_%s.json" % tag), "w"), indent=1)
     with open(os.path.join(out, "ber_sweep_%s.md" % tag), "w") as f:
         f.write("# AWGN sweep (BASELINE configs[3]): B200 path vs CPU oracle on identical windows, mode %d at %d Hz, %d windows/point\n\n" % (mode, rate, n))
         f.write("| AWGN dB | GPU FER | CPU FER | GPU BER | CPU BER | both decode but differ | only GPU | only CPU |\n|---|---|---|---|---|---|---|---|\n")

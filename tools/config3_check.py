@@ -8,13 +8,13 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import modem_b200 as M
 import oracle_lib as O
+from _stimulus import windows
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 n = int(os.environ.get("N_FRAMES", "10000"))
 cores = os.cpu_count() or 1
-imp = O.impair(multipath=True, cfo_hz=234.567, sfo_ppm=147, awgn_db=-30, seed=12345)
 t = time.time()
-pcm, ns, sent = O.encode_batch(n, seed0=31337, channels=2, imp=imp, nthreads=cores)
+pcm, ns, sent = windows(n, 31337, channels=2, imp=dict(multipath=True, cfo_hz=234.567, sfo_ppm=147, awgn_db=-30, seed=12345))  # STIM=device: generated on the GPU
 t_enc = time.time() - t
 rx = M.Receiver(max_frames=n)
 d = torch.from_numpy(pcm).cuda()
@@ -37,7 +37,7 @@ res = {"frames": n, "impairments": "multipath(4 taps) + CFO 234.567 Hz + SFO 147
        "gpu_ok": int((gs["status"] == 0).sum()), "cpu_ok": int((ost == 0).sum()), "status_equal": int((gs["status"] == ost).sum()),
        "payload_equal_windows": int((gp == op).all(axis=1).sum()), "payload_bit_errors_vs_sent_gpu": int(np.unpackbits(gp ^ sent, axis=1).sum()),
        "gpu_ms_per_batch": min(ms), "gpu_frames_per_s": n / min(ms) * 1e3, "stage_ms": stages,
-       "cpu_oracle_s": t_cpu, "cpu_frames_per_s": n / t_cpu, "cpu_threads": cores, "encode_s": t_enc}
+       "cpu_oracle_s": t_cpu, "cpu_frames_per_s": n / t_cpu, "cpu_threads": cores, "encode_s": t_enc, "stimulus": os.environ.get("STIM", "cpu")}
 print(json.dumps(res))
 json.dump(res, open(os.path.join(ROOT, "profiles", "config3_%s.json" % tag), "w"), indent=1)
 rx.close()
