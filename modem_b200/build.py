@@ -49,7 +49,9 @@ def _run(cmd, log):
         raise RuntimeError("build step failed: " + " ".join(cmd))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, helpers=True):
+    """helpers=False builds the product only (library + CLI drivers): the GPU test session uses that, so a problem with a
+    host-side test helper (emulator, host builds of the FFT / stimulus routines, the ThreadSanitizer harness) cannot stop it."""
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, h) for h in HDRS] + [os.path.abspath(__file__)]
@@ -71,22 +73,23 @@ def build(force=False, verbose=False):
     if os.path.exists(enc) and (rebuilt or _stale(ENCODE, [enc, LIB])):
         _run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), enc, "-o", ENCODE,
               "-L", PKG, "-lofdmrx", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], log)
-    emu = os.path.join(ROOT, "tests", "scl_emulator.cc")
-    if os.path.exists(emu) and (force or _stale(HOSTTEST, [emu, os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "host_tables.h")])):
-        _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", emu, os.path.join(CSRC, "host_tables.cc"), "-o", HOSTTEST], log)
-    ffth = os.path.join(ROOT, "tests", "fft_host.cu")
-    if os.path.exists(ffth) and (force or _stale(FFTHOST, [ffth, os.path.join(CSRC, "fft.cuh"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "host_tables.cc")])):
-        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC", "-shared", ffth,
-              os.path.join(CSRC, "host_tables.cc"), "-o", FFTHOST], log)
-    stim = os.path.join(ROOT, "tests", "stimulus_host.cu")
-    stim_deps = [stim] + [os.path.join(CSRC, f) for f in ("stimulus.cuh", "fft.cuh", "common.cuh", "host_tables.cc", "tx_tables.cc", "tx_tables.h")]
-    if os.path.exists(stim) and (force or _stale(STIMHOST, stim_deps)):
-        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", stim,
-              os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMHOST], log)
-    tsan = os.path.join(ROOT, "tests", "stimulus_cta_tsan.cu")
-    if os.path.exists(tsan) and (force or _stale(STIMTSAN, [tsan] + stim_deps[1:])):
-        _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O1", "-g", "-Xcompiler", "-fsanitize=thread,-ffp-contract=off,-pthread", tsan,
-              os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMTSAN], log)
+    if helpers:
+        emu = os.path.join(ROOT, "tests", "scl_emulator.cc")
+        if os.path.exists(emu) and (force or _stale(HOSTTEST, [emu, os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "host_tables.h")])):
+            _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", emu, os.path.join(CSRC, "host_tables.cc"), "-o", HOSTTEST], log)
+        ffth = os.path.join(ROOT, "tests", "fft_host.cu")
+        if os.path.exists(ffth) and (force or _stale(FFTHOST, [ffth, os.path.join(CSRC, "fft.cuh"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "host_tables.cc")])):
+            _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC", "-shared", ffth,
+                  os.path.join(CSRC, "host_tables.cc"), "-o", FFTHOST], log)
+        stim = os.path.join(ROOT, "tests", "stimulus_host.cu")
+        stim_deps = [stim] + [os.path.join(CSRC, f) for f in ("stimulus.cuh", "fft.cuh", "common.cuh", "host_tables.cc", "tx_tables.cc", "tx_tables.h")]
+        if os.path.exists(stim) and (force or _stale(STIMHOST, stim_deps)):
+            _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", stim,
+                  os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMHOST], log)
+        tsan = os.path.join(ROOT, "tests", "stimulus_cta_tsan.cu")
+        if os.path.exists(tsan) and (force or _stale(STIMTSAN, [tsan] + stim_deps[1:])):
+            _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++20", "-O1", "-g", "-Xcompiler", "-fsanitize=thread,-ffp-contract=off,-pthread", tsan,
+                  os.path.join(CSRC, "host_tables.cc"), os.path.join(CSRC, "tx_tables.cc"), "-o", STIMTSAN], log)
     with open(os.path.join(OBJ, "build.log"), "a") as f:
         f.write("\n".join(log))
     if verbose:

@@ -40,7 +40,7 @@ def _built_product(request):
     """GPU sessions need libofdmrx.so and the `decode` host driver: (re)build them when sources are newer (nvcc, in-tree)."""
     if "gpu" in (request.config.getoption("-m") or "") and "not gpu" not in (request.config.getoption("-m") or ""):
         from modem_b200 import build as B
-        B.build()
+        B.build(helpers=False)
 
 
 @pytest.fixture(scope="session")
