@@ -251,7 +251,10 @@ class Transmitter:
         payloads = np.ascontiguousarray(payloads, np.uint8).reshape(-1, self.frames_per_window * PAYLOAD_BYTES)
         n = payloads.shape[0]
         fmt = (FMT_S16_MONO if channels == 1 else FMT_S16_IQ) if fmt is None else fmt
-        stride = stride or self.window_samples(mode) + (64 if imp is not None and imp.sfo_ppm < 0 else 0)
+        if not stride:   # a negative SFO stretches the window: len / (1 + ppm 1e-6) sample frames
+            stride = self.window_samples(mode)
+            if imp is not None and imp.sfo_ppm < 0:
+                stride = int(stride / (1.0 + imp.sfo_ppm * 1e-6)) + 2
         out = np.zeros((n, stride), np.complex64) if fmt == FMT_F32_IQ else np.zeros((n, stride * (1 if fmt == FMT_S16_MONO else 2)), np.int16)
         ns = np.zeros(n, np.int32)
         cs = int(self._lib.ofdmtx_call_sign(call_sign))
