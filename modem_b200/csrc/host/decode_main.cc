@@ -1,6 +1,7 @@
 // modem_b200/csrc/host/decode_main.cc — `decode OUTPUT INPUT [SKIP]`: the reference receiver's command line
 // (/root/reference/decode.cc:559-620) as a thin C++ host driver over libofdmrx (include/ofdmrx.h).
-// Same argv rules, "-" for stdin/stdout, same stderr lines, always writes 5380 bytes and exits 0 once the WAV opened.
+// Same argv rules, "-" for stdin/stdout, same stderr lines (tests/test_cli_host.py diffs them against the reference's own
+// main() on the CPU through a mock of the library), always writes 5380 bytes and exits 0 once the WAV opened.
 // Extension: `decode --batch OUTPUT INPUT [SKIP]` treats INPUT as N back-to-back windows of 95200 frames (one
 // single-frame recording each) and writes N x 5380 bytes.  There is no CPU fallback: without a B200 it exits 1.
 #include "ofdmrx.h"
@@ -105,37 +106,68 @@ int main(int argc, char **argv)
 	int rc = ofdmrx_create(&h, 0, w.rate, std::min(n_frames, 4096), (int)stride);
 	if (rc) { std::cerr << "ofdmrx_create failed (" << rc << "): a B200 is required, there is no CPU path" << std::endl; return 1; }
 	std::vector<uint8_t> out((size_t)n_frames * OFDMRX_PAYLOAD_BYTES);
-	std::vector<ofdmrx_frame_status> st(n_frames);
 	if (w.pcm.size() < (size_t)n_frames * stride * w.channels) w.pcm.resize((size_t)n_frames * stride * w.channels, 0);
 	std::vector<int32_t> ns(n_frames, (int32_t)std::min<int64_t>(stride, total));
-	rc = ofdmrx_decode_batch(h, w.pcm.data(), OFDMRX_MEM_HOST, w.channels == 1 ? OFDMRX_FMT_S16_MONO : OFDMRX_FMT_S16_IQ, n_frames, stride,
-		ns.data(), skip, out.data(), st.data(), nullptr);
-	ofdmrx_destroy(h);
-	if (rc) { std::cerr << "ofdmrx_decode_batch failed (" << rc << ")" << std::endl; return 1; }
+	// The reference prints the header diagnostics of EVERY detection it consumes on the way to the SKIP-th one
+	// (decode.cc:390-448).  The library reports the last consumed detection of a call, so the driver asks for skip = 0, 1, ..
+	// SKIP in turn (the walk is deterministic: call k ends on detection k) and prints each new detection once.
+	std::vector<std::vector<ofdmrx_frame_status>> walk(skip + 1, std::vector<ofdmrx_frame_status>(n_frames));
+	for (int k = 0; k <= skip && !rc; ++k) {
+		rc = ofdmrx_decode_batch(h, w.pcm.data(), OFDMRX_MEM_HOST, w.channels == 1 ? OFDMRX_FMT_S16_MONO : OFDMRX_FMT_S16_IQ, n_frames, stride,
+			ns.data(), k, out.data(), walk[k].data(), nullptr);
+		bool any = false;
+		for (int i = 0; i < n_frames; ++i) any |= walk[k][i].detections == k + 1;
+		if (!any) break; // no window holds a detection k: larger skips end the same way (a huge SKIP costs one extra call)
+	}
+	if (rc) { ofdmrx_destroy(h); std::cerr << "ofdmrx_decode_batch failed (" << rc << ")" << std::endl; return 1; }
+	const int sym_len = 1280 * w.rate / 8000, pitch = sym_len + sym_len / 8;
 	for (int i = 0; i < n_frames; ++i) {
-		const ofdmrx_frame_status &s = st[i];
 		if (batch) std::cerr << "window " << i << ":" << std::endl;
-		if (s.detections > 0) {
+		const ofdmrx_frame_status *last = nullptr;
+		for (int k = 0; k <= skip; ++k) {
+			const ofdmrx_frame_status &s = walk[k][i];
+			if (s.detections != k + 1) break; // the stream ended before detection k
+			last = &s;
 			std::cerr << "symbol pos: " << s.symbol_pos << std::endl;
 			std::cerr << "coarse cfo: " << s.cfo_rad * ((float)w.rate / 6.28318530717958647692f) << " Hz " << std::endl;
+			switch (s.status) {
+			case OFDMRX_ST_OSD_FAIL: std::cerr << "OSD error." << std::endl; break;
+			case OFDMRX_ST_HDR_CRC: std::cerr << "header CRC error." << std::endl; break;
+			case OFDMRX_ST_BAD_MODE: case OFDMRX_ST_UNSUPPORTED_MODE: std::cerr << "operation mode " << s.mode << " unsupported." << std::endl; break;
+			case OFDMRX_ST_BAD_CALL: std::cerr << "oper mode: " << s.mode << std::endl << "call sign unsupported." << std::endl; break;
+			default: {
+				char cs[10];
+				base37(cs, (long long)((((uint64_t)s.md_hi << 32) | s.md_lo) >> 8), 9);
+				cs[9] = 0;
+				std::cerr << "oper mode: " << s.mode << std::endl << "call sign: " << cs << std::endl;
+			}
+			}
 		}
-		switch (s.status) {
-		case OFDMRX_ST_OSD_FAIL: std::cerr << "OSD error." << std::endl; break;
-		case OFDMRX_ST_HDR_CRC: std::cerr << "header CRC error." << std::endl; break;
-		case OFDMRX_ST_BAD_MODE: case OFDMRX_ST_UNSUPPORTED_MODE: std::cerr << "operation mode " << s.mode << " unsupported." << std::endl; break;
-		case OFDMRX_ST_BAD_CALL: std::cerr << "oper mode: " << s.mode << std::endl << "call sign unsupported." << std::endl; break;
-		default: break;
+		if (!last || last->detections != skip + 1 || (last->status != OFDMRX_ST_OK && last->status != OFDMRX_ST_PAYLOAD_CRC)) continue;
+		const ofdmrx_frame_status &s = *last;
+		static const int rows_of_mode[8] = {50, 54, 81, 90, 42, 56, 84, 126}; // cons_bits / mod_bits / cons_cols, decode.cc:302-374
+		const int rows = rows_of_mode[s.mode - 6];
+		std::cerr << "demod ";
+		for (int j = 0; j < rows; ++j) std::cerr << ".";
+		std::cerr << " done" << std::endl;
+		// per-row phase line and Es/N0 (decode.cc:479-523) from the stage taps of the chunk this window was decoded in
+		std::vector<float> ts((size_t)ofdmrx_tap_elems(h, OFDMRX_TAP_TS));
+		if (n_frames <= 4096 && ofdmrx_get_taps(h, OFDMRX_TAP_TS, i, 1, ts.data(), ts.size() * sizeof(float)) == 0) {
+			float sum_slope = 0, sum_yint = 0;
+			for (int j = 0; j < rows; ++j) { sum_slope += ts[3 * j]; sum_yint += ts[3 * j + 1]; }
+			// sfo_rad starts from an uninitialised member in the reference (decode.cc:210,500); zero is what a fresh heap gives
+			const float sfo_rad = 0.f - (sum_slope / rows) * sym_len / float(pitch);
+			const float cfo_rad = s.cfo_rad + (sum_yint / rows) / pitch;
+			std::cerr << "coarse sfo: " << 1000000 * sfo_rad / 6.28318530717958647692f << " ppm" << std::endl;
+			std::cerr << "finer cfo: " << cfo_rad * ((float)w.rate / 6.28318530717958647692f) << " Hz " << std::endl;
+			std::cerr << "Es/N0 (dB):";
+			for (int j = 0; j < rows; ++j) std::cerr << " " << 10.f * std::log10(ts[3 * j + 2]);
+			std::cerr << std::endl;
 		}
-		if (s.status == OFDMRX_ST_OK || s.status == OFDMRX_ST_PAYLOAD_CRC) {
-			char cs[10];
-			base37(cs, (long long)((((uint64_t)s.md_hi << 32) | s.md_lo) >> 8), 9);
-			cs[9] = 0;
-			std::cerr << "oper mode: " << s.mode << std::endl << "call sign: " << cs << std::endl;
-			std::cerr << "demod .................................................. done" << std::endl;
-			if (s.status == OFDMRX_ST_OK) std::cerr << "bit flips: " << s.flips << std::endl;
-			else std::cerr << "payload decoding error." << std::endl;
-		}
+		if (s.status == OFDMRX_ST_OK) std::cerr << "bit flips: " << s.flips << std::endl;
+		else std::cerr << "payload decoding error." << std::endl;
 	}
+	ofdmrx_destroy(h);
 	std::ofstream of(output_name, std::ios::binary | std::ios::trunc);
 	if (of.bad()) { std::cerr << "Couldn't open file \"" << output_name << "\" for writing." << std::endl; return 1; }
 	of.write(reinterpret_cast<const char *>(out.data()), out.size());

@@ -1,0 +1,65 @@
+// tests/mock_ofdmrx.cc — TEST HELPER.  A CPU stand-in for libofdmrx.so's C-ABI (include/ofdmrx.h) built on the oracle, so that
+// the product's host drivers (modem_b200/csrc/host/decode_main.cc) can be exercised without a GPU: argv handling, WAV parsing,
+// the SKIP walk and every stderr line are then diffed against the reference's own main() (oracle/_ref/decode) by
+// tests/test_cli_host.py.  Never shipped, never linked into the product: the real library has no CPU path.
+#include "../include/ofdmrx.h"
+#include "../oracle/ref_modem.hh"
+#include <cstring>
+#include <vector>
+
+struct ofdmrx_handle {
+	int rate, max_frames;
+	std::vector<std::vector<float>> ts; // per window of the last call: slope, yint, precision per row
+};
+
+extern "C" {
+
+const char *ofdmrx_version(void) { return "mock over the CPU oracle (tests only)"; }
+int ofdmrx_create(ofdmrx_t **h, int, int rate_hz, int max_frames, int)
+{
+	if (rate_hz != 8000 && rate_hz != 16000 && rate_hz != 44100 && rate_hz != 48000) return -22;
+	*h = new ofdmrx_handle{rate_hz, max_frames, {}};
+	return 0;
+}
+void ofdmrx_destroy(ofdmrx_t *h) { delete h; }
+int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int format, int n_frames, int64_t stride, const int32_t *n_samples,
+	int skip, uint8_t *payload_out, ofdmrx_frame_status *st, void *)
+{
+	if (mem_kind != OFDMRX_MEM_HOST || format > OFDMRX_FMT_S16_IQ) return -22;
+	const int ch = format == OFDMRX_FMT_S16_MONO ? 1 : 2;
+	h->ts.assign(n_frames, std::vector<float>(126 * 3, 0.f));
+	for (int i = 0; i < n_frames; ++i) {
+		const int16_t *pcm = (const int16_t *)samples + (size_t)i * stride * ch;
+		const int64_t n = n_samples ? n_samples[i] : stride;
+		std::vector<float> f((size_t)n * ch);
+		for (size_t k = 0; k < f.size(); ++k) f[k] = float(pcm[k]) / 32767.f;
+		ref::Receiver rx(h->rate);
+		uint8_t buf[ref::kDataBytes];
+		std::memset(buf, 0, sizeof(buf));
+		int status = rx.run(buf, f.data(), (size_t)n, ch, skip);
+		ref::descramble(buf);
+		std::memcpy(payload_out + (size_t)i * ref::kDataBytes, buf, ref::kDataBytes);
+		const ref::Taps &t = rx.taps;
+		if (st) {
+			ofdmrx_frame_status &s = st[i];
+			std::memset(&s, 0, sizeof(s));
+			s.status = status; s.detections = t.detections; s.t_fire = t.t_fire; s.symbol_pos = t.symbol_pos; s.sc_pos = t.sc_pos;
+			s.index_max = t.index_max; s.shift = t.shift; s.pos_err = t.pos_err; s.timing_max = t.timing_max; s.frac_cfo = t.frac_cfo;
+			s.cfo_rad = t.cfo_rad; s.osd_unique = t.osd_unique; s.mode = t.mode; s.md_lo = (uint32_t)t.md; s.md_hi = (uint32_t)(t.md >> 32);
+			s.best_lane = t.best_lane; s.flips = t.flips;
+		}
+		for (size_t j = 0; j < t.slope.size() && j < 126; ++j) {
+			h->ts[i][3 * j] = t.slope[j]; h->ts[i][3 * j + 1] = t.yint[j]; h->ts[i][3 * j + 2] = t.precision[j];
+		}
+	}
+	return 0;
+}
+int64_t ofdmrx_tap_elems(ofdmrx_t *, int stage) { return stage == OFDMRX_TAP_TS ? 126 * 3 : -22; }
+int ofdmrx_get_taps(ofdmrx_t *h, int stage, int first, int count, void *dst, size_t bytes)
+{
+	if (stage != OFDMRX_TAP_TS || first < 0 || first + count > (int)h->ts.size() || bytes < (size_t)count * 126 * 3 * 4) return -22;
+	for (int i = 0; i < count; ++i) std::memcpy((float *)dst + (size_t)i * 126 * 3, h->ts[first + i].data(), 126 * 3 * 4);
+	return 0;
+}
+
+} // extern "C"
