@@ -63,10 +63,10 @@ int main(int argc, char **argv)
 	std::memcpy(&o[0], "RIFF", 4); wr32(4, (uint32_t)(36 + n * bytes)); std::memcpy(&o[8], "WAVEfmt ", 8);
 	wr32(16, 16); wr16(20, 1); wr16(22, chan); wr32(24, rate); wr32(28, rate * chan * bytes);
 	wr16(32, chan * bytes); wr16(34, bits); std::memcpy(&o[36], "data", 4); wr32(40, (uint32_t)(n * bytes));
-	const double fac = std::ldexp(1.0, bits - 1) - 1.0; // DSP::WritePCM scale: 2^(bits-1) - 1, 8-bit samples offset by 128
+	const float fac = (float)(std::ldexp(1.0, bits - 1) - 1.0); // DSP::WritePCM scale: 2^(bits-1) - 1 in fp32, 8-bit samples offset by 128
 	for (size_t i = 0; i < n; ++i) {
 		const float x = std::min(std::max(chan == 2 ? iq[i] : iq[2 * i], -1.f), 1.f);
-		const int64_t v = (int64_t)std::nearbyint(fac * (double)x) + (bytes == 1 ? 128 : 0);
+		const int64_t v = std::min<int64_t>((int64_t)std::nearbyint(fac * x), 2147483647LL) + (bytes == 1 ? 128 : 0);
 		for (int b = 0; b < bytes; ++b) o[44 + i * bytes + b] = (uint8_t)((v >> (8 * b)) & 255);
 	}
 	std::ofstream out(output_name, std::ios::binary | std::ios::trunc);

@@ -3,9 +3,12 @@
 // the SKIP walk and every stderr line are then diffed against the reference's own main() (oracle/_ref/decode) by
 // tests/test_cli_host.py.  Never shipped, never linked into the product: the real library has no CPU path.
 #include "../include/ofdmrx.h"
+#include "../include/ofdmtx.h"
 #include "../oracle/ref_modem.hh"
 #include <cstring>
 #include <vector>
+
+struct ofdmtx_handle { int rate, fpw; };
 
 struct ofdmrx_handle {
 	int rate, max_frames;
@@ -61,5 +64,43 @@ int ofdmrx_get_taps(ofdmrx_t *h, int stage, int first, int count, void *dst, siz
 	for (int i = 0; i < count; ++i) std::memcpy((float *)dst + (size_t)i * 126 * 3, h->ts[first + i].data(), 126 * 3 * 4);
 	return 0;
 }
+
+// ---- include/ofdmtx.h over the oracle's transmitter: clean streams only, float I/Q or 16-bit output to host memory
+int ofdmtx_create(ofdmtx_t **h, int, int rate_hz, int, int frames_per_window)
+{
+	if (rate_hz != 8000 && rate_hz != 16000 && rate_hz != 44100 && rate_hz != 48000) return -22;
+	*h = new ofdmtx_handle{rate_hz, frames_per_window};
+	return 0;
+}
+void ofdmtx_destroy(ofdmtx_t *h) { delete h; }
+int64_t ofdmtx_call_sign(const char *str) { return ref::base37_encode(str); }
+int64_t ofdmtx_window_samples(int rate_hz, int mode, int frames_per_window)
+{
+	ref::ModeParams mp{};
+	if (!ref::mode_params(mode, mp)) return -22;
+	const int pitch = 1440 * rate_hz / 8000;
+	return 2LL * rate_hz + (2LL + (long long)frames_per_window * (3 + mp.cons_rows())) * pitch;
+}
+int ofdmtx_encode_batch(ofdmtx_t *h, const uint8_t *payloads, int, int n_windows, int mode, int64_t call_sign, int freq_off_hz,
+	const ofdmtx_impairments *imp, void *samples_out, int mem_kind, int format, int64_t stride, int32_t *n_samples_out, void *)
+{
+	if (mem_kind != OFDMRX_MEM_HOST || imp) return -22;
+	if (!ref::Transmitter::check_args(h->rate, format == OFDMRX_FMT_S16_MONO ? 1 : 2, freq_off_hz, mode, call_sign)) return -22;
+	for (int i = 0; i < n_windows; ++i) {
+		ref::Transmitter tx(h->rate);
+		std::vector<ref::cf> s;
+		if (!tx.encode(s, payloads + (size_t)i * h->fpw * ref::kDataBytes, h->fpw, freq_off_hz, call_sign, mode)) return -22;
+		if ((int64_t)s.size() > stride) return -22;
+		for (size_t n = 0; n < s.size(); ++n) {
+			if (format == OFDMRX_FMT_F32_IQ) { ((float *)samples_out)[2 * ((size_t)i * stride + n)] = s[n].re; ((float *)samples_out)[2 * ((size_t)i * stride + n) + 1] = s[n].im; }
+			else if (format == OFDMRX_FMT_S16_IQ) { ((int16_t *)samples_out)[2 * ((size_t)i * stride + n)] = ref::quantize16(s[n].re); ((int16_t *)samples_out)[2 * ((size_t)i * stride + n) + 1] = ref::quantize16(s[n].im); }
+			else ((int16_t *)samples_out)[(size_t)i * stride + n] = ref::quantize16(s[n].re);
+		}
+		if (n_samples_out) n_samples_out[i] = (int32_t)s.size();
+	}
+	return 0;
+}
+int ofdmtx_get_code(ofdmtx_t *, int, int, uint32_t *) { return -38; }
+int ofdmtx_last_launches(ofdmtx_t *) { return 0; }
 
 } // extern "C"

@@ -24,6 +24,7 @@ def cli(oracle):
     inc = os.path.join(ROOT, "include")
     subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", inc, os.path.join(ROOT, "tests", "mock_ofdmrx.cc"), "-o", lib], check=True)
     subprocess.run(["g++", "-std=c++17", "-O2", "-I", inc, os.path.join(B.CSRC, "host", "decode_main.cc"), "-o", exe, "-L", d, "-lofdmrx", "-Wl,-rpath," + d], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", inc, os.path.join(B.CSRC, "host", "encode_main.cc"), "-o", os.path.join(d, "encode"), "-L", d, "-lofdmrx", "-Wl,-rpath," + d], check=True)
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
     return exe
 
@@ -101,3 +102,40 @@ def test_batch_extension(cli, oracle, tmp_path):
     p = subprocess.run([cli, "--batch", str(tmp_path / "b.dat"), str(tmp_path / "b.wav")], capture_output=True)
     assert p.returncode == 0 and (tmp_path / "b.dat").read_bytes() == sent.tobytes()
     assert p.stderr.count(b"bit flips: 0") == 3 and b"window 2:" in p.stderr
+
+
+@needs_reference
+@pytest.mark.parametrize("args", [["8000", "16", "1", "2000", "6", "CALLSIGN"], ["8000", "8", "1", "2000", "6", "ANONYMOUS"], ["8000", "16", "2", "-450", "9", "dl1abc"],
+                                  ["16000", "24", "2", "3000", "10", "A"], ["48000", "32", "1", "1600", "12", "Q 1"]])
+def test_encode_driver_writes_the_reference_bytes(cli, oracle, tmp_path, args):
+    """modem_b200/csrc/host/encode_main.cc over the mock (the oracle's float stream behind include/ofdmtx.h): header, sample
+    widths, channel selection and quantisation of the WAV writer against the reference's own encode main()"""
+    names = []
+    for i in range(2):
+        (tmp_path / ("in%d.dat" % i)).write_bytes(oracle.make_payload(70 + i).tobytes())
+        names.append(str(tmp_path / ("in%d.dat" % i)))
+    enc = os.path.join(os.path.dirname(cli), "encode")
+    p = subprocess.run([enc, str(tmp_path / "p.wav")] + args + names, capture_output=True)
+    r = subprocess.run([os.path.join(T.REF, "encode"), str(tmp_path / "r.wav")] + args + names, capture_output=True)
+    assert p.returncode == r.returncode == 0, (p.stderr, r.stderr)
+    pw, rw = (tmp_path / "p.wav").read_bytes(), (tmp_path / "r.wav").read_bytes()
+    assert len(pw) == len(rw) and pw[:44] == rw[:44]
+    if args[1] != "32":
+        assert pw == rw
+    else:   # 2^31 - 1 is not a float: the last bits of a 32-bit sample depend on where the product is rounded
+        d = np.abs(np.frombuffer(pw[44:], "<i4").astype(np.int64) - np.frombuffer(rw[44:], "<i4").astype(np.int64))
+        assert d.max() <= 256
+
+
+@needs_reference
+def test_encode_driver_argument_errors(cli, tmp_path):
+    (tmp_path / "in.dat").write_bytes(bytes(5380))
+    enc = os.path.join(os.path.dirname(cli), "encode")
+    for args in (["8000", "16", "1", "2000", "5", "CALLSIGN"], ["8000", "16", "1", "2000", "6", "call-sign"], ["8000", "16", "1", "2000", "6", "TENLETTERS"],
+                 ["8000", "16", "1", "1300", "6", "CALLSIGN"], ["8000", "16", "2", "2700", "6", "CALLSIGN"], ["8000", "16", "1", "2025", "6", "CALLSIGN"],
+                 ["22050", "16", "1", "2000", "6", "CALLSIGN"]):
+        p = subprocess.run([enc, str(tmp_path / "x.wav")] + args + [str(tmp_path / "in.dat")], capture_output=True)
+        r = subprocess.run([os.path.join(T.REF, "encode"), str(tmp_path / "y.wav")] + args + [str(tmp_path / "in.dat")], capture_output=True)
+        assert p.returncode == r.returncode == 1 and p.stderr == r.stderr, (args, p.stderr, r.stderr)
+    p = subprocess.run([enc], capture_output=True)
+    assert p.returncode == 1 and b"usage:" in p.stderr
