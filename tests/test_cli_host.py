@@ -139,3 +139,32 @@ def test_encode_driver_argument_errors(cli, tmp_path):
         assert p.returncode == r.returncode == 1 and p.stderr == r.stderr, (args, p.stderr, r.stderr)
     p = subprocess.run([enc], capture_output=True)
     assert p.returncode == 1 and b"usage:" in p.stderr
+
+
+def test_python_mirror_plumbing_through_the_mock(cli, oracle, tmp_path, monkeypatch):
+    """modem_b200's ctypes layer (argument order and types of every call it makes) against the mock library: Transmitter.encode,
+    Receiver.decode and decode_wav return what the oracle returns.  The product itself never loads anything but libofdmrx.so."""
+    import modem_b200 as M
+    monkeypatch.setattr(M, "LIB_PATH", os.path.join(os.path.dirname(cli), "libofdmrx.so"))
+    monkeypatch.setattr(M, "_lib", None)
+    try:
+        pls = np.stack([oracle.make_payload(880 + i) for i in range(2)])
+        tx = M.Transmitter(max_windows=2)
+        assert tx.window_samples(6) == 95200 and tx.window_samples(13) == oracle.frame_samples(13)
+        for ch in (1, 2):
+            pcm, ns = tx.encode(pls, channels=ch)
+            assert (ns == 95200).all()
+            for i in range(2):
+                assert (pcm[i].reshape(-1) == oracle.encode(pls[i], channels=ch).reshape(-1)).all()
+        iq, ns = tx.encode(pls[:1], fmt=M.FMT_F32_IQ)
+        assert iq.dtype == np.complex64 and iq.shape == (1, 95200) and abs(np.abs(iq[0, 8000:87200]) ** 2).mean() > 0.05
+        tx.close()
+        rx = M.Receiver(max_frames=2)
+        payload, st = rx.decode(pcm, channels=2)
+        assert (payload == pls).all() and (st["status"] == 0).all() and (st["mode"] == 6).all() and M.call_sign(st[0]) == " CALLSIGN"
+        rx.close()
+        T.write_wav(tmp_path / "w.wav", oracle.encode(pls[1]), 8000, 1)
+        data, s = M.decode_wav(str(tmp_path / "w.wav"))
+        assert data == pls[1].tobytes() and s["flips"] == 0
+    finally:
+        M._lib = None   # later tests must bind the real library again
