@@ -92,13 +92,24 @@ int64_t ofdmtx_window_samples(int rate_hz, int mode, int frames_per_window)
 int ofdmtx_encode_batch(ofdmtx_t *h, const uint8_t *payloads, int, int n_windows, int mode, int64_t call_sign, int freq_off_hz,
 	const ofdmtx_impairments *imp, void *samples_out, int mem_kind, int format, int64_t stride, int32_t *n_samples_out, void *)
 {
-	if (mem_kind != OFDMRX_MEM_HOST || imp) return -22;
+	if (mem_kind != OFDMRX_MEM_HOST) return -22;
 	if (!ref::Transmitter::check_args(h->rate, format == OFDMRX_FMT_S16_MONO ? 1 : 2, freq_off_hz, mode, call_sign)) return -22;
 	for (int i = 0; i < n_windows; ++i) {
 		ref::Transmitter tx(h->rate);
 		std::vector<ref::cf> s;
 		if (!tx.encode(s, payloads + (size_t)i * h->fpw * ref::kDataBytes, h->fpw, freq_off_hz, call_sign, mode)) return -22;
+		if (imp) { // the oracle's chain (its own mt19937 noise: the mock is about plumbing, not about the Philox stream)
+			ref::Impair im;
+			im.multipath = imp->multipath != 0; im.cfo_hz = imp->cfo_hz; im.sfo_ppm = imp->sfo_ppm; im.awgn = imp->awgn != 0;
+			im.awgn_db = imp->awgn_db; im.seed = imp->seed + (uint64_t)i;
+			ref::apply_impairments(s, h->rate, im);
+		}
 		if ((int64_t)s.size() > stride) return -22;
+		for (int64_t n = (int64_t)s.size(); n < stride; ++n) { // zero-fill behind the window
+			if (format == OFDMRX_FMT_F32_IQ) { ((float *)samples_out)[2 * ((size_t)i * stride + n)] = 0.f; ((float *)samples_out)[2 * ((size_t)i * stride + n) + 1] = 0.f; }
+			else if (format == OFDMRX_FMT_S16_IQ) { ((int16_t *)samples_out)[2 * ((size_t)i * stride + n)] = 0; ((int16_t *)samples_out)[2 * ((size_t)i * stride + n) + 1] = 0; }
+			else ((int16_t *)samples_out)[(size_t)i * stride + n] = 0;
+		}
 		for (size_t n = 0; n < s.size(); ++n) {
 			if (format == OFDMRX_FMT_F32_IQ) { ((float *)samples_out)[2 * ((size_t)i * stride + n)] = s[n].re; ((float *)samples_out)[2 * ((size_t)i * stride + n) + 1] = s[n].im; }
 			else if (format == OFDMRX_FMT_S16_IQ) { ((int16_t *)samples_out)[2 * ((size_t)i * stride + n)] = ref::quantize16(s[n].re); ((int16_t *)samples_out)[2 * ((size_t)i * stride + n) + 1] = ref::quantize16(s[n].im); }

@@ -166,5 +166,15 @@ def test_python_mirror_plumbing_through_the_mock(cli, oracle, tmp_path, monkeypa
         T.write_wav(tmp_path / "w.wav", oracle.encode(pls[1]), 8000, 1)
         data, s = M.decode_wav(str(tmp_path / "w.wav"))
         assert data == pls[1].tobytes() and s["flips"] == 0
+        # the probes' window source (tools/_stimulus.py) with STIM=device: same payloads and impairment definitions as the CPU path
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import _stimulus
+        kw = dict(multipath=True, cfo_hz=234.567, sfo_ppm=147.0, awgn_db=-30.0, seed=21)
+        monkeypatch.setenv("STIM", "cpu")
+        c_pcm, c_ns, c_sent = _stimulus.windows(2, 300, channels=2, imp=kw)
+        monkeypatch.setenv("STIM", "device")
+        d_pcm, d_ns, d_sent = _stimulus.windows(2, 300, channels=2, imp=kw)
+        assert (c_sent == d_sent).all() and (c_ns == d_ns).all() and (c_pcm == d_pcm).all()
     finally:
         M._lib = None   # later tests must bind the real library again
