@@ -40,6 +40,15 @@ int main(int argc, char **argv)
 		std::cerr << "demod ";
 		for (size_t j = 0; j < t.slope.size(); ++j) std::cerr << ".";
 		std::cerr << " done" << std::endl;
+		{ // decode.cc:480,491-503; sfo_rad is an uninitialised member there (decode.cc:210): zero, as a fresh heap gives
+			float sum_slope = 0, sum_yint = 0;
+			for (size_t j = 0; j < t.slope.size(); ++j) { sum_slope += t.slope[j]; sum_yint += t.yint[j]; }
+			const int symbol_len = 1280 * w.rate / 8000, guard_len = symbol_len / 8, rows = (int)t.slope.size();
+			const float sfo_rad = 0.f - (sum_slope / rows) * symbol_len / float(symbol_len + guard_len);
+			const float cfo_rad = t.cfo_rad + (sum_yint / rows) / (symbol_len + guard_len);
+			std::cerr << "coarse sfo: " << 1000000 * sfo_rad / kTwoPi << " ppm" << std::endl;
+			std::cerr << "finer cfo: " << cfo_rad * (w.rate / kTwoPi) << " Hz " << std::endl;
+		}
 		std::cerr << "Es/N0 (dB):";
 		for (float p : t.precision) std::cerr << " " << 10.f * std::log10(p);
 		std::cerr << std::endl;

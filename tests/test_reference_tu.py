@@ -30,8 +30,7 @@ def ref_bins(oracle):
 
 
 def _stderr_lines(b):
-    """decode.cc's stderr without the two lines the oracle CLI does not print (they read an uninitialised member, decode.cc:210,500)"""
-    return [l for l in b.decode().splitlines() if not l.startswith(("coarse sfo:", "finer cfo:"))]
+    return b.decode().splitlines()
 
 
 def write_wav(path, pcm, rate, channels):
