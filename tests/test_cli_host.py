@@ -178,3 +178,39 @@ def test_python_mirror_plumbing_through_the_mock(cli, oracle, tmp_path, monkeypa
         assert (c_sent == d_sent).all() and (c_ns == d_ns).all() and (c_pcm == d_pcm).all()
     finally:
         M._lib = None   # later tests must bind the real library again
+
+
+@needs_reference
+def test_integration_binding_compiles_into_the_reference_main(cli, oracle, tmp_path):
+    """INTEGRATION.md §2 for real: tests/integration/decode_cc_binding.inc spliced into a scratch copy of the reference's
+    decode.cc (nothing of the reference is kept in the repository), compiled over oracle/shim/ and linked to the mock of the
+    C-ABI — the patched binary returns the payload through ofdmrx_decode_batch and skips the reference's own Decoder."""
+    src = open(os.path.join(T.REFSRC, "decode.cc")).read().split("\n")
+    inc = open(os.path.join(ROOT, "tests", "integration", "decode_cc_binding.inc")).read()
+    out, state = [], 0
+    for ln in src:
+        if state == 0 and ln.startswith("#include \"polar_list_decoder.hh\""):
+            out += [ln, "#include <vector>", "#include \"ofdmrx.h\""]
+            continue
+        if ln.strip() == "switch (input_file.rate()) {":
+            out += [inc, "\tif (!ofdmrx_done)"]          # the reference's CPU path stays as the fallback
+            state = 1
+        if ln.strip() == "CODE::Xorshift32 scrambler;":
+            out.append("\tif (!ofdmrx_done) {")          # the library already de-scrambled
+            state = 2
+        out.append(ln)
+        if state == 2 and "output_data[i] ^= scrambler();" in ln:
+            out.append("\t}")
+            state = 3
+    assert state == 3
+    (tmp_path / "decode_patched.cc").write_text("\n".join(out))
+    d = os.path.dirname(cli)
+    exe = str(tmp_path / "decode_patched")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-strict-aliasing", "-D__AVX2__=1", "-I", os.path.join(ROOT, "oracle", "shim"),
+                    "-I", T.REFSRC, "-I", os.path.join(ROOT, "include"), str(tmp_path / "decode_patched.cc"), "-o", exe, "-L", d, "-lofdmrx", "-Wl,-rpath," + d], check=True)
+    pls = np.stack([oracle.make_payload(990 + i) for i in range(2)])
+    T.write_wav(tmp_path / "two.wav", oracle.encode(pls, channels=2, imp=oracle.impair(cfo_hz=12.5, awgn_db=-26.0, seed=2)), 8000, 2)
+    for skip in (0, 1):
+        r = subprocess.run([exe, str(tmp_path / "o.dat"), str(tmp_path / "two.wav"), str(skip)], capture_output=True)
+        assert r.returncode == 0 and (tmp_path / "o.dat").read_bytes() == pls[skip].tobytes()
+        assert b"demod" not in r.stderr          # the reference's own Decoder did not run
