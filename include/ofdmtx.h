@@ -20,7 +20,7 @@ typedef struct ofdmtx_handle ofdmtx_t;
 /* The impairment chain in README.md:49 order.  aicodix/disorders is not part of the reference repository; these are the
  * definitions the CPU oracle uses (oracle/ref_modem.hh: apply_impairments): a fixed 4-tap sparse complex FIR, a complex
  * mixer, 33-tap Kaiser-windowed-sinc resampling by (1 + ppm 1e-6), complex Gaussian noise of total variance
- * 10^(awgn_db / 10).  Window i draws its noise from a Philox stream keyed by seed + i. */
+ * 10^(awgn_db / 10).  Window i of a call draws its noise from the Philox-4x32-10 stream with key `seed` and counter (sample index, i). */
 typedef struct ofdmtx_impairments {
 	int32_t multipath; /* 0 / 1 */
 	float cfo_hz;

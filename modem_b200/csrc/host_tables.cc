@@ -38,57 +38,87 @@ static bool all_frozen(const std::vector<uint32_t> &fr, int index, int n)
 		if (fr[w] != 0xffffffffu) return false;
 	return true;
 }
-// number of F steps that can be chained below a node of `level` at `index` whose alpha has just been produced:
-// the node must be an internal node above the 32-leaf words (level >= 6) and must not be a rate-0 node.
-static int chain_len(const std::vector<uint32_t> &fr, int level, int index, int max_more)
+static bool all_free(const std::vector<uint32_t> &fr, int index, int n)
 {
-	int n = 0;
-	while (n < max_more && level >= 6 && !all_frozen(fr, index, 1 << level)) { ++n; --level; }
-	return n;
+	for (int w = index / 32; w < (index + n) / 32; ++w)
+		if (fr[w] != 0u) return false;
+	return true;
 }
-// skip_f: this node's own F step was already performed by a fused op of an ancestor (skip_f - 1 more follow)
-static void gen(std::vector<uint32_t> &ops, const std::vector<uint32_t> &fr, int level, int index, int skip_f, int max_depth, bool top)
-{
-	const int n = 1 << level;
-	if (top && level > kSclTopLevel) { // virtual node: its children are produced from the channel values by TOP ops
-		for (int half = 0; half < 2; ++half) {
-			const int ci = index + half * (n / 2);
-			if (level - 1 == kSclTopLevel) {
-				const int more = 1; // the kernel's TOP op always produces the left child too (no rate-0 node up here)
-				ops.push_back(scl_pack(OP_TOP, kSclTopLevel, ci, 1 + more));
-				gen(ops, fr, kSclTopLevel, ci, more, max_depth, top);
-			} else {
-				gen(ops, fr, level - 1, ci, 0, max_depth, top);
-			}
-		}
-		ops.push_back(scl_pack(OP_C, level, index));
-		return;
-	}
-	if (all_frozen(fr, index, n)) { ops.push_back(scl_pack(OP_R0, level, index)); return; }
-	if (level == 5) { ops.push_back(scl_pack(OP_WORD, level, index)); return; }
-	int pass_down = 0;
-	if (skip_f > 0) pass_down = skip_f - 1;
-	else {
-		const int more = chain_len(fr, level - 1, index, max_depth - 1);
-		ops.push_back(scl_pack(OP_F, level, index, 1 + more));
-		pass_down = more;
-	}
-	gen(ops, fr, level - 1, index, pass_down, max_depth, top);
-	const int more = chain_len(fr, level - 1, index + n / 2, max_depth - 1);
-	ops.push_back(scl_pack(OP_G, level, index, 1 + more));
-	gen(ops, fr, level - 1, index + n / 2, more, max_depth, top);
-	ops.push_back(scl_pack(OP_C, level, index));
-}
-std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth, bool top_ops)
-{
+namespace {
+struct SclGen {
 	std::vector<uint32_t> ops;
+	const std::vector<uint32_t> &fr;
+	int max_depth;
+	bool top, r1;
+	// a node gets a rate-1 attempt (OP_R1) when it is all-free, sits above the 32-leaf words and is not the left child of a
+	// rate-1 node (whose attempt has the same operands: same metrics, same minimum — it would fail again)
+	bool tries(int level, int index, bool notry) const { return r1 && !notry && level >= 6 && level <= kSclR1MaxLevel && all_free(fr, index, 1 << level); }
+	// number of F steps that can be chained below a node of `level` at `index` whose alpha has just been produced: the node must
+	// be an internal node above the 32-leaf words (level >= 6), not a rate-0 node and not a node that starts with a rate-1 attempt
+	int chain_len(int level, int index, int max_more, bool notry) const
+	{
+		int n = 0;
+		while (n < max_more && level >= 6 && !all_frozen(fr, index, 1 << level)) {
+			if (tries(level, index, notry)) break;
+			notry = r1 && all_free(fr, index, 1 << level);
+			++n; --level;
+		}
+		return n;
+	}
+	// skip_f: this node's own F step was already performed by a fused op of an ancestor (skip_f - 1 more follow)
+	void gen(int level, int index, int skip_f, bool notry)
+	{
+		const int n = 1 << level;
+		if (top && level > kSclTopLevel) { // virtual node: its children are produced from the channel values by TOP ops
+			for (int half = 0; half < 2; ++half) {
+				const int ci = index + half * (n / 2);
+				if (level - 1 == kSclTopLevel) {
+					const int more = 1; // the kernel's TOP op always produces the left child too (no rate-0 / rate-1 node up here)
+					ops.push_back(scl_pack(OP_TOP, kSclTopLevel, ci, 1 + more));
+					gen(kSclTopLevel, ci, more, false);
+				} else {
+					gen(level - 1, ci, 0, false);
+				}
+			}
+			ops.push_back(scl_pack(OP_C, level, index));
+			return;
+		}
+		if (all_frozen(fr, index, n)) { ops.push_back(scl_pack(OP_R0, level, index)); return; }
+		if (level == 5) { ops.push_back(scl_pack(OP_WORD, level, index)); return; }
+		const bool rate1 = r1 && all_free(fr, index, n);
+		size_t patch = 0;
+		if (tries(level, index, notry)) { // OP_R1 + the pc to continue at when the attempt succeeds
+			ops.push_back(scl_pack(OP_R1, level, index));
+			patch = ops.size();
+			ops.push_back(0);
+		}
+		int pass_down = 0;
+		if (skip_f > 0) pass_down = skip_f - 1;
+		else {
+			const int more = chain_len(level - 1, index, max_depth - 1, rate1);
+			ops.push_back(scl_pack(OP_F, level, index, 1 + more));
+			pass_down = more;
+		}
+		gen(level - 1, index, pass_down, rate1);
+		const int more = chain_len(level - 1, index + n / 2, max_depth - 1, false);
+		ops.push_back(scl_pack(OP_G, level, index, 1 + more));
+		gen(level - 1, index + n / 2, more, false);
+		ops.push_back(scl_pack(OP_C, level, index));
+		if (patch) ops[patch] = (uint32_t)ops.size();
+	}
+};
+} // namespace
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth, bool top_ops, bool r1_ops)
+{
 	max_depth = std::max(1, std::min(max_depth, kSclMaxFuse));
-	// TOP ops need no rate-0 node at or above the top level (true for both tables of the reference: the largest is R0-2048)
+	// TOP ops need no rate-0 node at or above the top level (true for both tables of the reference: the largest are R0-2048 and
+	// R1-2048; rate-1 attempts stop at level kSclR1MaxLevel < kSclTopLevel)
 	for (int i = 0; top_ops && i < (1 << order); i += 1 << kSclTopLevel)
 		if (all_frozen(frozen, i, 1 << kSclTopLevel)) top_ops = false;
-	gen(ops, frozen, order, 0, 0, max_depth, top_ops && order > kSclTopLevel);
-	ops.push_back(scl_pack(OP_END, 0, 0));
-	return ops;
+	SclGen g{{}, frozen, max_depth, top_ops && order > kSclTopLevel, r1_ops};
+	g.gen(order, 0, 0, false);
+	g.ops.push_back(scl_pack(OP_END, 0, 0));
+	return g.ops;
 }
 
 std::vector<uint8_t> mls_bits(int poly, int n)

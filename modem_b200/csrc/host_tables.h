@@ -69,8 +69,15 @@ std::vector<uint32_t> make_frozen(int order, int n_tx, int k_info);
 //   TOP(13, idx) alpha_13 of the level-13 node at idx recomputed straight from the channel LLRs and the partial sums of its
 //                left-hand relatives (levels 16..14 are then never materialised: their alphas are functions of the
 //                lane-shared channel values and a few beta bits)
-enum SclOp : uint32_t { OP_F = 0, OP_G = 1, OP_WORD = 2, OP_R0 = 3, OP_C = 4, OP_TOP = 5, OP_END = 7 };
+//   R1(l, idx)   rate-1 attempt on a maximal all-free node (6 <= l <= kSclR1MaxLevel), followed by one extra word = the pc to continue at
+//                when it succeeds: if the lanes are in metric order and every lane's  metric + min|alpha_l|  exceeds the
+//                largest metric, no fork inside the node can change the list, so beta = sign bits of alpha_l, metrics and
+//                lanes stay as they are (exact: the smallest |leaf LLR| of a sign-following path IS min|alpha_l|, every
+//                other leaf's is a rounded sum >= it).  Otherwise the ops of the sub-tree follow as usual; the left spine
+//                of a rate-1 node carries no further attempts (same metrics, same minimum).
+enum SclOp : uint32_t { OP_F = 0, OP_G = 1, OP_WORD = 2, OP_R0 = 3, OP_C = 4, OP_TOP = 5, OP_R1 = 6, OP_END = 7 };
 constexpr int kSclTopLevel = 13;
+constexpr int kSclR1MaxLevel = 12;
 constexpr int kSclMaxFuse = 2; // longest op chain the kernel instantiates: the op itself + one F step
 // F and G carry a fusion depth d = 1..3 in bits 30..31 (stored as d-1): the op also performs the d-1 F steps that always
 // follow it on the way down the left spine (F(l-1), F(l-2)), so those levels are produced in registers and written once.
@@ -79,7 +86,7 @@ static inline uint32_t scl_op(uint32_t w) { return w & 7; }
 static inline uint32_t scl_level(uint32_t w) { return (w >> 3) & 31; }
 static inline uint32_t scl_index(uint32_t w) { return ((w >> 8) & 0x3fffffu) * 32; }
 static inline uint32_t scl_depth(uint32_t w) { return (w >> 30) + 1; }
-std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth = kSclMaxFuse, bool top_ops = true);
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth = kSclMaxFuse, bool top_ops = true, bool r1_ops = true);
 
 // ---- misc sequences / codes -----------------------------------------------------------------------------------
 std::vector<uint8_t> mls_bits(int poly, int n);              // first n outputs of the Galois LFSR (reg = 1)

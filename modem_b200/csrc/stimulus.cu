@@ -303,7 +303,7 @@ int ofdmtx_encode_batch(ofdmtx_t *h, const uint8_t *payloads, int payload_mem, i
 		}
 		char *dst = mem_kind == OFDMRX_MEM_HOST ? (char *)h->d_out : (char *)samples_out + (size_t)w0 * stride * sample_bytes;
 		TxImpair imw = im;
-		imw.seed = im.seed + (unsigned long long)w0; // window index inside the kernels is chunk-relative
+		imw.window0 = (unsigned long long)w0; // the window index inside the kernels is chunk-relative
 		if (sfo) {
 			k_tx_stream_a<<<(unsigned)(nw * tiles_a), kTxStreamThreads, 0, s>>>(p, imw, 1, stride, tiles_a, h->d_iq, nullptr, format);
 			OFDMRX_CUDA_TRY(cudaGetLastError());

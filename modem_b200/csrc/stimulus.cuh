@@ -35,7 +35,8 @@ struct TxImpair {
 	float sfo_ppm;   // 33-tap Kaiser-windowed-sinc resampling by (1 + ppm 1e-6)
 	int awgn;        // complex Gaussian, total variance 10^(awgn_db/10)
 	float awgn_db;
-	unsigned long long seed; // window i draws from the stream keyed by seed + i
+	unsigned long long seed;    // Philox key; window i of a call draws from the counter plane (window0 + i, sample)
+	unsigned long long window0; // index of the kernel's window 0 inside the call (chunked calls), set by the launcher
 };
 
 struct TxParams {
@@ -306,7 +307,8 @@ OFDMRX_HD cfx tx_resample(const cfx *src, long long len, float sfo_ppm, long lon
 	return make_float2((float)are, (float)aim);
 }
 
-// Philox-4x32-10 keyed by the window's seed, counter = sample index: the device's noise stream.  (The oracle draws from
+// Philox-4x32-10 keyed by the call's seed, counter = (sample index, window index of the call): the device's noise stream;
+// streams of different (seed, window) pairs never coincide, whatever the chunking.  (The oracle draws from
 // mt19937_64; the two streams are different realisations of the same distribution — tests compare statistics, and decode
 // parity is checked on whatever windows this generator produced.)
 OFDMRX_HD uint32_t tx_mulhi(uint32_t a, uint32_t b)
@@ -317,9 +319,9 @@ OFDMRX_HD uint32_t tx_mulhi(uint32_t a, uint32_t b)
 	return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
-OFDMRX_HD void tx_philox(unsigned long long seed, unsigned long long ctr, uint32_t out[4])
+OFDMRX_HD void tx_philox(unsigned long long seed, unsigned long long ctr, unsigned long long plane, uint32_t out[4])
 {
-	uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0, c3 = 0, k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+	uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)plane, c3 = (uint32_t)(plane >> 32), k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 	for (int r = 0; r < 10; ++r) {
 		const uint32_t h0 = tx_mulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = tx_mulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
 		const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
@@ -331,7 +333,7 @@ OFDMRX_HD void tx_philox(unsigned long long seed, unsigned long long ctr, uint32
 OFDMRX_HD cfx tx_noise(const TxImpair &im, long long window, long long n)
 {
 	uint32_t r[4];
-	tx_philox(im.seed + (unsigned long long)window, (unsigned long long)n, r);
+	tx_philox(im.seed, (unsigned long long)n, im.window0 + (unsigned long long)window, r);
 	const double u1 = ((double)r[0] * 4294967296.0 + (double)r[1] + 0.5) / 18446744073709551616.0;
 	const float u2 = ((float)(r[2] >> 8) + 0.5f) / 16777216.f;
 	const float sigma = sqrtf(powf(10.f, im.awgn_db / 10.f) / 2.f);

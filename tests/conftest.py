@@ -10,7 +10,6 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "gpu_unverified: GPU tests of code that has not run on hardware yet (kept out of -m gpu until it has)")
 
 
 @pytest.fixture(scope="session")

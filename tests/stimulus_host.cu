@@ -2,6 +2,8 @@
 // routines the kernels of stimulus.cu call, compiled for the host, one "thread") so that the CPU suite can check the
 // transmitter arithmetic, the guard cross-fade gather and the impairment chain against the oracle without a GPU.
 // Mirrors the orchestration of ofdmtx_encode_batch (stimulus.cu) for one window.
+#include <cstddef>
+#include <cstring>
 #include "../modem_b200/csrc/stimulus.cuh"
 #include "../modem_b200/csrc/tx_tables.h"
 #include <vector>
@@ -42,7 +44,7 @@ extern "C" int stimulus_host_code(const uint8_t *payload, int table, uint32_t *o
 	return 0;
 }
 
-// one window of `fpw` frames; window_index only selects the noise stream (seed + window_index)
+// one window of `fpw` frames; window_index only selects the noise stream (counter plane window_index of key seed)
 extern "C" long long stimulus_host(int rate, int mode, int freq_off, long long call_sign, const uint8_t *payloads, int fpw,
 	const TxImpair *imp, int window_index, int format, void *out, long long stride)
 {
@@ -75,7 +77,7 @@ extern "C" long long stimulus_host(int rate, int mode, int freq_off, long long c
 #undef SYMBOLS
 	TxImpair im{};
 	const bool has_imp = imp && (imp->multipath || imp->cfo_hz != 0.f || imp->sfo_ppm != 0.f || imp->awgn);
-	if (has_imp) { im = *imp; im.seed += (unsigned long long)window_index; }
+	if (has_imp) { std::memcpy(&im, imp, offsetof(TxImpair, window0)); im.window0 = (unsigned long long)window_index; } // the caller's struct is ofdmtx_impairments (no window0)
 	const bool sfo = has_imp && im.sfo_ppm != 0.f;
 	const long long nout = tx_resampled_len(p.len, sfo ? im.sfo_ppm : 0.f);
 	if (stride < nout) return -22;

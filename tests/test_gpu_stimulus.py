@@ -8,10 +8,8 @@ import subprocess
 import numpy as np
 import pytest
 
-# NOT marked `gpu` yet: these kernels were written after the round's GPU budget was spent and have never run on hardware, so they
-# must not be able to turn the receiver's `-m gpu` parity run red.  First hardware run: `pytest -m gpu_unverified` (or
-# tools/stimulus_first_run.sh); once green, rename the marker to `gpu`.
-pytestmark = [pytest.mark.gpu_unverified, pytest.mark.skipif(not os.path.exists("/dev/nvidia0"), reason="needs a B200")]
+# First hardware run: round 2 (profiles/r2a_stimulus_first_run.md): memcheck clean, device loop-back 2048 / 2048.
+pytestmark = pytest.mark.gpu
 
 
 def close_pcm(got, ref):

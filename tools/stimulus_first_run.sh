@@ -17,5 +17,5 @@ for rate in (8000, 48000):
     tx.close()
 PY
 echo "memcheck exit $?"; tail -5 gpurun_out/stim_memcheck.log
-timeout 600 python -m pytest tests/test_gpu_stimulus.py -m gpu_unverified -q 2>&1 | tail -15 | tee gpurun_out/stim_tests.log
+timeout 600 python -m pytest tests/test_gpu_stimulus.py -m gpu -q 2>&1 | tail -15 | tee gpurun_out/stim_tests.log
 timeout 300 python tools/tx_speed.py 2>&1 | tee gpurun_out/stim_speed.log
