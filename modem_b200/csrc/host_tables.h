@@ -86,7 +86,7 @@ static inline uint32_t scl_op(uint32_t w) { return w & 7; }
 static inline uint32_t scl_level(uint32_t w) { return (w >> 3) & 31; }
 static inline uint32_t scl_index(uint32_t w) { return ((w >> 8) & 0x3fffffu) * 32; }
 static inline uint32_t scl_depth(uint32_t w) { return (w >> 30) + 1; }
-std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth = kSclMaxFuse, bool top_ops = true, bool r1_ops = false);
+std::vector<uint32_t> make_scl_schedule(const std::vector<uint32_t> &frozen, int order, int max_depth = kSclMaxFuse, bool top_ops = true, bool r1_ops = true);
 
 // ---- misc sequences / codes -----------------------------------------------------------------------------------
 std::vector<uint8_t> mls_bits(int poly, int n);              // first n outputs of the Galois LFSR (reg = 1)

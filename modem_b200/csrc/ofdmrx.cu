@@ -25,13 +25,11 @@ struct ofdmrx_handle {
 	int rate = 8000;    // 8000, 16000, 44100 or 48000 (decode.cc:590-606)
 	int max_frames = 0, max_samples = 0, iq_len = 0;
 	bool keep_taps = false;
-	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0, scl_stream_level = 17;
+	int scl_ctas_per_sm = 0, scl_grid = 0, scl_warps = 0;
 	int launches = 0;
 	// constants
 	uint32_t *d_tbl[2] = {}, *d_scr = nullptr, *d_bch = nullptr; // [code table]: frozen set | message offsets | SCL schedule
 	int polar_table = 0; // table used by ofdmrx_polar_decode (option "polar_table")
-	bool scl_top = true;  // schedules use TOP ops: alpha levels 14 and 15 are never stored
-	size_t scl_a_stride = 0; // floats of alpha scratch per resident warp
 	uint8_t *d_mls1 = nullptr;
 	cfx *d_tw1280 = nullptr, *d_tw640 = nullptr, *d_kern = nullptr;
 	FrontendConsts fc;
@@ -47,7 +45,7 @@ struct ofdmrx_handle {
 	int8_t *d_soft = nullptr;
 	cfx *d_cons_raw = nullptr, *d_cons = nullptr;
 	float *d_ts = nullptr, *d_llr = nullptr, *d_y = nullptr;
-	int *d_cwlist = nullptr, *d_ncw = nullptr;
+	int *d_cwlist = nullptr, *d_ncw = nullptr, *d_work = nullptr;
 	uint32_t *d_payload = nullptr;
 	float *d_A = nullptr; uint32_t *d_B = nullptr;
 	uint32_t *d_xbits = nullptr; size_t xbits_frames = 0;
@@ -91,10 +89,8 @@ int ensure_scl_scratch(ofdmrx_handle *h)
 	while (h->scl_grid > 1 && (h->scl_grid - 1) * (kSclThreads / 32) >= need_warps) { --h->scl_grid; }
 	warps = h->scl_grid * (kSclThreads / 32);
 	h->scl_warps = warps;
-	// per warp: alpha levels 5.. back to back ([quad][lane] float4); with TOP ops levels 14 and 15 are never touched, so a
-	// warp needs 2.1 MB instead of 8.4 MB
-	h->scl_a_stride = h->scl_top ? scl_off(14) : kSclWarpFloats;
-	if (int r = dev_alloc(&h->d_A, (size_t)warps * h->scl_a_stride)) return r;
+	// per warp: alpha levels 6..13 back to back (2.1 MB; polar.cuh) + the beta words
+	if (int r = dev_alloc(&h->d_A, (size_t)warps * kSclWarpFloats)) return r;
 	if (int r = dev_alloc(&h->d_B, (size_t)warps * kSclWarpWords)) return r;
 	return 0;
 }
@@ -131,21 +127,29 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	// ---- constant tables
 	int fuse = kSclMaxFuse; // F/G chain fusion depth of the SCL schedule (1 = none); OFDMRX_SCL_FUSE overrides for A/B runs
 	if (const char *e = std::getenv("OFDMRX_SCL_FUSE")) fuse = std::max(1, std::min(kSclMaxFuse, std::atoi(e)));
-	h->scl_stream_level = 11; // alpha levels >= 11 written by the TOP ops stream through L2 (evict-first)
-	if (const char *e = std::getenv("OFDMRX_SCL_STREAM_LEVEL")) h->scl_stream_level = std::atoi(e);
-	bool top = true; // levels 16..14 recomputed from the channel LLRs (OP_TOP); OFDMRX_SCL_TOP=0 stores them instead
-	if (const char *e = std::getenv("OFDMRX_SCL_TOP")) top = std::atoi(e) != 0;
-	h->scl_top = top;
+	bool r1 = true; // rate-1 attempts (OP_R1); OFDMRX_SCL_R1=0 walks every node (A/B runs)
+	if (const char *e = std::getenv("OFDMRX_SCL_R1")) r1 = std::atoi(e) != 0;
+	bool sched_ok = true;
 	std::vector<uint32_t> msg_off[2];
 	for (int tb = 0; tb < 2; ++tb) { // code tables of modes 6..9 and 10..13 (decode.cc:310-311,342-343)
 		h->h_frozen[tb] = make_frozen(kCodeOrder, tb ? 64512 : 64800, kCrcBits);
-		h->h_ops[tb] = make_scl_schedule(h->h_frozen[tb], kCodeOrder, fuse, top);
+		h->h_ops[tb] = make_scl_schedule(h->h_frozen[tb], kCodeOrder, fuse, true, r1);
 		msg_off[tb].resize(2048);
 		uint32_t acc = 0;
 		for (int w = 0; w < 2048; ++w) { msg_off[tb][w] = acc; acc += 32 - __builtin_popcount(h->h_frozen[tb][w]); }
-		bool has_top = false; // the generator falls back to stored levels if a rate-0 node reached the top level
+		bool has_top = false; // the kernel never stores levels 14..16: the generator must have been able to use TOP ops
 		for (uint32_t op : h->h_ops[tb]) has_top |= scl_op(op) == OP_TOP;
-		if (!has_top) h->scl_top = false;
+		if (!has_top) sched_ok = false;
+		// lengthen() writes 9000 at code[cons_bits..65535] (demod.cu): that equals decode.cc:245-253 only while those indices are
+		// all non-frozen; the sets are recomputed here in long double, so check instead of assuming
+		const int cons_bits = tb ? 64512 : 64800;
+		for (int i = cons_bits; i < kCodeLen; ++i)
+			if ((h->h_frozen[tb][i / 32] >> (i % 32)) & 1u) sched_ok = false;
+	}
+	if (!sched_ok) {
+		std::fprintf(stderr, "ofdmrx: the frozen sets computed on this host do not have the structure the kernels rely on\n");
+		delete h;
+		return -5;
 	}
 	std::vector<uint32_t> scr(kDataBytes / 4, 0);
 	{
@@ -196,6 +200,7 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_ts, F * kMaxRows * 3);
 	if (!r) r = dev_alloc(&h->d_cwlist, F + 4);
 	if (!r) r = dev_alloc(&h->d_ncw, (size_t)2);
+	if (!r) r = dev_alloc(&h->d_work, (size_t)1);
 	if (!r) r = dev_alloc(&h->d_payload, F * (size_t)(kDataBytes / 4));
 	for (int i = 0; i < 10 && !r; ++i) if (cudaEventCreate(&h->ev[i]) != cudaSuccess) r = -12;
 	for (int i = 0; i < 16 && !r; ++i) if (cudaEventCreateWithFlags(&h->ev_slice[i], cudaEventDisableTiming) != cudaSuccess) r = -12;
@@ -213,7 +218,7 @@ void ofdmrx_destroy(ofdmrx_t *h)
 	cudaSetDevice(h->device);
 	void *ptrs[] = {h->d_tbl[0], h->d_tbl[1], h->d_scr, h->d_bch, h->d_mls1, h->d_tw1280, h->d_tw640, h->d_kern, h->d_in,
 		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr, h->d_y,
-		h->d_cwlist, h->d_ncw, h->d_payload, h->d_A, h->d_B, h->d_xbits};
+		h->d_cwlist, h->d_ncw, h->d_work, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
 	for (int i = 0; i < 16; ++i) if (h->ev_slice[i]) cudaEventDestroy(h->ev_slice[i]);
@@ -303,13 +308,13 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 static int run_scl(ofdmrx_handle *h, int nf, cudaStream_t s)
 {
 	OFDMRX_CUDA_TRY(launch_compact(h->d_st, nf, h->d_cwlist, h->d_ncw, s));
-	OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, s));
+	OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, h->d_work, s));
 	if (int r = ensure_scl_scratch(h)) return r;
 	cudaEventRecord(h->ev[6], s);
 	SclParams p{};
 	p.llr = h->d_llr; p.cw_list = h->d_cwlist; p.n_cw_ptr = h->d_ncw; p.A = h->d_A; p.B = h->d_B;
-	p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1]; p.a_stride = h->scl_a_stride;
-	p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr; p.stream_level = h->scl_stream_level;
+	p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1]; p.work = h->d_work;
+	p.payload = h->d_payload; p.st = h->d_st; p.xbits = nullptr;
 	OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
 	cudaEventRecord(h->ev[7], s);
 	h->ev_valid = true;
@@ -384,7 +389,7 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
 		const int nf = std::min(h->max_frames, n - f0);
 		OFDMRX_CUDA_TRY(cudaMemcpyAsync(h->d_llr, llr + (size_t)f0 * kCodeLen, (size_t)nf * kCodeLen * 4, cudaMemcpyHostToDevice, s));
 		OFDMRX_CUDA_TRY(cudaMemsetAsync(h->d_st, 0, (size_t)nf * sizeof(FrameState), s));
-		OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, s));
+		OFDMRX_CUDA_TRY(launch_payload_init(h->d_payload, h->d_scr, nf, h->d_work, s));
 		if (xbits && h->xbits_frames < (size_t)nf) {
 			if (h->d_xbits) cudaFree(h->d_xbits);
 			h->d_xbits = nullptr;
@@ -394,10 +399,9 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
 		SclParams p{};
 		p.llr = h->d_llr; p.cw_list = nullptr; p.n_cw_ptr = nullptr; p.A = h->d_A; p.B = h->d_B;
 		p.n_cw[h->polar_table] = nf; p.n_cw[1 - h->polar_table] = 0;
-		p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1]; p.a_stride = h->scl_a_stride;
+		p.tbl[0] = h->d_tbl[0]; p.tbl[1] = h->d_tbl[1]; p.work = h->d_work;
 		p.payload = h->d_payload; p.st = h->d_st;
 		p.xbits = xbits ? h->d_xbits : nullptr;
-		p.stream_level = h->scl_stream_level;
 		OFDMRX_CUDA_TRY(launch_polar_scl(p, h->scl_grid, s));
 		h->launches += 2;
 		OFDMRX_CUDA_TRY(cudaMemcpyAsync(payload_out + (size_t)f0 * kDataBytes, h->d_payload, (size_t)nf * kDataBytes, cudaMemcpyDeviceToHost, s));

@@ -2,21 +2,28 @@
 //
 // Replaces CODE::PolarListDecoder<SIMD<float,8>,16> + systematic() + the CRC-32 candidate scan of the reference
 // receiver (/root/reference/decode.cc:201,530-555).  Design (B200-first, not a port of the SIMD recursion):
-//   * one list lane per THREAD, one codeword per 8 threads, four codewords per warp.  Every codeword walks the
-//     same precomputed op schedule (host_tables.cc: the frozen set is fixed), so a warp never diverges and the
-//     only cross-thread traffic is 8-wide shuffles (lane permutation after a fork, fork ranking).
-//   * alpha (LLR) buffers of tree levels 6..13 live in a per-warp HBM/L2 scratch laid out [quad][warp lane][4]
-//     (a quad = 4 consecutive tree positions) so that every warp access is 512 coalesced bytes of 128-bit loads,
-//     also when a thread reads through the lane map; level 5 lives in shared memory; levels 14..16 are never stored
-//     (TOP ops recompute level 13 from the lane-shared channel LLRs); levels 0..4 (a 32-leaf "word") are fully
-//     unrolled and live in registers.
+//   * one warp decodes four codewords in lock step along a precomputed op schedule (host_tables.cc: the frozen set is
+//     fixed, so the tree walk is static and a warp never diverges on it).  The eight threads of a codeword play two roles:
+//       - in the 32-leaf words (levels 4..0, registers) thread t IS list lane t: forks are ranked with 8-wide shuffles;
+//       - above the words (levels 6..13, HBM/L2 scratch; level 5 in shared memory) the eight threads split the tree
+//         POSITIONS of one path at a time (thread j takes quads j, j+8, ...), looping over the codeword's path classes.
+//   * path classes: the reference starts its eight lanes as copies of one path (metrics 0, 1000, 1000, ...); copies stay
+//     copies until a flipped decision displaces one, which on a clean channel never happens and on the README
+//     impairment chain happens late.  Lanes holding the same path form a class, only the class representative (lowest
+//     lane) owns alpha / beta storage and is computed; every lane keeps its own fp32 metric, so the result is the
+//     reference's bit for bit.  Work and scratch traffic scale with the number of DISTINCT paths (1..8), not with L.
+//   * rate-1 attempts (OP_R1 and inside the words): an all-free node whose forks provably cannot change the list —
+//     lanes in metric order and largest metric < every lane's metric + min|alpha| — is decided by the signs of its alphas
+//     in one pass; exact, because on a sign-following path the smallest |leaf LLR| of the node IS min|alpha| (the first
+//     leaf's) and every other leaf's magnitude is a rounded sum that is not smaller.  Otherwise the node is walked as usual.
+//   * levels 14..16 are never stored (TOP ops recompute level 13 from the lane-shared channel LLRs and a few beta bits).
 //   * two code tables (modes 6..9 / 10..13): one op schedule each; the four codewords of a warp share a table.
 //   * partial sums (beta) are bit-packed, 32 tree positions per word; at the root they ARE the re-encoded
 //     codeword, whose non-frozen positions are the systematic message (decode.cc:254-261) — no message/map
 //     trace-back is stored.
 //   * fp32 operation order is identical to oracle/ref_code.hh PolarListDecoder (f = sign-min, g = b +- a,
 //     rate-0 nodes summed in index order, forks ranked by (metric, 2*lane+bit)), so the result is bit-exact
-//     against the oracle for the same LLRs.
+//     against the oracle for the same LLRs.  tests/scl_emulator.cc is the scalar statement of this file's bookkeeping.
 // No tensor cores: there is no dense contraction anywhere on this path.
 #include "common.cuh"
 #include "polar.cuh"
@@ -40,17 +47,28 @@ __device__ __forceinline__ float g_op(float a, float b, uint32_t bit)
 struct SclCtx {
 	float metric;
 	int ret;          // lane map returned by the node that completed last: my path descends from lane `ret`
+	int rep;          // representative (lowest lane) of my path class
 	uint32_t W;       // partial sums of the current 32-leaf word
 	uint32_t fmask;   // frozen mask of the current word
 	int t, gbase;     // my list lane (0..7), warp lane of lane 0 of my codeword
-	const float4 *A5; // level-5 alpha buffer of this warp ([8 quads][32 lanes])
 };
 
-struct ForkResult { float metric; int src_bit; };
+// "no fork at the next free leaves can change the list": lanes in metric order and the largest metric below every lane's
+// metric + mn (mn = the smallest |LLR| a free leaf can show on my path).  Warp-wide vote: the four codewords walk one op list.
+__device__ __forceinline__ bool list_is_stable(const SclCtx &c, float mn)
+{
+	const float m7 = __shfl_sync(FULL, c.metric, c.gbase | 7);
+	const float prev = __shfl_up_sync(FULL, c.metric, 1);
+	const bool easy = m7 < __fadd_rn(c.metric, mn) && (c.t == 0 || prev <= c.metric);
+	return __all_sync(FULL, easy);
+}
 
-// Free leaf: 2L forks, keep the L smallest by (metric, fork index); survivors land in rank order.
+struct ForkResult { float metric; int src_bit; int rep; };
+
+// Free leaf: 2L forks, keep the L smallest by (metric, fork index); survivors land in rank order.  Survivors that extend
+// the same class by the same bit are the same path: the new class representative is the lowest such lane.
 // Not inlined: the 32-leaf word is fully unrolled around it and would otherwise carry 32 copies (I-cache).
-__device__ __noinline__ ForkResult leaf_fork(float metric, float a, int t, int gbase)
+__device__ __noinline__ ForkResult leaf_fork(float metric, float a, int t, int gbase, int rep)
 {
 	const float pen = fabsf(a);
 	const float m0 = a < 0.f ? __fadd_rn(metric, pen) : metric; // decide 0
@@ -76,9 +94,15 @@ __device__ __noinline__ ForkResult leaf_fork(float metric, float a, int t, int g
 		if ((pr & 255) == t) { sb = j; nm = o0[j]; }
 		if ((pr >> 8) == t) { sb = j | 8; nm = o1[j]; }
 	}
+	const int key = (__shfl_sync(FULL, rep, gbase + (sb & 7)) << 1) | (sb >> 3);
+	int nrep = t;
+#pragma unroll
+	for (int j = 7; j >= 0; --j)
+		if (__shfl_sync(FULL, key, gbase + j) == key) nrep = j;
 	ForkResult r;
 	r.metric = nm;
 	r.src_bit = sb;
+	r.rep = nrep;
 	return r;
 }
 
@@ -86,7 +110,7 @@ __device__ __noinline__ ForkResult leaf_fork(float metric, float a, int t, int g
 // Code footprint matters more than instruction count here (the first fully unrolled version was 210 KB of SASS and
 // spent 55 % of its stall cycles waiting for instruction fetch): the word is decoded by ONE non-inlined 8-leaf routine
 // (levels 2..0 unrolled in registers, called four times) under ONE non-inlined 16-leaf routine (called twice).
-struct Sub { float metric; uint32_t W; int ret; int pad; }; // result of a sub-tree: path metric, partial sums, lane map
+struct Sub { float metric; uint32_t W; int ret; int rep; }; // result of a sub-tree: path metric, partial sums, lane map, class
 
 // One node of an 8-leaf group, LVL = log2(size) <= 3, BASE = first leaf inside the group.  `a` = the node's alphas
 // (registers); c.W / c.fmask hold the group's 8 local partial-sum / frozen bits.
@@ -106,25 +130,32 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 	}
 	if constexpr (LVL == 0) {
 		// Fast path (exact): if every "follow the sign" fork beats every "flip" fork and the lanes are already in
-		// (metric, lane) order, the 8 survivors are the 8 keeps in place — no ranking, no permutation.  Metrics are
-		// non-negative, so their bit patterns order like unsigned integers (REDUX instead of shuffle trees).
-		const float a0 = a[0];
+		// (metric, lane) order, the 8 survivors are the 8 keeps in place — no ranking, no permutation, classes unchanged.
 		// (no 8-lane REDUX here: a __reduce_*_sync whose mask differs between the four codewords of the warp is compiled
-		// into one serialised WARPSYNC.COLLECTIVE pass per group.)  If the lanes are in order, the largest keep metric is
-		// lane 7's, and "it is below every flip metric" can be tested per lane.
-		const float m7 = __shfl_sync(FULL, c.metric, c.gbase | 7);
-		const float prev = __shfl_up_sync(FULL, c.metric, 1);
-		const bool easy = m7 < __fadd_rn(c.metric, fabsf(a0)) && (c.t == 0 || prev <= c.metric);
-		if (__all_sync(FULL, easy)) {
+		// into one serialised WARPSYNC.COLLECTIVE pass per group.)
+		const float a0 = a[0];
+		if (list_is_stable(c, fabsf(a0))) {
 			c.ret = c.t;
 			c.W |= (a0 < 0.f ? 1u : 0u) << BASE;
 		} else {
-			const ForkResult r = leaf_fork(c.metric, a0, c.t, c.gbase);
+			const ForkResult r = leaf_fork(c.metric, a0, c.t, c.gbase, c.rep);
 			c.metric = r.metric;
 			c.ret = r.src_bit & 7;
+			c.rep = r.rep;
 			c.W |= (uint32_t)(r.src_bit >> 3) << BASE;
 		}
 	} else {
+		if ((c.fmask & SUB) == 0u) { // rate-1 attempt
+			float mn = fabsf(a[0]);
+#pragma unroll
+			for (int k = 1; k < N; ++k) mn = fminf(mn, fabsf(a[k]));
+			if (list_is_stable(c, mn)) {
+#pragma unroll
+				for (int k = 0; k < N; ++k) c.W |= (a[k] < 0.f ? 1u : 0u) << (BASE + k);
+				c.ret = c.t;
+				return;
+			}
+		}
 		constexpr int H = N / 2;
 		float ch[H];
 #pragma unroll
@@ -147,89 +178,110 @@ __device__ __forceinline__ void blk_node(SclCtx &c, const float *a)
 }
 
 __device__ __noinline__ Sub leaf8(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
-	uint32_t fmask8, float metric, int t, int gbase)
+	uint32_t fmask8, float metric, int t, int gbase, int rep)
 {
 	SclCtx c;
-	c.metric = metric; c.ret = t; c.W = 0; c.fmask = fmask8; c.t = t; c.gbase = gbase; c.A5 = nullptr;
+	c.metric = metric; c.ret = t; c.rep = rep; c.W = 0; c.fmask = fmask8; c.t = t; c.gbase = gbase;
 	const float a[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
 	blk_node<3, 0>(c, a);
 	Sub r;
-	r.metric = c.metric; r.W = c.W; r.ret = c.ret; r.pad = 0;
+	r.metric = c.metric; r.W = c.W; r.ret = c.ret; r.rep = c.rep;
 	return r;
 }
 
 // 16 leaves: f -> left 8 -> g (parents through the lane map) -> right 8 -> combine
-__device__ __noinline__ Sub node16(float4 x0, float4 x1, float4 x2, float4 x3, uint32_t fmask16, float metric, int t, int gbase)
+__device__ __noinline__ Sub node16(float4 x0, float4 x1, float4 x2, float4 x3, uint32_t fmask16, float metric, int t, int gbase, int rep)
 {
 	const float a[16] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x, x2.y, x2.z, x2.w, x3.x, x3.y, x3.z, x3.w};
 	Sub r;
-	r.pad = 0;
+	r.rep = rep;
 	if (fmask16 == 0xffffu) {
 #pragma unroll
 		for (int k = 0; k < 16; ++k) if (a[k] < 0.f) metric = __fsub_rn(metric, a[k]);
 		r.metric = metric; r.W = 0; r.ret = t;
 		return r;
 	}
+	if (fmask16 == 0u) { // rate-1 attempt
+		float mn = fabsf(a[0]);
+#pragma unroll
+		for (int k = 1; k < 16; ++k) mn = fminf(mn, fabsf(a[k]));
+		SclCtx c;
+		c.metric = metric; c.t = t; c.gbase = gbase;
+		if (list_is_stable(c, mn)) {
+			uint32_t W = 0;
+#pragma unroll
+			for (int k = 0; k < 16; ++k) W |= (a[k] < 0.f ? 1u : 0u) << k;
+			r.metric = metric; r.W = W; r.ret = t;
+			return r;
+		}
+	}
 	float ch[8];
 #pragma unroll
 	for (int k = 0; k < 8; ++k) ch[k] = f_op(a[k], a[k + 8]);
-	const Sub l = leaf8(ch[0], ch[1], ch[2], ch[3], ch[4], ch[5], ch[6], ch[7], fmask16 & 0xffu, metric, t, gbase);
+	const Sub l = leaf8(ch[0], ch[1], ch[2], ch[3], ch[4], ch[5], ch[6], ch[7], fmask16 & 0xffu, metric, t, gbase, rep);
 	const int srcl = gbase + l.ret;
 #pragma unroll
 	for (int k = 0; k < 8; ++k) {
 		const float pa = __shfl_sync(FULL, a[k], srcl), pb = __shfl_sync(FULL, a[k + 8], srcl);
 		ch[k] = g_op(pa, pb, (l.W >> k) & 1u);
 	}
-	const Sub rr = leaf8(ch[0], ch[1], ch[2], ch[3], ch[4], ch[5], ch[6], ch[7], fmask16 >> 8, l.metric, t, gbase);
+	const Sub rr = leaf8(ch[0], ch[1], ch[2], ch[3], ch[4], ch[5], ch[6], ch[7], fmask16 >> 8, l.metric, t, gbase, l.rep);
 	const int srcr = gbase + rr.ret;
 	const uint32_t Wl = __shfl_sync(FULL, l.W, srcr);
 	r.metric = rr.metric;
 	r.W = ((Wl ^ rr.W) & 0xffu) | (rr.W << 8);
 	r.ret = __shfl_sync(FULL, l.ret, srcr);
+	r.rep = rr.rep;
 	return r;
 }
 
-// the whole word: alphas of the level-5 node are in the scratch buffer (8 quads per lane)
-__device__ __forceinline__ void word32(SclCtx &c)
+// Alpha level 5 (the buffer every 32-leaf word reads twice and every F6/G6 writes) lives in shared memory: 4 KB per warp,
+// [quad][codeword * 8 + slot] float4 with a row pitch of 33: the word's readers (8 lanes of a codeword, one quad, their
+// slots) and the level-6 ops' writers (8 quads of one slot) both touch eight different 16-byte bank groups.
+constexpr int kS5Pitch = 33;
+constexpr int kS5Quads = 8 * kS5Pitch;
+
+// the whole word: thread = list lane; `rs5` = the slot that holds my level-5 alphas (my class representative when they were written)
+__device__ __forceinline__ void word32(SclCtx &c, const float4 *S5, int rs5)
 {
 	float4 v[8];
-	const int own = c.gbase + c.t;
+	const int own = c.gbase + rs5;
 #pragma unroll
-	for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + own];
+	for (int q = 0; q < 8; ++q) v[q] = S5[q * kS5Pitch + own];
+	if (c.fmask == 0u) { // rate-1 attempt on the whole word
+		float mn = fabsf(v[0].x);
+#pragma unroll
+		for (int q = 0; q < 8; ++q) mn = fminf(fminf(mn, fabsf(v[q].x)), fminf(fminf(fabsf(v[q].y), fabsf(v[q].z)), fabsf(v[q].w)));
+		if (list_is_stable(c, mn)) {
+			uint32_t W = 0;
+#pragma unroll
+			for (int q = 0; q < 8; ++q)
+				W |= ((v[q].x < 0.f ? 1u : 0u) | (v[q].y < 0.f ? 2u : 0u) | (v[q].z < 0.f ? 4u : 0u) | (v[q].w < 0.f ? 8u : 0u)) << (4 * q);
+			c.W = W;
+			c.ret = c.t;
+			return;
+		}
+	}
 	float4 x[4];
 #pragma unroll
 	for (int q = 0; q < 4; ++q) x[q] = make_float4(f_op(v[q].x, v[q + 4].x), f_op(v[q].y, v[q + 4].y), f_op(v[q].z, v[q + 4].z), f_op(v[q].w, v[q + 4].w));
-	const Sub l = node16(x[0], x[1], x[2], x[3], c.fmask & 0xffffu, c.metric, c.t, c.gbase);
-	const int srcl = c.gbase + l.ret;
+	const Sub l = node16(x[0], x[1], x[2], x[3], c.fmask & 0xffffu, c.metric, c.t, c.gbase, c.rep);
+	const int srcl = c.gbase + __shfl_sync(FULL, rs5, c.gbase + l.ret); // the slot of the lane I descend from
 #pragma unroll
-	for (int q = 0; q < 8; ++q) v[q] = c.A5[q * 32 + srcl];
+	for (int q = 0; q < 8; ++q) v[q] = S5[q * kS5Pitch + srcl];
 #pragma unroll
 	for (int q = 0; q < 4; ++q) {
 		const uint32_t wb = l.W >> (4 * q);
 		x[q] = make_float4(g_op(v[q].x, v[q + 4].x, wb & 1u), g_op(v[q].y, v[q + 4].y, (wb >> 1) & 1u),
 			g_op(v[q].z, v[q + 4].z, (wb >> 2) & 1u), g_op(v[q].w, v[q + 4].w, (wb >> 3) & 1u));
 	}
-	const Sub r = node16(x[0], x[1], x[2], x[3], c.fmask >> 16, l.metric, c.t, c.gbase);
+	const Sub r = node16(x[0], x[1], x[2], x[3], c.fmask >> 16, l.metric, c.t, c.gbase, l.rep);
 	const int srcr = c.gbase + r.ret;
 	const uint32_t Wl = __shfl_sync(FULL, l.W, srcr);
 	c.metric = r.metric;
 	c.W = ((Wl ^ r.W) & 0xffffu) | (r.W << 16);
 	c.ret = __shfl_sync(FULL, l.ret, srcr);
-}
-
-// L2 cache policy for the stores of the TOP ops (levels 13 and 12 stream through: evict-first keeps them from pushing
-// the small, frequently re-read levels out of the 126 MB L2); the policy is a runtime operand.  The F/G ops use plain
-// generic accesses (their lowest level lives in shared memory; hints measured no gain there).
-__device__ __forceinline__ uint64_t l2_policy(bool stream)
-{
-	uint64_t p;
-	if (stream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-	else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-	return p;
-}
-__device__ __forceinline__ void st_pol(float4 *ptr, float4 v, uint64_t pol)
-{
-	asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+	c.rep = r.rep;
 }
 
 __device__ __forceinline__ float4 f_op4(float4 a, float4 b) { return make_float4(f_op(a.x, b.x), f_op(a.y, b.y), f_op(a.z, b.z), f_op(a.w, b.w)); }
@@ -245,162 +297,155 @@ __device__ __forceinline__ float r0_acc(float m, float4 v)
 	if (v.w < 0.f) m = __fsub_rn(m, v.w);
 	return m;
 }
+__device__ __forceinline__ float min_abs4(float m, float4 v) { return fminf(fminf(m, fabsf(v.x)), fminf(fminf(fabsf(v.y), fabsf(v.z)), fabsf(v.w))); }
+__device__ __forceinline__ uint32_t neg_bits4(float4 v) { return (v.x < 0.f ? 1u : 0u) | (v.y < 0.f ? 2u : 0u) | (v.z < 0.f ? 4u : 0u) | (v.w < 0.f ? 8u : 0u); }
 
-// Alpha level 5 (the buffer every 32-leaf word reads twice and every F6/G6 writes) lives in shared memory: 4 KB per warp,
-// [quad][lane] float4 like the global levels; accesses below use generic addressing.  Measured per 10 000 codewords:
-// none 70.2 ms, level 5 68.2 ms, levels 5 and 6 85.7 ms (204 KB of shared memory leave almost no L1 for the rest).
-#ifndef OFDMRX_SCL_SMEM_LEVELS
-#define OFDMRX_SCL_SMEM_LEVELS 1
-#endif
-constexpr int kSclSmemLevels = OFDMRX_SCL_SMEM_LEVELS; // 0: none, 1: level 5, 2: levels 5 and 6
-constexpr int kSclSmemBytes = (kSclSmemLevels >= 1 ? 8 : 0) * 32 * 16 + (kSclSmemLevels >= 2 ? 16 : 0) * 32 * 16;
-__device__ __forceinline__ float4 *lvl_ptr(float4 *A, float4 *S, int l)
+// ---- storage of the levels above the words -------------------------------------------------------------------------
+// level l (6..13) of codeword group `gbase` (= codeword * 8), slot s, quad q  ->  A[scl_off4(l) + ((gbase + s) << (l - 2)) + q]
+__device__ __forceinline__ float4 *lvl_row(float4 *A, int l, int gslot) { return A + scl_off4(l) + ((size_t)gslot << (l - 2)); }
+__device__ __forceinline__ void st_lvl(float4 *A, float4 *S5, int l, int gslot, int q, float4 v)
 {
-	if (kSclSmemLevels >= 1 && l == 5) return S;
-	if (kSclSmemLevels >= 2 && l == 6) return S + 8 * 32;
-	return A + scl_off4(l);
+	if (l == 5) S5[q * kS5Pitch + gslot] = v;
+	else lvl_row(A, l, gslot)[q] = v;
 }
 
-#ifndef OFDMRX_SCL_PAIRS
-#define OFDMRX_SCL_PAIRS 4
-#endif
-constexpr int kSclPairsInFlight = OFDMRX_SCL_PAIRS; // quad pairs loaded per thread before the first store (x2 128-bit loads in flight)
+// 3-bit-per-level stacks (lane maps, slots) in one 64-bit register
+__device__ __forceinline__ int stk_get(uint64_t s, int l) { return (int)((s >> (3 * l)) & 7ull); }
+__device__ __forceinline__ uint64_t stk_set(uint64_t s, int l, int v) { return (s & ~(7ull << (3 * l))) | ((uint64_t)v << (3 * l)); }
 
-// F or G at level l fused with the D-1 F steps that follow it down the left spine (host_tables.cc: depth field).
-// One iteration takes the 2^(D-1) quad pairs of the parent whose results meet again in the chained F steps, so the
-// intermediate levels are produced in registers, written once (the later G needs them) and never re-read by an F.
-// 8 x 128-bit loads are in flight per thread for every D (D <= kSclMaxFuse = 2: deeper chains cost registers and
-// instruction-cache footprint and measured slower).
+// F or G at level l fused with the D-1 F steps that follow it down the left spine (host_tables.cc: depth field), for every
+// path class of the codeword in turn.  The eight threads of the codeword split the positions: thread j takes the quad
+// pairs q = j, j + 8, ... of the parent whose results meet again in the chained F step, so the intermediate level is
+// produced in registers, written once (the later G needs it) and never re-read by an F.  Up to 8 x 128-bit loads are in
+// flight per thread.  `myps` = slot of the parent alphas of MY lane (meaningful on the representatives).
 template <int D, bool IS_G>
-__device__ __forceinline__ void fused_op(float4 *A, float4 *S, const float4 *C4, const uint32_t *Bw, int l, int src, int lane32)
+__device__ __forceinline__ void fused_op(float4 *A, float4 *S5, const uint32_t *Bn, int l, int gbase, int j, uint32_t repmask, int myps)
 {
-	constexpr int M = 1 << (D - 1), U = kSclPairsInFlight / M;
+	constexpr int M = 1 << (D - 1);
 	const int hq = 1 << (l - 3), step = hq >> (D - 1);
-	const float4 *P = lvl_ptr(A, S, l > 15 ? 15 : l);
-	float4 *D1 = lvl_ptr(A, S, l - 1);
-	float4 *D2 = lvl_ptr(A, S, D >= 2 ? l - 2 : l - 1);
-	const bool root = l == 16;
-	for (int q0 = 0; q0 < step; q0 += 8) {
-		uint32_t bw[M];
-		if constexpr (IS_G) {
+	uint32_t m = repmask;
+	while (__any_sync(FULL, m != 0u)) {
+		const bool act = m != 0u;
+		const int r = act ? __ffs(m) - 1 : 0;
+		m &= m - 1u;
+		const int ps = __shfl_sync(FULL, myps, gbase + r);
+		if (act) {
+			const float4 *P = lvl_row(A, l, gbase + ps);
+			const uint32_t *Bw = Bn + r;
+			for (int q0 = j; q0 < step; q0 += 16) {
+				const bool two = q0 + 8 < step;
+				float4 pa[2][M], pb[2][M];
+				uint32_t bw[2][M];
 #pragma unroll
-			for (int m = 0; m < M; ++m) bw[m] = Bw[((q0 + m * step) >> 3) * 32];
-		}
-#pragma unroll 1
-		for (int k = 0; k < 8; k += U) {
-			float4 pa[U][M], pb[U][M];
+				for (int u = 0; u < 2; ++u)
+					if (u == 0 || two) {
 #pragma unroll
-			for (int u = 0; u < U; ++u)
-#pragma unroll
-				for (int m = 0; m < M; ++m) {
-					const int q = q0 + k + u + m * step;
-					if (root) { pa[u][m] = __ldg(&C4[q]); pb[u][m] = __ldg(&C4[q + hq]); }
-					else { pa[u][m] = P[q * 32 + src]; pb[u][m] = P[(q + hq) * 32 + src]; }
-				}
-#pragma unroll
-			for (int u = 0; u < U; ++u) {
-				float4 v1[M];
-#pragma unroll
-				for (int m = 0; m < M; ++m) {
-					const int q = q0 + k + u + m * step;
-					if constexpr (IS_G) v1[m] = g_op4(pa[u][m], pb[u][m], (bw[m] >> (4 * (k + u))) & 15u);
-					else v1[m] = f_op4(pa[u][m], pb[u][m]);
-					D1[q * 32 + lane32] = v1[m];
-				}
-				if constexpr (D >= 2) {
-					float4 v2[M / 2];
-#pragma unroll
-					for (int m = 0; m < M / 2; ++m) {
-						v2[m] = f_op4(v1[m], v1[m + M / 2]);
-						D2[(q0 + k + u + m * step) * 32 + lane32] = v2[m];
+						for (int mm = 0; mm < M; ++mm) {
+							const int q = q0 + 8 * u + mm * step;
+							pa[u][mm] = P[q];
+							pb[u][mm] = P[q + hq];
+							if constexpr (IS_G) bw[u][mm] = Bw[(q >> 3) * 32];
+						}
 					}
-				}
+#pragma unroll
+				for (int u = 0; u < 2; ++u)
+					if (u == 0 || two) {
+						float4 v1[M];
+#pragma unroll
+						for (int mm = 0; mm < M; ++mm) {
+							const int q = q0 + 8 * u + mm * step;
+							if constexpr (IS_G) v1[mm] = g_op4(pa[u][mm], pb[u][mm], (bw[u][mm] >> (4 * j)) & 15u);
+							else v1[mm] = f_op4(pa[u][mm], pb[u][mm]);
+							st_lvl(A, S5, l - 1, gbase + r, q, v1[mm]);
+						}
+						if constexpr (D >= 2) st_lvl(A, S5, l - 2, gbase + r, q0 + 8 * u, f_op4(v1[0], v1[1]));
+					}
 			}
 		}
 	}
 }
 
-// TOP(j): alpha of the level-13 node j (8192 positions) straight from the channel LLRs: three f/g steps per value whose
+// TOP(jn): alpha of the level-13 node jn (8192 positions) straight from the channel LLRs: three f/g steps per value whose
 // operands are 8 lane-shared channel values and up to 7 partial-sum bits of the node's left-hand relatives at levels
-// 15, 14 and 13 (read from the lanes this path descends from: s15, s14, own).  Levels 16..14 are never stored — they
-// were 2 x 2.1 MB of writes plus as much again in reads per codeword, all of it DRAM traffic.  D = 2 also produces
+// 15, 14 and 13 (read from the slots s15, s14, own of the lanes this path descended from).  Levels 16..14 are never stored
+// — they were 2 x 2.1 MB of writes plus as much again in reads per codeword, all of it DRAM traffic.  The op also produces
 // the left child at level 12 (the F step that always follows).
-template <int D>
-__device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32_t *B, int j, int s15, int s14, int lane32, int stream_level)
+__device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32_t *B, int jn, int gbase, int j, uint32_t repmask, int mys14, int mys15)
 {
-	const bool j2 = j & 4, j1 = j & 2, j0 = j & 1;
-	const uint32_t *B15 = B + s15;                                           // beta of node (15, 0): words 0..1023
-	const uint32_t *B14 = B + (size_t)(j2 ? 1024 : 0) * 32 + s14;            // beta of node (14, 2 j2)
-	const uint32_t *B13 = B + (size_t)(j0 ? (j - 1) * 256 : 0) * 32 + lane32; // beta of node (13, j - 1)
-	float4 *D13 = A + scl_off4(13), *D12 = A + scl_off4(12);
-	const uint64_t p13 = l2_policy(13 >= stream_level), p12 = l2_policy(12 >= stream_level);
-	constexpr int NQ = D == 2 ? 1024 : 2048;
-	for (int q0 = 0; q0 < NQ; q0 += 8) {
-		uint32_t w15[D][4], w14[D][2], w13[D];
-#pragma unroll
-		for (int h = 0; h < D; ++h) {
-			const int wq = (q0 + 1024 * h) >> 3;
-#pragma unroll
-			for (int m = 0; m < 4; ++m) w15[h][m] = j2 ? B15[(size_t)(wq + 256 * m) * 32] : 0u;
-#pragma unroll
-			for (int m = 0; m < 2; ++m) w14[h][m] = j1 ? B14[(size_t)(wq + 256 * m) * 32] : 0u;
-			w13[h] = j0 ? B13[(size_t)wq * 32] : 0u;
-		}
+	const bool j2 = jn & 4, j1 = jn & 2, j0 = jn & 1;
+	uint32_t m = repmask;
+	while (__any_sync(FULL, m != 0u)) {
+		const bool act = m != 0u;
+		const int r = act ? __ffs(m) - 1 : 0;
+		m &= m - 1u;
+		const int s14 = __shfl_sync(FULL, mys14, gbase + r), s15 = __shfl_sync(FULL, mys15, gbase + r);
+		if (act) {
+			const uint32_t *B15 = B + gbase + s15;                                            // beta of node (15, 0): words 0..1023
+			const uint32_t *B14 = B + (size_t)(j2 ? 1024 : 0) * 32 + gbase + s14;             // beta of node (14, 2 j2)
+			const uint32_t *B13 = B + (size_t)(j0 ? (jn - 1) * 256 : 0) * 32 + gbase + r;     // beta of node (13, jn - 1)
+			float4 *D13 = lvl_row(A, 13, gbase + r), *D12 = lvl_row(A, 12, gbase + r);
+			const int sh = 4 * j;
 #pragma unroll 1
-		for (int k = 0; k < 8; ++k) {
-			const int sh = 4 * k;
-			float4 z[D];
+			for (int q0 = j; q0 < 1024; q0 += 8) {
+				float4 z[2];
 #pragma unroll
-			for (int h = 0; h < D; ++h) {
-				float4 c[8];
+				for (int h = 0; h < 2; ++h) {
+					const int q = q0 + 1024 * h, wq = q >> 3;
+					float4 c[8];
 #pragma unroll
-				for (int kk = 0; kk < 8; ++kk) c[kk] = __ldg(&C4[q0 + k + 1024 * h + 2048 * kk]);
-				float4 x[4], y[2];
-				if (j2) {
+					for (int kk = 0; kk < 8; ++kk) c[kk] = __ldg(&C4[q + 2048 * kk]);
+					float4 x[4], y[2];
+					if (j2) {
 #pragma unroll
-					for (int m = 0; m < 4; ++m) x[m] = g_op4(c[m], c[m + 4], (w15[h][m] >> sh) & 15u);
-				} else {
+						for (int mm = 0; mm < 4; ++mm) x[mm] = g_op4(c[mm], c[mm + 4], (B15[(size_t)(wq + 256 * mm) * 32] >> sh) & 15u);
+					} else {
 #pragma unroll
-					for (int m = 0; m < 4; ++m) x[m] = f_op4(c[m], c[m + 4]);
+						for (int mm = 0; mm < 4; ++mm) x[mm] = f_op4(c[mm], c[mm + 4]);
+					}
+					if (j1) {
+#pragma unroll
+						for (int mm = 0; mm < 2; ++mm) y[mm] = g_op4(x[mm], x[mm + 2], (B14[(size_t)(wq + 256 * mm) * 32] >> sh) & 15u);
+					} else {
+#pragma unroll
+						for (int mm = 0; mm < 2; ++mm) y[mm] = f_op4(x[mm], x[mm + 2]);
+					}
+					z[h] = j0 ? g_op4(y[0], y[1], (B13[(size_t)wq * 32] >> sh) & 15u) : f_op4(y[0], y[1]);
+					D13[q] = z[h];
 				}
-				if (j1) {
-#pragma unroll
-					for (int m = 0; m < 2; ++m) y[m] = g_op4(x[m], x[m + 2], (w14[h][m] >> sh) & 15u);
-				} else {
-#pragma unroll
-					for (int m = 0; m < 2; ++m) y[m] = f_op4(x[m], x[m + 2]);
-				}
-				z[h] = j0 ? g_op4(y[0], y[1], (w13[h] >> sh) & 15u) : f_op4(y[0], y[1]);
-				st_pol(&D13[(size_t)(q0 + k + 1024 * h) * 32 + lane32], z[h], p13);
+				D12[q0] = f_op4(z[0], z[1]);
 			}
-			if constexpr (D == 2) st_pol(&D12[(size_t)(q0 + k) * 32 + lane32], f_op4(z[0], z[1]), p12);
 		}
 	}
 }
-
-// Upper-level ops work on quads (float4 = 4 consecutive tree positions of one lane); loads of a batch of U quads are
-// issued before anything is stored so that U*2 128-bit loads are in flight per thread (the stores may alias the loads
-// as far as the compiler knows, so the batching has to be explicit).
-constexpr int kU = 4;
 
 __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclParams p)
 {
 	const int lane32 = threadIdx.x & 31;
 	const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int n_warps = (gridDim.x * blockDim.x) >> 5;
-	float4 *A = reinterpret_cast<float4 *>(p.A + (size_t)warp_global * p.a_stride);
+	float4 *A = reinterpret_cast<float4 *>(p.A) + (size_t)warp_global * kSclWarpQuads;
 	uint32_t *B = p.B + (size_t)warp_global * kSclWarpWords;
+	__shared__ __align__(16) float4 S5[kS5Quads];
+	__shared__ uint32_t crc_lut[256];
+	for (int i = lane32; i < 256; i += 32) { // CRC-32 0xD419CC15, reflected, one byte per step (decode.cc:198,534-537)
+		uint32_t v = (uint32_t)i;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) v = (v >> 1) ^ ((v & 1u) ? 0xD419CC15u : 0u);
+		crc_lut[i] = v;
+	}
+	__syncwarp();
 	SclCtx c;
 	c.t = lane32 & 7;
 	c.gbase = lane32 & ~7;
-	extern __shared__ __align__(16) float4 scl_smem[];
-	float4 *S = scl_smem;
-	c.A5 = lvl_ptr(A, S, 5);
+	const int j = c.t, gbase = c.gbase; // role above the words: position slice j of my codeword
 
 	// groups of four codewords never mix code tables (the four walk one schedule in lock step): table 0's groups first
 	const int n0 = p.n_cw_ptr ? p.n_cw_ptr[0] : p.n_cw[0], n1 = p.n_cw_ptr ? p.n_cw_ptr[1] : p.n_cw[1];
 	const int g0 = (n0 + 3) >> 2, g1 = (n1 + 3) >> 2;
-	for (int g4 = warp_global; g4 < g0 + g1; g4 += n_warps) {
+	for (;;) {
+		int g4 = 0;
+		if (lane32 == 0) g4 = atomicAdd(p.work, 1);
+		g4 = __shfl_sync(FULL, g4, 0);
+		if (g4 >= g0 + g1) break;
 		const int tb = g4 < g0 ? 0 : 1;
 		const int first = tb ? 4 * g0 : 0, n_cw = tb ? n1 : n0; // table 1's list starts at the next multiple of 4
 		const int slot = (g4 - (tb ? g0 : 0)) * 4 + (lane32 >> 3);
@@ -414,103 +459,177 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 		const float4 *C4 = reinterpret_cast<const float4 *>(C);
 		c.metric = c.t == 0 ? 0.f : 1000.f;
 		c.ret = c.t;
-		uint64_t lmstack = 0;
+		c.rep = 0;                // eight copies of one path
+		uint64_t lmstack = 0;     // [level]: lane map of the left child of the level's current node (kept by G / TOP for the C op)
+		uint64_t rsstack = 0;     // [level]: my class representative when the level's data was written (alphas until the G, then
+		                          // the left child's betas until the C): the slot to read them from
 
 		for (int pc = 0;; ++pc) {
 			const uint32_t opw = __ldg(&ops[pc]);
-			const uint32_t op = opw & 7u, l = (opw >> 3) & 31u, iw = (opw >> 8) & 0x3fffffu; // iw = first word of the node
+			const uint32_t op = opw & 7u, iw = (opw >> 8) & 0x3fffffu; // iw = first word of the node
+			const int l = (int)((opw >> 3) & 31u);
 			if (op == OP_END) break;
-			const int hq = 1 << (l - 3);               // quads per half node
-			const float4 *P = lvl_ptr(A, S, l > 15 ? 15 : (int)l); // parent level (valid for l <= 15)
+			const uint32_t repmask = (__ballot_sync(FULL, c.rep == c.t) >> gbase) & 255u; // my codeword's class representatives
 			if (op == OP_F || op == OP_G) {
-				const uint32_t depth = opw >> 30; // fused F steps that follow (0..2)
-				if (op == OP_G) lmstack = (lmstack & ~(7ull << (3 * l))) | ((uint64_t)c.ret << (3 * l));
-				const int src = op == OP_G ? c.gbase + c.ret : lane32;
-				const uint32_t *Bw = B + (size_t)iw * 32 + lane32;
-				// chains of at most kSclMaxFuse - 1 F steps (host_tables.h); deeper fusion measured slower (registers) and
-				// every instantiation costs instruction-cache footprint, which this kernel is short of
+				const uint32_t depth = opw >> 30; // fused F steps that follow (0..1)
+				int myps = stk_get(rsstack, l);
+				if (op == OP_G) {
+					lmstack = stk_set(lmstack, l, c.ret);
+					myps = __shfl_sync(FULL, myps, gbase + c.ret); // the slot of the lane I was when this node's alphas were written
+					rsstack = stk_set(rsstack, l, c.rep);          // from now on: where the left child's betas are (for the C op)
+				}
+				rsstack = stk_set(rsstack, l - 1, c.rep);
+				if (depth) rsstack = stk_set(rsstack, l - 2, c.rep);
+				const uint32_t *Bn = B + (size_t)iw * 32 + gbase;
+				// chains of at most kSclMaxFuse - 1 F steps (host_tables.h); every instantiation costs instruction-cache footprint
 				if (op == OP_F) {
-					if (depth == 1) fused_op<2, false>(A, S, C4, Bw, l, src, lane32);
-					else fused_op<1, false>(A, S, C4, Bw, l, src, lane32);
+					if (depth == 1) fused_op<2, false>(A, S5, Bn, l, gbase, j, repmask, myps);
+					else fused_op<1, false>(A, S5, Bn, l, gbase, j, repmask, myps);
 				} else {
-					if (depth == 1) fused_op<2, true>(A, S, C4, Bw, l, src, lane32);
-					else fused_op<1, true>(A, S, C4, Bw, l, src, lane32);
+					if (depth == 1) fused_op<2, true>(A, S5, Bn, l, gbase, j, repmask, myps);
+					else fused_op<1, true>(A, S5, Bn, l, gbase, j, repmask, myps);
 				}
 				__syncwarp();
 			} else if (op == OP_TOP) {
-				const int j = (int)(iw >> 8); // node index at level 13
-				if (j > 0) { // the left-hand relative at level 13 + ctz(j) has just completed: keep its lane map (as a G would)
-					const int lv = 14 + (__ffs(j) - 1);
-					lmstack = (lmstack & ~(7ull << (3 * lv))) | ((uint64_t)c.ret << (3 * lv));
+				const int jn = (int)(iw >> 8); // node index at level 13
+				if (jn > 0) { // the left-hand relative at level 13 + ctz(jn) has just completed: keep its lane map and slots (as a G would)
+					const int lv = 14 + (__ffs(jn) - 1);
+					lmstack = stk_set(lmstack, lv, c.ret);
+					rsstack = stk_set(rsstack, lv, c.rep);
 				}
-				const int lm14 = (int)((lmstack >> 42) & 7ull), lm15 = (int)((lmstack >> 45) & 7ull);
-				const int u = (j & 1) ? lm14 : c.t;                  // my lane when node (14, 2 j2) completed
-				const int a15 = __shfl_sync(FULL, lm15, c.gbase + u); // ... and when node (15, 0) completed
-				const int s14 = c.gbase + u, s15 = c.gbase + ((j & 2) ? a15 : u);
-				top_op<2>(A, C4, B, j, s15, s14, lane32, p.stream_level); // always chained with the F step below (host_tables.cc)
+				const int u = (jn & 1) ? stk_get(lmstack, 14) : c.t;                                        // my lane when the level-14 relative completed
+				const int v = (jn & 2) ? __shfl_sync(FULL, stk_get(lmstack, 15), gbase + u) : u;              // ... and when node (15, 0) completed
+				const int mys14 = __shfl_sync(FULL, stk_get(rsstack, 15), gbase + u);
+				const int mys15 = __shfl_sync(FULL, stk_get(rsstack, 16), gbase + v);
+				rsstack = stk_set(stk_set(rsstack, 13, c.rep), 12, c.rep);
+				top_op(A, C4, B, jn, gbase, j, repmask, mys14, mys15); // always chained with the F step below (host_tables.cc)
 				__syncwarp();
 			} else if (op == OP_WORD) {
 				c.fmask = __ldg(&frozen[iw]);
-				word32(c);
-				B[(size_t)iw * 32 + lane32] = c.W;
+				c.W = 0;
+				word32(c, S5, stk_get(rsstack, 5));
+				B[(size_t)iw * 32 + lane32] = c.W; // every lane writes its own slot (a superset of the representatives')
 				__syncwarp();
 			} else if (op == OP_R0) {
-				const int nq = 2 * hq;
-				float m = c.metric;
-				for (int q0 = 0; q0 < nq; q0 += 2 * kU) {
-					float4 v[2 * kU];
-					if (l == 16) {
+				// thread = list lane again: the penalties are summed in index order into every lane's own metric
+				const int nq = 1 << (l - 2);
+				const int gslot = gbase + stk_get(rsstack, l);
+				float mt = c.metric;
+				if (l == 5) {
 #pragma unroll
-						for (int u = 0; u < 2 * kU; ++u) v[u] = __ldg(&C4[q0 + u]);
-					} else {
+					for (int q = 0; q < 8; ++q) mt = r0_acc(mt, S5[q * kS5Pitch + gslot]);
+				} else {
+					const float4 *P = lvl_row(A, l, gslot);
+					for (int q0 = 0; q0 < nq; q0 += 8) {
+						float4 v[8];
 #pragma unroll
-						for (int u = 0; u < 2 * kU; ++u) v[u] = P[(q0 + u) * 32 + lane32];
+						for (int uu = 0; uu < 8; ++uu) v[uu] = P[q0 + uu];
+#pragma unroll
+						for (int uu = 0; uu < 8; ++uu) mt = r0_acc(mt, v[uu]);
 					}
-#pragma unroll
-					for (int u = 0; u < 2 * kU; ++u) m = r0_acc(m, v[u]);
 				}
-				c.metric = m;
+				c.metric = mt;
 				for (int w = 0; w < nq / 8; ++w) B[(size_t)(iw + w) * 32 + lane32] = 0u;
 				c.ret = c.t;
 				__syncwarp();
-			} else { // OP_C
-				const int hw = hq >> 3;
-				const int src = c.gbase + c.ret;
-				for (int w0 = 0; w0 < hw; w0 += 8) {
-					uint32_t x[8];
+			} else if (op == OP_R1) {
+				// rate-1 attempt: per class one pass over the node's alphas (thread j takes the words j, j + 8, ...): minimum
+				// magnitude and sign bits; the betas are stored before the verdict (nobody reads this node's words before they
+				// are decoded, and a failed attempt is followed by the ops that decode them)
+				const int nw = 1 << (l - 5);
+				float mymin = 0.f;
+				uint32_t m = repmask;
+				while (__any_sync(FULL, m != 0u)) {
+					const bool act = m != 0u;
+					const int r = act ? __ffs(m) - 1 : 0;
+					m &= m - 1u;
+					float mn = __int_as_float(0x7f800000);
+					if (act) {
+						const float4 *P = lvl_row(A, l, gbase + r);
+						for (int w = j; w < nw; w += 8) {
+							float4 v[8];
 #pragma unroll
-					for (int k = 0; k < 8; ++k)
-						if (w0 + k < hw) x[k] = B[(size_t)(iw + w0 + k) * 32 + src] ^ B[(size_t)(iw + hw + w0 + k) * 32 + lane32];
-					__syncwarp();
+							for (int q = 0; q < 8; ++q) v[q] = P[w * 8 + q];
+							uint32_t x = 0;
 #pragma unroll
-					for (int k = 0; k < 8; ++k)
-						if (w0 + k < hw) B[(size_t)(iw + w0 + k) * 32 + lane32] = x[k];
-					__syncwarp();
+							for (int q = 0; q < 8; ++q) { mn = min_abs4(mn, v[q]); x |= neg_bits4(v[q]) << (4 * q); }
+							B[(size_t)(iw + w) * 32 + gbase + r] = x;
+						}
+					}
+#pragma unroll
+					for (int d = 1; d < 8; d <<= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, d));
+					if (act && c.rep == r) mymin = mn;
 				}
-				const int lm = (int)((lmstack >> (3 * l)) & 7ull);
-				c.ret = __shfl_sync(FULL, lm, src);
+				if (list_is_stable(c, mymin)) {
+					c.ret = c.t;
+					pc = (int)__ldg(&ops[pc + 1]) - 1;
+				} else {
+					++pc;
+				}
+				__syncwarp();
+			} else { // OP_C
+				const int hw = 1 << (l - 6);
+				const int myL = __shfl_sync(FULL, stk_get(rsstack, l), gbase + c.ret); // the slot that holds the left half's betas of my path
+				uint32_t *Bl = B + (size_t)iw * 32 + gbase, *Br = Bl + (size_t)hw * 32;
+				if (__all_sync(FULL, repmask == 1u)) { // one class in every codeword of the warp: only slot 0 is written
+					const int L0 = __shfl_sync(FULL, myL, gbase);
+					for (int w = j; w < hw; w += 8) Bl[w * 32] = Bl[w * 32 + L0] ^ Br[w * 32];
+				} else {
+					const uint32_t b0 = (__ballot_sync(FULL, myL & 1) >> gbase) & 255u, b1 = (__ballot_sync(FULL, myL & 2) >> gbase) & 255u,
+						b2 = (__ballot_sync(FULL, myL & 4) >> gbase) & 255u;
+					for (int w = j; w < hw; w += 8) {
+						uint32_t x[8];
+#pragma unroll
+						for (int d = 0; d < 8; ++d)
+							if ((repmask >> d) & 1u) {
+								const int Ld = (int)(((b0 >> d) & 1u) | (((b1 >> d) & 1u) << 1) | (((b2 >> d) & 1u) << 2));
+								x[d] = Bl[w * 32 + Ld] ^ Br[w * 32 + d];
+							}
+#pragma unroll
+						for (int d = 0; d < 8; ++d)
+							if ((repmask >> d) & 1u) Bl[w * 32 + d] = x[d];
+					}
+				}
+				__syncwarp();
+				c.ret = __shfl_sync(FULL, stk_get(lmstack, l), gbase + c.ret);
 			}
 		}
 
 		// ---- candidate order, CRC-32 (decode.cc:532-541), payload (decode.cc:546-554) ------------------------
 		int rank = 0;
 #pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const float mj = __shfl_sync(FULL, c.metric, c.gbase + j);
-			rank += (mj < c.metric) || (mj == c.metric && j < c.t);
+		for (int k = 0; k < 8; ++k) {
+			const float mk = __shfl_sync(FULL, c.metric, gbase + k);
+			rank += (mk < c.metric) || (mk == c.metric && k < c.t);
 		}
+		const uint32_t *Bmine = B + gbase + c.rep; // the root's betas = my path's re-encoded codeword
 		uint32_t crc = 0;
 		{
-			int cnt = 0;
+			uint64_t acc = 0;
+			int nacc = 0, cnt = 0;
 			for (int w = 0; w < kCodeLen / 32 && cnt < kCrcBits; ++w) {
-				const uint32_t x = B[(size_t)w * 32 + lane32];
 				uint32_t fr = ~__ldg(&frozen[w]);
-				while (fr && cnt < kCrcBits) {
-					const int b = __ffs(fr) - 1;
-					fr &= fr - 1;
-					const uint32_t bit = (x >> b) & 1u;
-					crc = (crc >> 1) ^ (((crc ^ bit) & 1u) ? 0xD419CC15u : 0u);
-					++cnt;
+				if (!fr) continue;
+				const uint32_t x = Bmine[(size_t)w * 32];
+				uint32_t bits = x;
+				int n = 32;
+				if (fr != 0xffffffffu) {
+					bits = 0; n = 0;
+					while (fr) {
+						const int b = __ffs(fr) - 1;
+						fr &= fr - 1;
+						bits |= ((x >> b) & 1u) << n;
+						++n;
+					}
+				}
+				if (cnt + n > kCrcBits) { n = kCrcBits - cnt; bits &= (1u << n) - 1u; }
+				acc |= (uint64_t)bits << nacc;
+				nacc += n;
+				cnt += n;
+				while (nacc >= 8) {
+					crc = (crc >> 8) ^ crc_lut[(crc ^ (uint32_t)acc) & 255u];
+					acc >>= 8;
+					nacc -= 8;
 				}
 			}
 		}
@@ -519,32 +638,43 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 #pragma unroll
 		for (int d = 1; d < 8; d <<= 1) key = min(key, __shfl_xor_sync(FULL, key, d));
 		const unsigned bal = __ballot_sync(FULL, ok && rank == key);
-		const int win = __ffs((bal >> c.gbase) & 0xffu) - 1; // -1: no candidate passes the CRC
+		const int win = __ffs((bal >> gbase) & 0xffu) - 1; // -1: no candidate passes the CRC
+		const int wslot = __shfl_sync(FULL, c.rep, gbase + (win < 0 ? 0 : win));
 		int flips = 0;
 		if (active) {
 			FrameState &st = p.st[frame];
 			st.metrics[rank] = c.metric;
 			if (p.xbits)
 				for (int w = 0; w < kCodeLen / 32; ++w)
-					p.xbits[((size_t)(first + slot) * 8 + rank) * (kCodeLen / 32) + w] = B[(size_t)w * 32 + lane32];
+					p.xbits[((size_t)(first + slot) * 8 + rank) * (kCodeLen / 32) + w] = Bmine[(size_t)w * 32];
 			if (win >= 0) {
 				uint32_t *out = p.payload + (size_t)frame * (kDataBytes / 4);
+				const uint32_t *Bwin = B + gbase + wslot;
 				for (int w = c.t; w < kCodeLen / 32; w += 8) {
 					const int base = (int)__ldg(&frozen[kSclTblMsgOff + w]);
 					if (base >= kDataBits) break;
-					const uint32_t x = B[(size_t)w * 32 + c.gbase + win];
 					uint32_t fr = ~__ldg(&frozen[w]);
-					uint64_t m = 0;
-					int k = 0;
-					while (fr && base + k < kDataBits) {
-						const int b = __ffs(fr) - 1;
-						fr &= fr - 1;
-						const uint32_t bit = (x >> b) & 1u;
-						m |= (uint64_t)bit << k;
-						flips += (int)((C[w * 32 + b] < 0.f) != (bit != 0u));
-						++k;
+					if (!fr) continue;
+					const uint32_t x = Bwin[(size_t)w * 32];
+					uint32_t neg = 0; // channel hard decisions of the word (decode.cc:549-552)
+#pragma unroll
+					for (int q = 0; q < 8; ++q) neg |= neg_bits4(__ldg(&C4[w * 8 + q])) << (4 * q);
+					uint64_t mbits = x;
+					int k = 32;
+					if (fr != 0xffffffffu || base + 32 > kDataBits) {
+						mbits = 0; k = 0;
+						while (fr && base + k < kDataBits) {
+							const int b = __ffs(fr) - 1;
+							fr &= fr - 1;
+							const uint32_t bit = (x >> b) & 1u;
+							mbits |= (uint64_t)bit << k;
+							flips += (int)(((neg >> b) & 1u) != bit);
+							++k;
+						}
+					} else {
+						flips += __popc(neg ^ x);
 					}
-					const uint64_t sh = m << (base & 31);
+					const uint64_t sh = mbits << (base & 31);
 					const int wi = base >> 5;
 					if ((uint32_t)sh) atomicXor(&out[wi], (uint32_t)sh);
 					if ((uint32_t)(sh >> 32) && wi + 1 < kDataBytes / 4) atomicXor(&out[wi + 1], (uint32_t)(sh >> 32));
@@ -563,10 +693,12 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 	}
 }
 
-// payload buffer <- scrambler sequence (decode.cc:613-615: out ^= xorshift); the decoder XORs the message in.
-__global__ void k_payload_init(uint32_t *payload, const uint32_t *scr_words, int n_frames)
+// payload buffer <- scrambler sequence (decode.cc:613-615: out ^= xorshift); the decoder XORs the message in.  Also resets
+// the list decoder's work counter.
+__global__ void k_payload_init(uint32_t *payload, const uint32_t *scr_words, int n_frames, int *work)
 {
 	const int per = kDataBytes / 4;
+	if (work && blockIdx.x == 0 && threadIdx.x == 0) *work = 0;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n_frames * per; i += (size_t)gridDim.x * blockDim.x)
 		payload[i] = scr_words[i % per];
 }
@@ -575,24 +707,23 @@ __global__ void k_payload_init(uint32_t *payload, const uint32_t *scr_words, int
 
 int scl_resident_warps(int ctas_per_sm, int n_sm) { return ctas_per_sm * n_sm * (kSclThreads / 32); }
 
-cudaError_t launch_payload_init(uint32_t *payload, const uint32_t *scr_words, int n_frames, cudaStream_t s)
+cudaError_t launch_payload_init(uint32_t *payload, const uint32_t *scr_words, int n_frames, int *work, cudaStream_t s)
 {
-	if (n_frames <= 0) return cudaSuccess;
-	k_payload_init<<<592, 256, 0, s>>>(payload, scr_words, n_frames);
+	k_payload_init<<<n_frames > 0 ? 592 : 1, 256, 0, s>>>(payload, scr_words, n_frames, work);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_polar_scl(const SclParams &p, int grid, cudaStream_t s)
 {
 	if (!p.n_cw_ptr && p.n_cw[0] + p.n_cw[1] <= 0) return cudaSuccess;
-	k_polar_scl<<<grid, kSclThreads, kSclSmemBytes, s>>>(p);
+	k_polar_scl<<<grid, kSclThreads, 0, s>>>(p);
 	return cudaGetLastError();
 }
 
 int scl_occupancy_ctas_per_sm()
 {
 	int n = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_polar_scl, kSclThreads, kSclSmemBytes);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_polar_scl, kSclThreads, 0);
 	return n;
 }
 

@@ -19,8 +19,18 @@ def test_frozen_sets_match(oracle, hostlib):
 
 def test_schedule_structure(hostlib):
     n = hostlib.host_schedule(None, 0)
-    ops = np.zeros(n, np.uint32)
-    hostlib.host_schedule(_p(ops), n)
+    raw = np.zeros(n, np.uint32)
+    hostlib.host_schedule(_p(raw), n)
+    # OP_R1 (6) carries one extra word: the pc to continue at when the rate-1 attempt succeeds
+    keep, skip_of, pc = [], {}, 0
+    while pc < n:
+        keep.append(pc)
+        if raw[pc] & 7 == 6:
+            skip_of[pc] = int(raw[pc + 1])
+            pc += 1
+        pc += 1
+    keep = np.array(keep)
+    ops = raw[keep]
     op, lvl, idx, depth = ops & 7, (ops >> 3) & 31, ((ops >> 8) & 0x3FFFFF) * 32, (ops >> 30) + 1
     assert op[-1] == 7 and (op[:-1] != 7).all()
     fr = np.zeros(2048, np.uint32)
@@ -41,6 +51,19 @@ def test_schedule_structure(hostlib):
     assert f_steps == (op == 1).sum() == (op == 4).sum() - 7
     assert (lvl[op == 1] - depth[op == 1] + 1).min() >= 6 and depth.max() == 2 and (depth[top] == 2).all()
     assert (depth[(op != 0) & (op != 1) & ~top] == 1).all()
+    # rate-1 attempts: on all-free nodes above the words only, never on the left child of an all-free node, and the skip
+    # target is the op after the node's own C (the next op that touches a later index or a higher level)
+    pos = {int(k): i for i, k in enumerate(keep)}
+    assert len(skip_of) > 100
+    for pc, tgt in skip_of.items():
+        i = pos[pc]
+        l, ix = int(lvl[i]), int(idx[i])
+        assert 6 <= l <= 12 and (fr[ix // 32:(ix + (1 << l)) // 32] == 0).all()
+        par = ix & ~((2 << l) - 1)
+        assert ix != par or not (fr[par // 32:(par + (2 << l)) // 32] == 0).all()   # a left child: its parent is not all-free
+        assert op[i + 1] == 0 and lvl[i + 1] == l and idx[i + 1] == ix               # the attempt is followed by the node's own F
+        k = pos[tgt]
+        assert op[k - 1] == 4 and lvl[k - 1] == l and idx[k - 1] == ix              # ... and skips to just after its own C
 
 
 def test_fft_plans_of_all_sample_rates():
