@@ -162,7 +162,7 @@ static_assert(sizeof(TsShared) == 11264, "11 KB per row: five 4-warp CTAs (20 ro
 
 // k-th smallest (0-based) of the n values v[] (shared memory of this warp; order-preserving integer images of
 // floats, see f2ord), exact: radix select, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
-__device__ __noinline__ int warp_select_kth(const int *v, int n, int k, int *hist, int lane)
+__device__ __noinline__ int warp_select_radix(const int *v, int n, int k, int *hist, int lane)
 {
 	int mn = 0x7fffffff, mx = (int)0x80000000;
 	for (int i = lane; i < n; i += 32) { const int o = v[i]; mn = min(mn, o); mx = max(mx, o); }
@@ -205,6 +205,63 @@ __device__ __noinline__ int warp_select_kth(const int *v, int n, int k, int *his
 		sh = max(0, sh - 8);
 	}
 	return lo;
+}
+
+// The same order statistic in two passes for values that spread like measurements do: 256 buckets linear in the float
+// value between min and max (a monotone map, so the k-th smallest lies in the bucket where the running count passes k),
+// then the few members of that bucket are ranked against each other.  Crowded buckets (ties, outliers that stretch the
+// range) go to the radix select, on the bucket's members only.  v[] is overwritten from its start with those members.
+__device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int lane)
+{
+	float mn = __int_as_float(0x7f800000), mx = -mn;
+	for (int i = lane; i < n; i += 32) { const float x = ord2f(v[i]); mn = fminf(mn, x); mx = fmaxf(mx, x); }
+#pragma unroll
+	for (int d = 16; d; d >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL, mn, d)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d)); }
+	if (!(mx - mn < 3.0e38f) || !(mx > mn)) return warp_select_radix(v, n, k, hist, lane); // all equal, or not finite
+	const float sc = 256.f / (mx - mn);
+#pragma unroll
+	for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0;
+	__syncwarp();
+	for (int i = lane; i < n; i += 32) atomicAdd(&hist[min(255, __float2int_rz((ord2f(v[i]) - mn) * sc))], 1);
+	__syncwarp();
+	int h[8], sum = 0;
+#pragma unroll
+	for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; sum += h[b]; }
+	int incl = sum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += o; }
+	const int excl = incl - sum;
+	const bool mine = k >= excl && k < incl;
+	int bin = 0, kk = 0;
+	if (mine) {
+		kk = k - excl;
+#pragma unroll
+		for (int b = 0; b < 8; ++b) { if (bin == b && kk >= h[b]) { kk -= h[b]; bin = b + 1; } }
+		bin += lane * 8;
+	}
+	const unsigned bal = __ballot_sync(FULL, mine);
+	if (bal == 0u) return f2ord(mx); // k out of range (callers never ask for it): keep the function total
+	const int src = __ffs(bal) - 1;
+	bin = __shfl_sync(FULL, bin, src);
+	kk = __shfl_sync(FULL, kk, src);
+	// members of that bucket, compacted to the front of v[] (reads run ahead of the writes: slot <= i)
+	int m = 0;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + lane;
+		const int o = i < n ? v[i] : 0;
+		const bool in = i < n && min(255, __float2int_rz((ord2f(o) - mn) * sc)) == bin;
+		const unsigned bl = __ballot_sync(FULL, in);
+		__syncwarp();
+		if (in) v[m + __popc(bl & ((1u << lane) - 1u))] = o;
+		m += __popc(bl);
+	}
+	__syncwarp();
+	if (m > 32) return warp_select_radix(v, m, kk, hist, lane);
+	const int mine_v = lane < m ? v[lane] : 0x7fffffff;
+	int rank = 0;
+	for (int e = 0; e < m; ++e) { const int o = v[e]; rank += (o < mine_v) || (o == mine_v && e < lane); }
+	const unsigned hit = __ballot_sync(FULL, lane < m && rank == kk);
+	return __shfl_sync(FULL, mine_v, __ffs(hit) - 1);
 }
 
 // ---- the pair sweep ---------------------------------------------------------------------------------------------

@@ -235,6 +235,29 @@ void crc32_table(uint32_t poly, uint32_t *lut)
 		lut[j] = t;
 	}
 }
+std::vector<uint32_t> crc32_pieces(const std::vector<uint32_t> &frozen, int crc_bits)
+{
+	const int words = (int)frozen.size();
+	std::vector<int> before(words + 1, 0);
+	for (int w = 0; w < words; ++w) before[w + 1] = before[w] + 32 - __builtin_popcount(frozen[w]);
+	std::vector<uint32_t> out(16 + 256, 0);
+	for (int j = 0; j <= 8; ++j) { // piece j starts at the first word holding message bit j * crc_bits / 8 or a later one
+		const int target = (int)((long long)j * crc_bits / 8);
+		int w = 0;
+		while (w < words && before[w] < target) ++w;
+		out[j] = (uint32_t)w;
+	}
+	for (int j = 0; j < 8; ++j) {
+		const int end_bits = std::min(crc_bits, before[out[j + 1]]); // message bits up to the end of piece j
+		const int follow = crc_bits - std::min(crc_bits, std::max(end_bits, 0));
+		for (int c = 0; c < 32; ++c) {
+			uint32_t reg = 1u << c;
+			for (int n = 0; n < follow; ++n) reg = (reg >> 1) ^ ((reg & 1u) ? 0xD419CC15u : 0u);
+			out[16 + 32 * j + c] = reg;
+		}
+	}
+	return out;
+}
 uint16_t crc16_u64(uint64_t v)
 {
 	uint16_t crc = 0;

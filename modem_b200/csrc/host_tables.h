@@ -95,6 +95,10 @@ std::vector<float> hilbert_coeffs(int taps, float *reco);    // imag-branch coef
 std::vector<float> twiddles(int n, int sign);                // n complex values exp(sign*2*pi*j*k/n) as (re,im) pairs
 std::vector<float> mls0_kernel(int half = kHalf);             // conj(FFT_half(template))/half, `half` complex values (decode.cc:76-83,236-244)
 void crc32_table(uint32_t poly, uint32_t *lut256);
+// CRC-32 (0xD419CC15, reflected, init 0) of the first crc_bits message bits in 8 pieces of about equal length: out[0..8] = word
+// bounds of the pieces (message bits = the non-frozen positions), out[16 + 32 j + c] = register bit c advanced over the message
+// bits that follow piece j.  The list decoder XORs the advanced piece registers (decode.cc:534-537 computes the same CRC bit by bit).
+std::vector<uint32_t> crc32_pieces(const std::vector<uint32_t> &frozen, int crc_bits);
 uint16_t crc16_u64(uint64_t v);                              // CRC-16 0xA8F4 over the 8 LE bytes (decode.cc:428-429)
 void base37_decode(char *str, long long val, int len);       // decode.cc:155-159
 

@@ -174,6 +174,8 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	for (int tb = 0; tb < 2; ++tb) {
 		std::vector<uint32_t> tbl(h->h_frozen[tb]);
 		tbl.insert(tbl.end(), msg_off[tb].begin(), msg_off[tb].end());
+		const std::vector<uint32_t> pieces = crc32_pieces(h->h_frozen[tb], kCrcBits);
+		tbl.insert(tbl.end(), pieces.begin(), pieces.end());
 		tbl.insert(tbl.end(), h->h_ops[tb].begin(), h->h_ops[tb].end());
 		if (!r) r = dev_upload(&h->d_tbl[tb], tbl.data(), tbl.size());
 	}

@@ -240,6 +240,7 @@ __device__ __noinline__ Sub node16(float4 x0, float4 x1, float4 x2, float4 x3, u
 // slots) and the level-6 ops' writers (8 quads of one slot) both touch eight different 16-byte bank groups.
 constexpr int kS5Pitch = 33;
 constexpr int kS5Quads = 8 * kS5Pitch;
+constexpr int kCStage = 2; // words per thread and round an OP_C stages in shared memory (2 KB per warp)
 
 // the whole word: thread = list lane; `rs5` = the slot that holds my level-5 alphas (my class representative when they were written)
 __device__ __forceinline__ void word32(SclCtx &c, const float4 *S5, int rs5)
@@ -313,16 +314,20 @@ __device__ __forceinline__ void st_lvl(float4 *A, float4 *S5, int l, int gslot, 
 __device__ __forceinline__ int stk_get(uint64_t s, int l) { return (int)((s >> (3 * l)) & 7ull); }
 __device__ __forceinline__ uint64_t stk_set(uint64_t s, int l, int v) { return (s & ~(7ull << (3 * l))) | ((uint64_t)v << (3 * l)); }
 
-// F or G at level l fused with the D-1 F steps that follow it down the left spine (host_tables.cc: depth field), for every
-// path class of the codeword in turn.  The eight threads of the codeword split the positions: thread j takes the quad
+// beta bits: [codeword * 8 + slot][2048 words] per warp — a path's partial sums are one contiguous 8 KB row, so the eight
+// threads of a codeword read and write consecutive words of it
+__device__ __forceinline__ uint32_t *beta_row(uint32_t *B, int gslot) { return B + ((size_t)gslot << 11); }
+
+// F or G at level l, optionally fused with the F step that follows it down the left spine (host_tables.cc: depth field), for
+// every path class of the codeword in turn.  The eight threads of the codeword split the positions: thread j takes the quad
 // pairs q = j, j + 8, ... of the parent whose results meet again in the chained F step, so the intermediate level is
-// produced in registers, written once (the later G needs it) and never re-read by an F.  Up to 8 x 128-bit loads are in
-// flight per thread.  `myps` = slot of the parent alphas of MY lane (meaningful on the representatives).
-template <int D, bool IS_G>
-__device__ __forceinline__ void fused_op(float4 *A, float4 *S5, const uint32_t *Bn, int l, int gbase, int j, uint32_t repmask, int myps)
+// produced in registers, written once (the later G needs it) and never re-read by an F.  Four 128-bit loads are in flight
+// per thread and turn.  One instantiation serves F and G, chained or not (the kernel is short of instruction cache, not
+// of issue slots).  `myps` = slot of the parent alphas of MY lane (meaningful on the representatives); iw = first beta word
+// of the node.
+__device__ __forceinline__ void fused_op(float4 *A, float4 *S5, const uint32_t *B, int iw, int l, bool is_g, bool chain, int gbase, int j, uint32_t repmask, int myps)
 {
-	constexpr int M = 1 << (D - 1);
-	const int hq = 1 << (l - 3), step = hq >> (D - 1);
+	const int hq = 1 << (l - 3), step = chain ? hq >> 1 : hq, second = chain ? step : 8;
 	uint32_t m = repmask;
 	while (__any_sync(FULL, m != 0u)) {
 		const bool act = m != 0u;
@@ -331,35 +336,26 @@ __device__ __forceinline__ void fused_op(float4 *A, float4 *S5, const uint32_t *
 		const int ps = __shfl_sync(FULL, myps, gbase + r);
 		if (act) {
 			const float4 *P = lvl_row(A, l, gbase + ps);
-			const uint32_t *Bw = Bn + r;
-			for (int q0 = j; q0 < step; q0 += 16) {
-				const bool two = q0 + 8 < step;
-				float4 pa[2][M], pb[2][M];
-				uint32_t bw[2][M];
-#pragma unroll
-				for (int u = 0; u < 2; ++u)
-					if (u == 0 || two) {
-#pragma unroll
-						for (int mm = 0; mm < M; ++mm) {
-							const int q = q0 + 8 * u + mm * step;
-							pa[u][mm] = P[q];
-							pb[u][mm] = P[q + hq];
-							if constexpr (IS_G) bw[u][mm] = Bw[(q >> 3) * 32];
-						}
-					}
-#pragma unroll
-				for (int u = 0; u < 2; ++u)
-					if (u == 0 || two) {
-						float4 v1[M];
-#pragma unroll
-						for (int mm = 0; mm < M; ++mm) {
-							const int q = q0 + 8 * u + mm * step;
-							if constexpr (IS_G) v1[mm] = g_op4(pa[u][mm], pb[u][mm], (bw[u][mm] >> (4 * j)) & 15u);
-							else v1[mm] = f_op4(pa[u][mm], pb[u][mm]);
-							st_lvl(A, S5, l - 1, gbase + r, q, v1[mm]);
-						}
-						if constexpr (D >= 2) st_lvl(A, S5, l - 2, gbase + r, q0 + 8 * u, f_op4(v1[0], v1[1]));
-					}
+			const uint32_t *Bw = beta_row(const_cast<uint32_t *>(B), gbase + r) + iw;
+			// per turn two quad pairs: q and q + step when an F step is chained (its two operands), else q and q + 8
+			for (int q0 = j; q0 < step; q0 += chain ? 8 : 16) {
+				const int q1 = q0 + second;
+				const bool two = chain || q1 < step;
+				const float4 pa0 = P[q0], pb0 = P[q0 + hq];
+				float4 pa1 = pa0, pb1 = pb0;
+				if (two) { pa1 = P[q1]; pb1 = P[q1 + hq]; }
+				float4 v0, v1;
+				if (is_g) {
+					const uint32_t w0 = Bw[q0 >> 3], w1 = two ? Bw[q1 >> 3] : 0u;
+					v0 = g_op4(pa0, pb0, (w0 >> (4 * j)) & 15u);
+					v1 = g_op4(pa1, pb1, (w1 >> (4 * j)) & 15u);
+				} else {
+					v0 = f_op4(pa0, pb0);
+					v1 = f_op4(pa1, pb1);
+				}
+				st_lvl(A, S5, l - 1, gbase + r, q0, v0);
+				if (two) st_lvl(A, S5, l - 1, gbase + r, q1, v1);
+				if (chain) st_lvl(A, S5, l - 2, gbase + r, q0, f_op4(v0, v1));
 			}
 		}
 	}
@@ -380,9 +376,9 @@ __device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32
 		m &= m - 1u;
 		const int s14 = __shfl_sync(FULL, mys14, gbase + r), s15 = __shfl_sync(FULL, mys15, gbase + r);
 		if (act) {
-			const uint32_t *B15 = B + gbase + s15;                                            // beta of node (15, 0): words 0..1023
-			const uint32_t *B14 = B + (size_t)(j2 ? 1024 : 0) * 32 + gbase + s14;             // beta of node (14, 2 j2)
-			const uint32_t *B13 = B + (size_t)(j0 ? (jn - 1) * 256 : 0) * 32 + gbase + r;     // beta of node (13, jn - 1)
+			const uint32_t *B15 = beta_row(const_cast<uint32_t *>(B), gbase + s15);                            // beta of node (15, 0): words 0..1023
+			const uint32_t *B14 = beta_row(const_cast<uint32_t *>(B), gbase + s14) + (j2 ? 1024 : 0);          // beta of node (14, 2 j2)
+			const uint32_t *B13 = beta_row(const_cast<uint32_t *>(B), gbase + r) + (j0 ? (jn - 1) * 256 : 0);  // beta of node (13, jn - 1)
 			float4 *D13 = lvl_row(A, 13, gbase + r), *D12 = lvl_row(A, 12, gbase + r);
 			const int sh = 4 * j;
 #pragma unroll 1
@@ -397,19 +393,19 @@ __device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32
 					float4 x[4], y[2];
 					if (j2) {
 #pragma unroll
-						for (int mm = 0; mm < 4; ++mm) x[mm] = g_op4(c[mm], c[mm + 4], (B15[(size_t)(wq + 256 * mm) * 32] >> sh) & 15u);
+						for (int mm = 0; mm < 4; ++mm) x[mm] = g_op4(c[mm], c[mm + 4], (B15[wq + 256 * mm] >> sh) & 15u);
 					} else {
 #pragma unroll
 						for (int mm = 0; mm < 4; ++mm) x[mm] = f_op4(c[mm], c[mm + 4]);
 					}
 					if (j1) {
 #pragma unroll
-						for (int mm = 0; mm < 2; ++mm) y[mm] = g_op4(x[mm], x[mm + 2], (B14[(size_t)(wq + 256 * mm) * 32] >> sh) & 15u);
+						for (int mm = 0; mm < 2; ++mm) y[mm] = g_op4(x[mm], x[mm + 2], (B14[wq + 256 * mm] >> sh) & 15u);
 					} else {
 #pragma unroll
 						for (int mm = 0; mm < 2; ++mm) y[mm] = f_op4(x[mm], x[mm + 2]);
 					}
-					z[h] = j0 ? g_op4(y[0], y[1], (B13[(size_t)wq * 32] >> sh) & 15u) : f_op4(y[0], y[1]);
+					z[h] = j0 ? g_op4(y[0], y[1], (B13[wq] >> sh) & 15u) : f_op4(y[0], y[1]);
 					D13[q] = z[h];
 				}
 				D12[q0] = f_op4(z[0], z[1]);
@@ -426,6 +422,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 	uint32_t *B = p.B + (size_t)warp_global * kSclWarpWords;
 	__shared__ __align__(16) float4 S5[kS5Quads];
 	__shared__ uint32_t crc_lut[256];
+	__shared__ uint32_t SX[kCStage * 8 * 32]; // OP_C staging: [word of the thread][slot][thread]
 	for (int i = lane32; i < 256; i += 32) { // CRC-32 0xD419CC15, reflected, one byte per step (decode.cc:198,534-537)
 		uint32_t v = (uint32_t)i;
 #pragma unroll
@@ -480,15 +477,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 				}
 				rsstack = stk_set(rsstack, l - 1, c.rep);
 				if (depth) rsstack = stk_set(rsstack, l - 2, c.rep);
-				const uint32_t *Bn = B + (size_t)iw * 32 + gbase;
-				// chains of at most kSclMaxFuse - 1 F steps (host_tables.h); every instantiation costs instruction-cache footprint
-				if (op == OP_F) {
-					if (depth == 1) fused_op<2, false>(A, S5, Bn, l, gbase, j, repmask, myps);
-					else fused_op<1, false>(A, S5, Bn, l, gbase, j, repmask, myps);
-				} else {
-					if (depth == 1) fused_op<2, true>(A, S5, Bn, l, gbase, j, repmask, myps);
-					else fused_op<1, true>(A, S5, Bn, l, gbase, j, repmask, myps);
-				}
+				fused_op(A, S5, B, (int)iw, l, op == OP_G, depth != 0u, gbase, j, repmask, myps); // chains of at most one F step (host_tables.h)
 				__syncwarp();
 			} else if (op == OP_TOP) {
 				const int jn = (int)(iw >> 8); // node index at level 13
@@ -508,7 +497,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 				c.fmask = __ldg(&frozen[iw]);
 				c.W = 0;
 				word32(c, S5, stk_get(rsstack, 5));
-				B[(size_t)iw * 32 + lane32] = c.W; // every lane writes its own slot (a superset of the representatives')
+				if (c.rep == c.t) beta_row(B, lane32)[iw] = c.W;
 				__syncwarp();
 			} else if (op == OP_R0) {
 				// thread = list lane again: the penalties are summed in index order into every lane's own metric
@@ -529,7 +518,10 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 					}
 				}
 				c.metric = mt;
-				for (int w = 0; w < nq / 8; ++w) B[(size_t)(iw + w) * 32 + lane32] = 0u;
+				if (c.rep == c.t) {
+					uint32_t *Bz = beta_row(B, lane32) + iw;
+					for (int w = 0; w < nq / 8; ++w) Bz[w] = 0u;
+				}
 				c.ret = c.t;
 				__syncwarp();
 			} else if (op == OP_R1) {
@@ -553,7 +545,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 							uint32_t x = 0;
 #pragma unroll
 							for (int q = 0; q < 8; ++q) { mn = min_abs4(mn, v[q]); x |= neg_bits4(v[q]) << (4 * q); }
-							B[(size_t)(iw + w) * 32 + gbase + r] = x;
+							beta_row(B, gbase + r)[iw + w] = x;
 						}
 					}
 #pragma unroll
@@ -570,24 +562,32 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 			} else { // OP_C
 				const int hw = 1 << (l - 6);
 				const int myL = __shfl_sync(FULL, stk_get(rsstack, l), gbase + c.ret); // the slot that holds the left half's betas of my path
-				uint32_t *Bl = B + (size_t)iw * 32 + gbase, *Br = Bl + (size_t)hw * 32;
-				if (__all_sync(FULL, repmask == 1u)) { // one class in every codeword of the warp: only slot 0 is written
-					const int L0 = __shfl_sync(FULL, myL, gbase);
-					for (int w = j; w < hw; w += 8) Bl[w * 32] = Bl[w * 32 + L0] ^ Br[w * 32];
-				} else {
-					const uint32_t b0 = (__ballot_sync(FULL, myL & 1) >> gbase) & 255u, b1 = (__ballot_sync(FULL, myL & 2) >> gbase) & 255u,
-						b2 = (__ballot_sync(FULL, myL & 4) >> gbase) & 255u;
-					for (int w = j; w < hw; w += 8) {
-						uint32_t x[8];
+				// every class: left half <- (left half of the slot it descends from) ^ (its right half).  A class may read a slot
+				// that another class of the codeword overwrites in the same op: all reads of a word come before its writes
+				// (staged in shared memory, one column per thread; thread j takes the words j, j + 8, ...).
+				for (int wb = 0; wb < hw; wb += 8 * kCStage) { // (warp-uniform trip count: the class loop below votes)
+					const int w0 = wb + j;
+					uint32_t m = repmask;
+					while (__any_sync(FULL, m != 0u)) {
+						const bool act = m != 0u;
+						const int r = act ? __ffs(m) - 1 : 0;
+						m &= m - 1u;
+						const int Lr = __shfl_sync(FULL, myL, gbase + r);
+						if (act) {
+							const uint32_t *Bl = beta_row(B, gbase + Lr) + iw, *Br = beta_row(B, gbase + r) + iw + hw;
 #pragma unroll
-						for (int d = 0; d < 8; ++d)
-							if ((repmask >> d) & 1u) {
-								const int Ld = (int)(((b0 >> d) & 1u) | (((b1 >> d) & 1u) << 1) | (((b2 >> d) & 1u) << 2));
-								x[d] = Bl[w * 32 + Ld] ^ Br[w * 32 + d];
-							}
+							for (int k = 0; k < kCStage; ++k)
+								if (w0 + 8 * k < hw) SX[(k * 8 + r) * 32 + lane32] = Bl[w0 + 8 * k] ^ Br[w0 + 8 * k];
+						}
+					}
+					m = repmask;
+					while (m) { // (no collective inside: this loop may run differently long in the four codewords)
+						const int r = __ffs(m) - 1;
+						m &= m - 1u;
+						uint32_t *Bl = beta_row(B, gbase + r) + iw;
 #pragma unroll
-						for (int d = 0; d < 8; ++d)
-							if ((repmask >> d) & 1u) Bl[w * 32 + d] = x[d];
+						for (int k = 0; k < kCStage; ++k)
+							if (w0 + 8 * k < hw) Bl[w0 + 8 * k] = SX[(k * 8 + r) * 32 + lane32];
 					}
 				}
 				__syncwarp();
@@ -602,37 +602,63 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 			const float mk = __shfl_sync(FULL, c.metric, gbase + k);
 			rank += (mk < c.metric) || (mk == c.metric && k < c.t);
 		}
-		const uint32_t *Bmine = B + gbase + c.rep; // the root's betas = my path's re-encoded codeword
+		// CRC-32 of every distinct path, once: the eight threads of the codeword take one eighth of the message bits each
+		// (word ranges from the table), and the pieces are joined through the CRC's linearity — the register after piece j,
+		// advanced over the bits that follow it (a 32 x 32 bit matrix per piece, host_tables.cc), XORed over the pieces.
 		uint32_t crc = 0;
 		{
-			uint64_t acc = 0;
-			int nacc = 0, cnt = 0;
-			for (int w = 0; w < kCodeLen / 32 && cnt < kCrcBits; ++w) {
-				uint32_t fr = ~__ldg(&frozen[w]);
-				if (!fr) continue;
-				const uint32_t x = Bmine[(size_t)w * 32];
-				uint32_t bits = x;
-				int n = 32;
-				if (fr != 0xffffffffu) {
-					bits = 0; n = 0;
-					while (fr) {
-						const int b = __ffs(fr) - 1;
-						fr &= fr - 1;
-						bits |= ((x >> b) & 1u) << n;
-						++n;
+			const uint32_t *ctab = frozen + kSclTblCrc;
+			const int w_begin = (int)__ldg(&ctab[j]), w_end = (int)__ldg(&ctab[j + 1]);
+			uint32_t m = (__ballot_sync(FULL, c.rep == c.t) >> gbase) & 255u;
+			while (__any_sync(FULL, m != 0u)) {
+				const bool act = m != 0u;
+				const int r = act ? __ffs(m) - 1 : 0;
+				m &= m - 1u;
+				uint32_t part = 0;
+				if (act) {
+					const uint32_t *Brow = beta_row(B, gbase + r);
+					uint32_t reg = 0;
+					uint64_t acc = 0;
+					int nacc = 0;
+					for (int w = w_begin; w < w_end; ++w) {
+						uint32_t fr = ~__ldg(&frozen[w]);
+						if (!fr) continue;
+						const int base = (int)__ldg(&frozen[kSclTblMsgOff + w]);
+						const uint32_t x = Brow[w];
+						uint32_t bits = x;
+						int n = 32;
+						if (fr != 0xffffffffu) {
+							bits = 0; n = 0;
+							while (fr) {
+								const int b = __ffs(fr) - 1;
+								fr &= fr - 1;
+								bits |= ((x >> b) & 1u) << n;
+								++n;
+							}
+						}
+						if (base + n > kCrcBits) { n = kCrcBits - base; bits &= (1u << n) - 1u; } // (only in the last piece; n > 0 there)
+						acc |= (uint64_t)bits << nacc;
+						nacc += n;
+						while (nacc >= 8) {
+							reg = (reg >> 8) ^ crc_lut[(reg ^ (uint32_t)acc) & 255u];
+							acc >>= 8;
+							nacc -= 8;
+						}
+					}
+					for (; nacc > 0; --nacc, acc >>= 1) reg = (reg >> 1) ^ (((reg ^ (uint32_t)acc) & 1u) ? 0xD419CC15u : 0u);
+					const uint32_t *M = ctab + 16 + 32 * j;
+					while (reg) {
+						const int b = __ffs(reg) - 1;
+						reg &= reg - 1u;
+						part ^= __ldg(&M[b]);
 					}
 				}
-				if (cnt + n > kCrcBits) { n = kCrcBits - cnt; bits &= (1u << n) - 1u; }
-				acc |= (uint64_t)bits << nacc;
-				nacc += n;
-				cnt += n;
-				while (nacc >= 8) {
-					crc = (crc >> 8) ^ crc_lut[(crc ^ (uint32_t)acc) & 255u];
-					acc >>= 8;
-					nacc -= 8;
-				}
+#pragma unroll
+				for (int d = 1; d < 8; d <<= 1) part ^= __shfl_xor_sync(FULL, part, d);
+				if (act && c.rep == r) crc = part;
 			}
 		}
+		const uint32_t *Bmine = beta_row(B, gbase + c.rep); // the root's betas = my path's re-encoded codeword
 		const bool ok = crc == 0u;
 		int key = ok ? rank : 64;
 #pragma unroll
@@ -646,16 +672,16 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 			st.metrics[rank] = c.metric;
 			if (p.xbits)
 				for (int w = 0; w < kCodeLen / 32; ++w)
-					p.xbits[((size_t)(first + slot) * 8 + rank) * (kCodeLen / 32) + w] = Bmine[(size_t)w * 32];
+					p.xbits[((size_t)(first + slot) * 8 + rank) * (kCodeLen / 32) + w] = Bmine[w];
 			if (win >= 0) {
 				uint32_t *out = p.payload + (size_t)frame * (kDataBytes / 4);
-				const uint32_t *Bwin = B + gbase + wslot;
+				const uint32_t *Bwin = beta_row(B, gbase + wslot);
 				for (int w = c.t; w < kCodeLen / 32; w += 8) {
 					const int base = (int)__ldg(&frozen[kSclTblMsgOff + w]);
 					if (base >= kDataBits) break;
 					uint32_t fr = ~__ldg(&frozen[w]);
 					if (!fr) continue;
-					const uint32_t x = Bwin[(size_t)w * 32];
+					const uint32_t x = Bwin[w];
 					uint32_t neg = 0; // channel hard decisions of the word (decode.cc:549-552)
 #pragma unroll
 					for (int q = 0; q < 8; ++q) neg |= neg_bits4(__ldg(&C4[w * 8 + q])) << (4 * q);

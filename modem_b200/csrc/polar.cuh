@@ -15,9 +15,11 @@ constexpr int kSclCtasPerSm = OFDMRX_SCL_CTAS;                      // 17 x 148 
 __host__ __device__ constexpr size_t scl_off4(int l) { return (size_t)32 * ((1u << (l - 2)) - 16u); } // float4 units
 constexpr size_t kSclWarpQuads = scl_off4(14);               // 130 560 float4 = 2.09 MB
 constexpr size_t kSclWarpFloats = kSclWarpQuads * 4;
-constexpr size_t kSclWarpWords = (size_t)2048 * 32;          // beta bits, [word][codeword * 8 + slot]
+constexpr size_t kSclWarpWords = (size_t)2048 * 32;          // beta bits, [codeword * 8 + slot][word]
 
-constexpr int kSclTblMsgOff = 2048, kSclTblOps = 4096; // word offsets inside SclParams::tbl
+// word offsets inside SclParams::tbl: frozen set | message bits before each word | CRC pieces (9 word bounds, pad, 8 x 32 matrix
+// columns: the CRC register advanced over the message bits that follow piece j) | op schedule
+constexpr int kSclTblMsgOff = 2048, kSclTblCrc = 4096, kSclTblOps = 4096 + 16 + 256;
 
 struct SclParams {
 	const float *llr;        // [frames][65536] channel LLRs after lengthen() (decode.cc:529)
@@ -27,8 +29,7 @@ struct SclParams {
 	const int *n_cw_ptr;
 	float *A;                // scratch: resident warps x kSclWarpFloats
 	uint32_t *B;             // scratch: resident warps x kSclWarpWords
-	const uint32_t *tbl[2];  // per code table, one array: frozen set (2048 words), number of non-frozen indices before each
-	                         // word (2048), op schedule (host_tables.cc) — one base pointer keeps the kernel's registers down
+	const uint32_t *tbl[2];  // per code table, one array (layout above) — one base pointer keeps the kernel's registers down
 	uint32_t *payload;       // [frames][1345] words pre-filled with the scrambler sequence
 	FrameState *st;
 	int *work;               // device counter (zeroed before the launch): next group of four codewords to hand out

@@ -179,7 +179,7 @@ struct Emu {
 		fmask = frozen[index / 32];
 		for (int t = 0; t < L; ++t) { W[t] = 0; rs5[t] = rs[5][t]; }
 		blk_node(5, 0);
-		for (int t = 0; t < L; ++t) B[(size_t)(index / 32) * L + t] = W[t]; // every lane writes its own slot (a superset of the representatives)
+		for (int t = 0; t < L; ++t) B[(size_t)(index / 32) * L + t] = is_rep(t) ? W[t] : 0xDEADBEEFu; // only the representatives' slots are written
 	}
 	// the d-1 fused F steps below the child (level l-1) just produced in the representatives' slots
 	void chain(int l, uint32_t depth)
@@ -272,7 +272,7 @@ struct Emu {
 						if (P[i] < 0.f) metric[t] -= P[i];
 				}
 				for (int w2 = 0; w2 < n / 32; ++w2)
-					for (int t = 0; t < L; ++t) B[(size_t)(index / 32 + w2) * L + t] = 0;
+					for (int t = 0; t < L; ++t) B[(size_t)(index / 32 + w2) * L + t] = is_rep(t) ? 0u : 0xDEADBEEFu;
 				for (int t = 0; t < L; ++t) ret[t] = t;
 				break;
 			case OP_R1: {
@@ -361,6 +361,13 @@ int host_schedule(uint32_t *out, int cap)
 	auto s = make_scl_schedule(f, kCodeOrder, kSclMaxFuse, true, true);
 	if (out) std::memcpy(out, s.data(), std::min<size_t>(cap, s.size()) * 4);
 	return (int)s.size();
+}
+// CRC pieces of the list decoder's epilogue (host_tables.cc: crc32_pieces): 16 + 256 words
+void host_crc_pieces(int table, uint32_t *out)
+{
+	auto f = make_frozen(kCodeOrder, table ? 64512 : kConsBits, kCrcBits);
+	auto p = crc32_pieces(f, kCrcBits);
+	std::memcpy(out, p.data(), p.size() * 4);
 }
 void host_bch_rows(uint32_t *out) { auto r = bch_generator_rows(); std::memcpy(out, r.data(), r.size() * 4); }
 void host_mls(int poly, int n, uint8_t *out) { auto m = mls_bits(poly, n); std::memcpy(out, m.data(), n); }

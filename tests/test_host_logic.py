@@ -112,6 +112,34 @@ def test_tables_match_oracle(oracle, hostlib):
     assert hostlib.host_crc16(323559855980806 << 9) == 0xE724
 
 
+def test_crc_pieces_join_to_the_bit_serial_crc(oracle, hostlib):
+    """The list decoder's epilogue computes CRC-32 in eight pieces and joins them with the matrices of crc32_pieces():
+    emulate that on random message bits and compare with the oracle's bit-serial CRC (decode.cc:534-537)."""
+    rng = np.random.default_rng(5)
+    for table in (0, 1):
+        fr = np.zeros(2048, np.uint32)
+        (hostlib.host_frozen_alt if table else hostlib.host_frozen)(_p(fr))
+        free = np.unpackbits((~fr).view(np.uint8), bitorder="little").reshape(2048, 32).astype(bool)
+        before = np.concatenate([[0], np.cumsum(free.sum(1))])
+        pc = np.zeros(16 + 256, np.uint32)
+        hostlib.host_crc_pieces(table, _p(pc))
+        bounds = pc[:9].astype(int)
+        assert bounds[0] == 0 and (np.diff(bounds) > 0).all() and before[bounds[8]] >= 43072 > before[bounds[8] - 1]
+        for trial in range(3):
+            code = rng.integers(0, 2, (2048, 32)).astype(np.uint8)
+            mesg = code[free][:43072]
+            want = oracle.lib().ref_crc32_bits(_p(np.ascontiguousarray(mesg)), 43072)
+            total = 0
+            for j in range(8):
+                bits = code[bounds[j]:bounds[j + 1]][free[bounds[j]:bounds[j + 1]]]
+                bits = bits[:max(0, 43072 - before[bounds[j]])]
+                reg = oracle.lib().ref_crc32_bits(_p(np.ascontiguousarray(bits)), len(bits))
+                for c in range(32):
+                    if (reg >> c) & 1:
+                        total ^= int(pc[16 + 32 * j + c])
+            assert total == want, (table, trial)
+
+
 def _noisy(oracle, seed, sigma):
     rng = np.random.default_rng(seed)
     pl = oracle.make_payload(500 + seed)
@@ -163,3 +191,38 @@ def test_emulator_ties_and_zero_llrs(oracle, hostlib):
         el, em = np.zeros((8, 65536), np.uint8), np.zeros(8, np.float32)
         hostlib.emu_polar_decode(_p(x), _p(el), _p(em), None)
         assert (el == lanes).all() and (em == met).all()
+
+
+def _scaled(oracle, seed, sigma, scale, mode=6):
+    rng = np.random.default_rng(seed)
+    pl = oracle.make_payload(500 + seed)
+    nb = 64800 if mode < 10 else 64512
+    code = np.zeros(nb, np.uint8)
+    oracle.lib().ref_payload_to_code(_p(pl), mode, _p(code))
+    y = (1.0 - 2.0 * code) + sigma * rng.standard_normal(nb)
+    return np.concatenate([scale * y, np.full(65536 - nb, 9000.0)]).astype(np.float32)
+
+
+def test_emulator_path_classes_and_rate1_attempts(oracle, hostlib):
+    """The kernel's class bookkeeping (one stored copy per distinct path, slots found through the lane maps) and its rate-1
+    attempts, over the regimes that matter: LLR scales at which the eight lanes stay copies of one path for the whole
+    codeword (clean channel), split late, or split at once; with and without random refusals of the attempts and leaf
+    shortcuts (what another codeword of the same warp can force).  The emulator poisons every slot that must not be read."""
+    hostlib.emu_set_fail_seed.argtypes = [C.c_uint32]
+    cases = [(0.0, 1000.0, 6), (0.05, 700.0, 6), (0.3, 60.0, 6), (0.5, 30.0, 6), (0.76, 300.0, 6), (0.7, 8.0, 6), (0.02, 900.0, 10), (0.65, 10.0, 10)]
+    try:
+        for seed, (sigma, scale, mode) in enumerate(cases):
+            llr = _scaled(oracle, seed, sigma, scale, mode)
+            best, lanes, met, payload, flips = oracle.polar_decode(llr, table=int(mode >= 10))
+            for fail in (0, 4242 + seed):
+                hostlib.emu_set_fail_seed(fail)
+                el, em, st = np.zeros((8, 65536), np.uint8), np.zeros(8, np.float32), np.zeros(16, np.int64)
+                (hostlib.emu_polar_decode_alt if mode >= 10 else hostlib.emu_polar_decode)(_p(llr), _p(el), _p(em), _p(st))
+                assert (el == lanes).all() and (em == met).all(), (sigma, scale, mode, fail)
+                classes = st[8:16]
+                if scale >= 700 and not fail:
+                    assert classes[0] == classes.sum() and st[3] == st[2] > 100   # one class throughout, every attempt succeeds
+                if sigma >= 0.7:
+                    assert classes[7] > 0.9 * classes.sum()                      # eight distinct paths almost from the start
+    finally:
+        hostlib.emu_set_fail_seed(0)
