@@ -24,7 +24,8 @@ extern "C" {
 /* sample formats: what DSP::ReadWAV<float> would deliver (decode.cc:294-301,576-581) */
 #define OFDMRX_FMT_S16_MONO 0 /* 1 channel, real: DC blocker + Hilbert are applied (decode.cc:298-299) */
 #define OFDMRX_FMT_S16_IQ 1   /* 2 channels, analytic I/Q, used as is */
-#define OFDMRX_FMT_F32_IQ 2   /* float2 I/Q already scaled to [-1,1) */
+#define OFDMRX_FMT_F32_IQ 2   /* float2 I/Q already scaled to [-1,1]: what ReadWAV delivers for 2 channels at any bit depth */
+#define OFDMRX_FMT_F32_MONO 3 /* float real samples in [-1,1] (8 / 24 / 32-bit WAVs at the reference's own precision); DC blocker + Hilbert applied */
 
 #define OFDMRX_MEM_HOST 0   /* samples/payload/status pointers are host memory (pinned memory makes the copies async) */
 #define OFDMRX_MEM_DEVICE 1 /* pointers are device memory on the handle's GPU */
@@ -58,7 +59,8 @@ typedef struct ofdmrx_frame_status {
 	float metrics[8];    /* final path metrics, ascending */
 	int32_t osd_visited;
 	int32_t ts_sweeps;   /* pair sweeps the Theil-Sen search took, summed over the rows (rows = the minimum) */
-	int32_t reserved;
+	int32_t det_overflow; /* 1: the window produced more correlator trigger edges than its detection list holds (sized at
+	                       * creation: one per symbol pitch of max_samples_per_frame + 8); detections beyond it were not examined */
 } ofdmrx_frame_status;
 
 /* stages whose outputs can be read back for parity tests (ofdmrx_get_taps); layouts are per window */

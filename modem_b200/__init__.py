@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(PKG, "libofdmrx.so")
 PAYLOAD_BYTES = 5380
 CODE_LEN = 65536
 FRAME_SAMPLES = 95200
-FMT_S16_MONO, FMT_S16_IQ, FMT_F32_IQ = 0, 1, 2
+FMT_S16_MONO, FMT_S16_IQ, FMT_F32_IQ, FMT_F32_MONO = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 ST_OK, ST_NO_SYNC, ST_OSD_FAIL, ST_HDR_CRC, ST_BAD_MODE, ST_BAD_CALL, ST_PAYLOAD_CRC, ST_UNSUPPORTED_MODE = range(8)
 STATUS_TEXT = {  # the reference's stderr strings (decode.cc:419,430,435,440,543)
@@ -39,7 +39,7 @@ STATUS_DTYPE = np.dtype([
     ("status", "<i4"), ("detections", "<i4"), ("t_fire", "<i4"), ("symbol_pos", "<i4"), ("sc_pos", "<i4"),
     ("index_max", "<i4"), ("shift", "<i4"), ("pos_err", "<i4"), ("timing_max", "<f4"), ("frac_cfo", "<f4"),
     ("cfo_rad", "<f4"), ("osd_unique", "<i4"), ("mode", "<i4"), ("md_lo", "<u4"), ("md_hi", "<u4"),
-    ("best_lane", "<i4"), ("flips", "<i4"), ("metrics", "<f4", (8,)), ("osd_visited", "<i4"), ("ts_sweeps", "<i4"), ("reserved", "<i4"),
+    ("best_lane", "<i4"), ("flips", "<i4"), ("metrics", "<f4", (8,)), ("osd_visited", "<i4"), ("ts_sweeps", "<i4"), ("det_overflow", "<i4"),
 ])
 assert STATUS_DTYPE.itemsize == 112
 
@@ -140,16 +140,19 @@ class Receiver:
 
     # ---- host buffers (numpy; pass pinned memory for asynchronous copies) ------------------------------------
     def decode(self, pcm, channels=1, n_samples=None, skip=0):
-        """pcm: int16 array [n_windows, stride*channels] (host).  Returns (payload uint8 [n,5380], status records)."""
-        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        """pcm: [n_windows, stride*channels] host array — int16 (16-bit WAV samples) or float32 (samples already scaled to
+        [-1, 1] as DSP::ReadWAV<float> delivers them for 8 / 24 / 32-bit files).  Returns (payload uint8 [n,5380], status)."""
+        pcm = np.asarray(pcm)
+        is_float = pcm.dtype.kind == "f"
+        pcm = np.ascontiguousarray(pcm, dtype=np.float32 if is_float else np.int16)
         if pcm.ndim == 1:
             pcm = pcm.reshape(1, -1)
         n, stride = pcm.shape[0], pcm.shape[1] // channels
         payload = np.empty((n, PAYLOAD_BYTES), np.uint8)
         status = np.zeros(n, STATUS_DTYPE)
         ns = None if n_samples is None else np.ascontiguousarray(n_samples, np.int32)
-        self.decode_raw(pcm.ctypes.data, MEM_HOST, FMT_S16_MONO if channels == 1 else FMT_S16_IQ, n, stride,
-                        ns, skip, payload.ctypes.data, status.ctypes.data, None)
+        fmt = (FMT_F32_MONO if channels == 1 else FMT_F32_IQ) if is_float else (FMT_S16_MONO if channels == 1 else FMT_S16_IQ)
+        self.decode_raw(pcm.ctypes.data, MEM_HOST, fmt, n, stride, ns, skip, payload.ctypes.data, status.ctypes.data, None)
         return payload, status
 
     # ---- raw pointers (device memory from torch: tensor.data_ptr(); stream: torch.cuda.current_stream().cuda_stream)
@@ -279,7 +282,8 @@ class Transmitter:
 
 
 def read_wav(path_or_bytes):
-    """Minimal RIFF/WAVE PCM reader (what DSP::ReadWAV delivers, decode.cc:576): returns (rate, channels, int16 [n, ch])."""
+    """Minimal RIFF/WAVE PCM reader (what DSP::ReadWAV<float> delivers, decode.cc:576): returns (rate, channels, samples [n, ch]) —
+    int16 for 16-bit files (the device scales them by 1/32767), float32 = v / (2^(bits-1) - 1) for 8 / 24 / 32 bits."""
     data = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray)) else open(path_or_bytes, "rb").read()
     if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
         raise ValueError("not a RIFF/WAVE file")
@@ -293,13 +297,17 @@ def read_wav(path_or_bytes):
                 raise ValueError("PCM WAV expected")
             ch, rate, bits = fmt[1], fmt[2], fmt[5]
             raw = data[o + 8:] if sz in (0, 0xFFFFFFFF) else data[o + 8:o + 8 + sz]
+            nb = bits // 8
+            if nb < 1 or nb > 4:
+                raise ValueError("8, 16, 24 or 32-bit PCM expected")
+            raw = raw[:len(raw) // (nb * ch) * nb * ch]
             if bits == 16:
-                a = np.frombuffer(raw[:len(raw) // (2 * ch) * 2 * ch], "<i2").astype(np.int16)
-            elif bits == 8:  # to the 16-bit grid of v/127 -> nearest v16/32767
-                a8 = np.frombuffer(raw[:len(raw) // ch * ch], np.uint8).astype(np.float32) - 128.0
-                a = np.rint(a8 / 127.0 * 32767.0).astype(np.int16)
+                a = np.frombuffer(raw, "<i2").astype(np.int16)
             else:
-                raise ValueError("only 8/16-bit PCM is supported by this driver")
+                b = np.frombuffer(raw, np.uint8).reshape(-1, nb).astype(np.int64)
+                v = sum(b[:, k] << (8 * k) for k in range(nb))
+                v = v - 128 if nb == 1 else np.where(v >= 1 << (bits - 1), v - (1 << bits), v)
+                a = (v.astype(np.float32) / np.float32((1 << (bits - 1)) - 1)).astype(np.float32)
             return rate, ch, a.reshape(-1, ch)
         o += 8 + sz + (sz & 1)
     raise ValueError("no data chunk")

@@ -244,7 +244,7 @@ constexpr size_t kAcqBufOff = (sizeof(AcqShared) + 15) & ~(size_t)15;
 
 template <int S>
 __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det,
-	const int32_t *det_count, int skip, FrameState *stv, int8_t *soft_out, AcquireConsts ac)
+	const int32_t *det_count, int det_cap, int skip, FrameState *stv, int8_t *soft_out, AcquireConsts ac)
 {
 	// geometry of this sample rate (shadows the 8 kHz constants of host_tables.h)
 	constexpr int kSymLen = Geo<S>::kSymLen, kHalf = Geo<S>::kHalf, kPitch = Geo<S>::kPitch, kGuardLen = Geo<S>::kGuardLen;
@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const cfx *a = iq + (size_t)f * iq_stride;
 	FrameState &st = stv[f];
-	const int nd = min(det_count[f], kMaxDet);
+	const int nd = min(det_count[f] & (kDetOverflowBit - 1), det_cap);
+	const int det_overflow = (det_count[f] & kDetOverflowBit) ? 1 : 0;
 	int status = ST_NO_SYNC, skip_left = skip, accepted = 0;
 	bool okay = false;
 	// results of the last accepted detection (CTA-uniform copies)
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 	unsigned long long r_md = 0;
 
 	for (int di = 0; di < nd; ++di) {
-		const Detection D = det[(size_t)f * kMaxDet + di];
+		const Detection D = det[(size_t)f * det_cap + di];
 		if (D.t_max < 0) continue;
 		// phase_max = arg(P[t_max - 80]),  P[t] = sum_{k<640} a[t-k-5119] conj(a[t-k-4479])   (decode.cc:86,91,101)
 		{
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kAcqThreads, 2) k_acquire(const cfx *iq, int64
 		st.best_lane = -1; st.flips = -1;
 		for (int k = 0; k < 8; ++k) st.metrics[k] = 0.f;
 		st.osd_visited = 0;
-		st.ts_sweeps = 0; st.reserved = 0;
+		st.ts_sweeps = 0; st.det_overflow = det_overflow;
 	}
 }
 
@@ -464,7 +465,7 @@ __global__ void k_compact(const FrameState *st, int n_frames, int *cw_list, int 
 } // namespace
 
 template <int S>
-static cudaError_t launch_acquire_t(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+static cudaError_t launch_acquire_t(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int det_cap, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s)
 {
 	static bool attr[64] = {};
@@ -472,16 +473,16 @@ static cudaError_t launch_acquire_t(const cfx *iq, int64_t iq_stride, int iq_len
 	if (first_use_on_device(attr)) {
 		cudaFuncSetAttribute(k_acquire<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	}
-	k_acquire<S><<<n_frames, kAcqThreads, smem, s>>>(iq, iq_stride, iq_len, det, det_count, skip, st, soft_out, ac);
+	k_acquire<S><<<n_frames, kAcqThreads, smem, s>>>(iq, iq_stride, iq_len, det, det_count, det_cap, skip, st, soft_out, ac);
 	return cudaGetLastError();
 }
 
-cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int det_cap, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
 	cudaError_t e = cudaSuccess;
-#define OFDMRX_CALL(R) e = launch_acquire_t<R>(iq, iq_stride, iq_len, det, det_count, skip, n_frames, st, soft_out, ac, s)
+#define OFDMRX_CALL(R) e = launch_acquire_t<R>(iq, iq_stride, iq_len, det, det_count, det_cap, skip, n_frames, st, soft_out, ac, s)
 	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
 #undef OFDMRX_CALL
 	return e;

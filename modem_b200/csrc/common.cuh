@@ -65,7 +65,7 @@ struct FrameState {
 	float metrics[8];
 	int32_t osd_visited;
 	int32_t ts_sweeps;    // pair sweeps the Theil-Sen search took, summed over the window's rows
-	int32_t reserved;
+	int32_t det_overflow; // 1: more trigger edges than the window's detection list holds (later detections were not examined)
 };
 static_assert(sizeof(FrameState) == 112, "FrameState layout");
 

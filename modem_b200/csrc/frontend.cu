@@ -22,8 +22,12 @@ constexpr unsigned FULL = 0xffffffffu;
 // across threads by a scan over (alpha, beta) pairs of the affine map y_out = alpha * y_in + beta.
 constexpr int kFeThreads = 256, kFePer = 8, kFeTile = kFeThreads * kFePer;
 
-template <int S>
-__global__ void __launch_bounds__(kFeThreads) k_frontend_mono(const int16_t *pcm, int64_t pcm_stride, const int32_t *n_samples,
+// ReadWAV scaling of a 16-bit sample (decode.cc:576: v / (2^15 - 1)); float input is what ReadWAV already delivered
+__device__ __forceinline__ float fe_sample(int16_t v) { return (float)v / 32767.f; }
+__device__ __forceinline__ float fe_sample(float v) { return v; }
+
+template <int S, typename SampleT>
+__global__ void __launch_bounds__(kFeThreads) k_frontend_mono(const SampleT *pcm, int64_t pcm_stride, const int32_t *n_samples,
 	int n_default, cfx *iq, int64_t iq_stride, int iq_len, FrontendConsts fc)
 {
 	// Hilbert<T>: the output at step t is formed before x[t] is pushed: centre tap y[t-1-mid], odd offsets up to mid-1,
@@ -35,7 +39,7 @@ __global__ void __launch_bounds__(kFeThreads) k_frontend_mono(const int16_t *pcm
 	const float dc_a = fc.dc_a, dc_b = fc.dc_b;
 	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = n_samples ? n_samples[f] : n_default;
-	const int16_t *src = pcm + (size_t)f * pcm_stride;
+	const SampleT *src = pcm + (size_t)f * pcm_stride;
 	cfx *dst = iq + (size_t)f * iq_stride;
 	if (tid < kHist) ybuf[tid] = 0.f;
 	if (tid == 0) { carry_y = 0.f; carry_x = 0.f; }
@@ -48,9 +52,9 @@ __global__ void __launch_bounds__(kFeThreads) k_frontend_mono(const int16_t *pcm
 #pragma unroll
 		for (int k = 0; k < kFePer; ++k) {
 			const int t = tb + k;
-			x[k] = t < n ? (float)src[t] / 32767.f : 0.f;
+			x[k] = t < n ? fe_sample(src[t]) : 0.f;
 		}
-		float xprev = tid == 0 ? carry_x : (tb - 1 < n ? (float)src[tb - 1] / 32767.f : 0.f);
+		float xprev = tid == 0 ? carry_x : (tb - 1 < n ? fe_sample(src[tb - 1]) : 0.f);
 		// local response with zero carry-in
 		float y = 0.f;
 #pragma unroll
@@ -261,12 +265,12 @@ constexpr int kDtWords = kDtTile / 32;
 
 template <int S>
 __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples,
-	int n_default, Detection *det, int32_t *det_count)
+	int n_default, Detection *det, int32_t *det_count, int det_cap, int32_t *edges)
 {
 	constexpr int kMatchLen = Geo<S>::kMatchLen, kMatchDel = Geo<S>::kMatchDel, kHalf = Geo<S>::kHalf, kGuardLen = Geo<S>::kGuardLen;
 	__shared__ uint32_t hi_m[kDtWords], lo_m[kDtWords];
-	__shared__ int ev_t[2 * kMaxDet + 2];
 	__shared__ int n_ev_s, state_s;
+	int32_t *ev_t = edges + (size_t)blockIdx.x * (2 * det_cap + 2); // rise / fall stream indices of this window, in order
 	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = (n_samples ? n_samples[f] : n_default) + 1; // steps t = 0..n_samples
 	const float *tm = timing + (size_t)f * timing_stride;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing,
 					uint32_t m = s ? lo_m[w] : hi_m[w];
 					while (m) {
 						const int b = __ffs(m) - 1;
-						if (ne < 2 * kMaxDet && lane == 0) ev_t[ne] = t0 + 32 * w + b;
+						if (ne < 2 * det_cap && lane == 0) ev_t[ne] = t0 + 32 * w + b;
 						++ne;
 						s ^= 1;
 						m = b == 31 ? 0u : (s ? lo_m[w] : hi_m[w]) & (0xfffffffeu << b);
@@ -309,7 +313,8 @@ __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing,
 		}
 		__syncthreads();
 	}
-	const int n_ev = min(n_ev_s, 2 * kMaxDet);
+	__syncthreads(); // the edge list (global memory, written by warp 0) is read by every warp below
+	const int n_ev = min(n_ev_s, 2 * det_cap);
 	const int n_seg = n_ev / 2; // (rise, fall) pairs; an unfinished segment never fires
 	// segments: edges alternate rise, fall, rise, ...  One warp per segment finds the first strict maximum.
 	for (int sgi = tid >> 5; sgi < n_seg; sgi += kDtThreads / 32) {
@@ -333,10 +338,10 @@ __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing,
 			d.timing_max = best;
 			// index_max: match_del at the maximum, +1 per later collect/process step, capped (decode.cc:99-105)
 			d.index_max = bi < 0 ? 0 : min(kMatchDel + (fall - bi), kHalf + kGuardLen + kMatchDel);
-			det[(size_t)f * kMaxDet + sgi] = d;
+			det[(size_t)f * det_cap + sgi] = d;
 		}
 	}
-	if (tid == 0) det_count[f] = n_seg;
+	if (tid == 0) det_count[f] = n_seg | (n_ev_s > 2 * det_cap ? kDetOverflowBit : 0);
 }
 
 } // namespace
@@ -346,7 +351,11 @@ cudaError_t launch_frontend(int rate, int format, const void *samples, int64_t s
 {
 	if (n_frames <= 0) return cudaSuccess;
 	if (format == 0) {
-#define OFDMRX_CALL(R) k_frontend_mono<R><<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc)
+#define OFDMRX_CALL(R) k_frontend_mono<R, int16_t><<<n_frames, kFeThreads, 0, s>>>((const int16_t *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc)
+		OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
+#undef OFDMRX_CALL
+	} else if (format == 3) {
+#define OFDMRX_CALL(R) k_frontend_mono<R, float><<<n_frames, kFeThreads, 0, s>>>((const float *)samples, stride, n_samples, n_default, iq, iq_stride, iq_len, fc)
 		OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
 #undef OFDMRX_CALL
 	} else if (format == 1) {
@@ -385,10 +394,10 @@ cudaError_t launch_sync_metric(int rate, const cfx *iq, int64_t iq_stride, int i
 }
 
 cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
-	Detection *det, int32_t *det_count, cudaStream_t s)
+	Detection *det, int32_t *det_count, int det_cap, int32_t *edges, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-#define OFDMRX_CALL(R) k_sync_detect<R><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count)
+#define OFDMRX_CALL(R) k_sync_detect<R><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count, det_cap, edges)
 	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
 #undef OFDMRX_CALL
 	return cudaGetLastError();

@@ -4,7 +4,10 @@
 
 namespace ofdmrx {
 
-constexpr int kMaxDet = 16; // Schmidl-Cox detections kept per window (more are dropped, documented in DESIGN.md)
+// Schmidl-Cox detections per window: the list is sized from the window length at handle creation (det_cap = one per symbol
+// pitch + 8, at least 16; decode.cc:390-448 has no bound).  A window that still produces more trigger edges than fit is
+// flagged (FrameState::det_overflow) instead of being silently truncated.
+constexpr int kDetOverflowBit = 1 << 30; // in det_count[]: the edge list of the window overflowed
 
 struct Detection {
 	int32_t t_fall;    // stream index of the falling-edge step (decode.cc:94)
@@ -25,13 +28,15 @@ struct AcquireConsts {
 	const uint32_t *bch_rows;  // 71 x 8 words, systematic generator (decode.cc:378-384)
 };
 
+// format: OFDMRX_FMT_* (0 int16 real, 1 int16 I/Q, 2 float2 I/Q, 3 float real)
 cudaError_t launch_frontend(int rate, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
 	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s);
 cudaError_t launch_sync_metric(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
 	float *timing, int64_t timing_stride, cudaStream_t s);
+// det: [n_frames][det_cap]; edges: scratch [n_frames][2 * det_cap + 2]
 cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
-	Detection *det, int32_t *det_count, cudaStream_t s);
-cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int skip,
+	Detection *det, int32_t *det_count, int det_cap, int32_t *edges, cudaStream_t s);
+cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int det_cap, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s);
 // three kernels: FFT + differential demodulation (cons_raw, phase errors yph), Theil-Sen per row (ts[row] = slope, yint,
 // precision), soft demapping (llr; cons = derotated constellation, optional)

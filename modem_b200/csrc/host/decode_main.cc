@@ -19,7 +19,9 @@ namespace {
 
 struct Wav {
 	int rate = 0, channels = 0, bits = 0;
-	std::vector<int16_t> pcm; // interleaved, converted to the 16-bit grid
+	std::vector<int16_t> pcm; // interleaved 16-bit samples (the device scales them like ReadWAV: v / 32767)
+	std::vector<float> flt;   // any other depth: interleaved floats, scaled exactly like DSP::ReadWAV<float> (decode.cc:576)
+	size_t count() const { return bits == 16 ? pcm.size() : flt.size(); }
 };
 
 bool parse_wav(const std::vector<uint8_t> &d, Wav &w)
@@ -41,16 +43,17 @@ bool parse_wav(const std::vector<uint8_t> &d, Wav &w)
 			int bytes = w.bits / 8;
 			if (bytes < 1 || bytes > 4) return false;
 			size_t cnt = n / bytes / w.channels * w.channels;
-			w.pcm.resize(cnt);
+			if (w.bits == 16) w.pcm.resize(cnt);
+			else w.flt.resize(cnt);
+			const float fac = (float)((1u << (w.bits - 1)) - 1u); // 2^(bits-1) - 1
 			for (size_t i = 0; i < cnt; ++i) {
 				const uint8_t *p = &d[o + 8 + i * bytes];
 				int32_t v = 0;
 				for (int b = 0; b < bytes; ++b) v |= (int32_t)p[b] << (8 * b);
 				if (bytes > 1 && bytes < 4 && (v & (1 << (8 * bytes - 1)))) v |= ~((1 << (8 * bytes)) - 1);
 				if (bytes == 1) v -= 128;
-				// ReadWAV scales by 1/(2^(bits-1)-1); the device ingests the 16-bit grid, so other depths are re-quantised
-				double x = (double)v / (double)((1u << (w.bits - 1)) - 1u);
-				w.pcm[i] = bytes == 2 ? (int16_t)v : (int16_t)std::lrint(std::max(-1.0, std::min(1.0, x)) * 32767.0);
+				if (w.bits == 16) w.pcm[i] = (int16_t)v;
+				else w.flt[i] = (float)v / fac;
 			}
 			return true;
 		}
@@ -98,7 +101,7 @@ int main(int argc, char **argv)
 		std::cerr << "Unsupported sample rate." << std::endl;
 		return 1;
 	}
-	const int64_t total = (int64_t)w.pcm.size() / w.channels;
+	const int64_t total = (int64_t)w.count() / w.channels;
 	const int64_t stride = batch ? batch_stride : std::max<int64_t>(total, 1);
 	const int n_frames = batch ? (int)(total / stride) : 1;
 	if (n_frames < 1) { std::cerr << "input shorter than one window" << std::endl; return 1; }
@@ -106,20 +109,26 @@ int main(int argc, char **argv)
 	int rc = ofdmrx_create(&h, 0, w.rate, std::min(n_frames, 4096), (int)stride);
 	if (rc) { std::cerr << "ofdmrx_create failed (" << rc << "): a B200 is required, there is no CPU path" << std::endl; return 1; }
 	std::vector<uint8_t> out((size_t)n_frames * OFDMRX_PAYLOAD_BYTES);
-	if (w.pcm.size() < (size_t)n_frames * stride * w.channels) w.pcm.resize((size_t)n_frames * stride * w.channels, 0);
+	const bool is16 = w.bits == 16;
+	if (is16 && w.pcm.size() < (size_t)n_frames * stride * w.channels) w.pcm.resize((size_t)n_frames * stride * w.channels, 0);
+	if (!is16 && w.flt.size() < (size_t)n_frames * stride * w.channels) w.flt.resize((size_t)n_frames * stride * w.channels, 0.f);
+	const void *samples = is16 ? (const void *)w.pcm.data() : (const void *)w.flt.data();
+	const int format = w.channels == 1 ? (is16 ? OFDMRX_FMT_S16_MONO : OFDMRX_FMT_F32_MONO) : (is16 ? OFDMRX_FMT_S16_IQ : OFDMRX_FMT_F32_IQ);
 	std::vector<int32_t> ns(n_frames, (int32_t)std::min<int64_t>(stride, total));
 	// The reference prints the header diagnostics of EVERY detection it consumes on the way to the SKIP-th one
 	// (decode.cc:390-448).  The library reports the last consumed detection of a call, so the driver asks for skip = 0, 1, ..
 	// SKIP in turn (the walk is deterministic: call k ends on detection k) and prints each new detection once.
 	std::vector<std::vector<ofdmrx_frame_status>> walk(skip + 1, std::vector<ofdmrx_frame_status>(n_frames));
 	for (int k = 0; k <= skip && !rc; ++k) {
-		rc = ofdmrx_decode_batch(h, w.pcm.data(), OFDMRX_MEM_HOST, w.channels == 1 ? OFDMRX_FMT_S16_MONO : OFDMRX_FMT_S16_IQ, n_frames, stride,
-			ns.data(), k, out.data(), walk[k].data(), nullptr);
+		rc = ofdmrx_decode_batch(h, samples, OFDMRX_MEM_HOST, format, n_frames, stride, ns.data(), k, out.data(), walk[k].data(), nullptr);
 		bool any = false;
 		for (int i = 0; i < n_frames; ++i) any |= walk[k][i].detections == k + 1;
 		if (!any) break; // no window holds a detection k: larger skips end the same way (a huge SKIP costs one extra call)
 	}
 	if (rc) { ofdmrx_destroy(h); std::cerr << "ofdmrx_decode_batch failed (" << rc << ")" << std::endl; return 1; }
+	for (int i = 0; i < n_frames; ++i)
+		if (walk[0][i].det_overflow) // (not a reference message: the reference's walk is unbounded, decode.cc:390-448)
+			std::cerr << "warning: window " << i << " holds more correlator detections than the library's list; later ones were not examined" << std::endl;
 	const int sym_len = 1280 * w.rate / 8000, pitch = sym_len + sym_len / 8;
 	for (int i = 0; i < n_frames; ++i) {
 		if (batch) std::cerr << "window " << i << ":" << std::endl;

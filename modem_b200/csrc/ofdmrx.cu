@@ -40,7 +40,8 @@ struct ofdmrx_handle {
 	cfx *d_iq = nullptr;
 	float *d_timing = nullptr;
 	Detection *d_det = nullptr;
-	int32_t *d_detcnt = nullptr;
+	int32_t *d_detcnt = nullptr, *d_edges = nullptr;
+	int det_cap = 16;
 	FrameState *d_st = nullptr;
 	int8_t *d_soft = nullptr;
 	cfx *d_cons_raw = nullptr, *d_cons = nullptr;
@@ -192,7 +193,9 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_nsamp, F);
 	if (!r) r = dev_alloc(&h->d_iq, F * (size_t)h->iq_len);
 	if (!r) r = dev_alloc(&h->d_timing, F * (size_t)h->iq_len);
-	if (!r) r = dev_alloc(&h->d_det, F * kMaxDet);
+	h->det_cap = std::max(16, max_samples / pitch + 8); // decode.cc:390-448 walks detections without bound: one per symbol pitch is generous
+	if (!r) r = dev_alloc(&h->d_det, F * h->det_cap);
+	if (!r) r = dev_alloc(&h->d_edges, F * (2 * (size_t)h->det_cap + 2));
 	if (!r) r = dev_alloc(&h->d_detcnt, F);
 	if (!r) r = dev_alloc(&h->d_st, F);
 	if (!r) r = dev_alloc(&h->d_soft, F * 256);
@@ -219,7 +222,7 @@ void ofdmrx_destroy(ofdmrx_t *h)
 	if (!h) return;
 	cudaSetDevice(h->device);
 	void *ptrs[] = {h->d_tbl[0], h->d_tbl[1], h->d_scr, h->d_bch, h->d_mls1, h->d_tw1280, h->d_tw640, h->d_kern, h->d_in,
-		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr, h->d_y,
+		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_edges, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr, h->d_y,
 		h->d_cwlist, h->d_ncw, h->d_work, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -292,10 +295,11 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 	if (record) cudaEventRecord(h->ev[1], s);
 	OFDMRX_CUDA_TRY(launch_sync_metric(h->rate, iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, s));
 	if (record) cudaEventRecord(h->ev[2], s);
-	OFDMRX_CUDA_TRY(launch_sync_detect(h->rate, timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, s));
+	OFDMRX_CUDA_TRY(launch_sync_detect(h->rate, timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * h->det_cap, h->d_detcnt + f0, h->det_cap,
+		h->d_edges + (size_t)f0 * (2 * h->det_cap + 2), s));
 	if (record) cudaEventRecord(h->ev[3], s);
 	AcquireConsts ac{h->d_tw1280, h->d_tw640, h->d_kern, h->d_mls1, h->d_bch};
-	OFDMRX_CUDA_TRY(launch_acquire(h->rate, iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * kMaxDet, h->d_detcnt + f0, skip, nf, h->d_st + f0,
+	OFDMRX_CUDA_TRY(launch_acquire(h->rate, iq, h->iq_len, h->iq_len, h->d_det + (size_t)f0 * h->det_cap, h->d_detcnt + f0, h->det_cap, skip, nf, h->d_st + f0,
 		h->d_soft + (size_t)f0 * 256, ac, s));
 	if (record) cudaEventRecord(h->ev[4], s);
 	OFDMRX_CUDA_TRY(launch_demod(h->rate, iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kMaxCons,
@@ -328,12 +332,11 @@ static int run_scl(ofdmrx_handle *h, int nf, cudaStream_t s)
 int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int format, int n_frames, int64_t stride,
 	const int32_t *n_samples, int skip, uint8_t *payload_out, ofdmrx_frame_status *status_out, void *stream)
 {
-	if (!h || !samples || n_frames < 0 || stride < 1 || format < 0 || format > 2 || skip < 0 || !payload_out) return -22;
-	if (format == OFDMRX_FMT_F32_IQ && mem_kind == OFDMRX_MEM_HOST) return -22; // float2 windows are accepted from device memory only
+	if (!h || !samples || n_frames < 0 || stride < 1 || format < 0 || format > 3 || skip < 0 || !payload_out) return -22;
 	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
 	cudaStream_t s = (cudaStream_t)stream;
 	h->launches = 0;
-	const size_t frame_bytes = (size_t)stride * (format == 0 ? 2 : format == 1 ? 4 : 8);
+	const size_t frame_bytes = (size_t)stride * (format == OFDMRX_FMT_S16_MONO ? 2 : format == OFDMRX_FMT_F32_IQ ? 8 : 4);
 	for (int f0 = 0; f0 < n_frames; f0 += h->max_frames) {
 		const int nf = std::min(h->max_frames, n_frames - f0);
 		const char *src = (const char *)samples + (size_t)f0 * frame_bytes;
@@ -351,7 +354,14 @@ int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int form
 		}
 		if (mem_kind == OFDMRX_MEM_HOST) {
 			// host windows: the H2D copy of slice k+1 runs on the copy stream while slice k goes through the front stages
-			if ((size_t)nf * frame_bytes > h->in_bytes) return -27;
+			if ((size_t)nf * frame_bytes > h->in_bytes) { // float2 windows need twice the staging the handle starts with
+				OFDMRX_CUDA_TRY(cudaStreamSynchronize(s));
+				OFDMRX_CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+				if (h->d_in) cudaFree(h->d_in);
+				h->d_in = nullptr; h->in_bytes = 0;
+				if (int r = dev_alloc((char **)&h->d_in, (size_t)h->max_frames * (size_t)h->max_samples * 8)) return r;
+				h->in_bytes = (size_t)h->max_frames * (size_t)h->max_samples * 8;
+			}
 			// (only the first slice's copy is exposed: many small slices keep that short)
 			const int slices = nf >= 8192 ? 16 : nf >= 4096 ? 8 : nf >= 1024 ? 4 : 1;
 			const int per = (nf + slices - 1) / slices;

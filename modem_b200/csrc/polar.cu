@@ -310,6 +310,15 @@ __device__ __forceinline__ void st_lvl(float4 *A, float4 *S5, int l, int gslot, 
 	else lvl_row(A, l, gslot)[q] = v;
 }
 
+// The big ops above the words are latency-bound streams (a warp holds four 128-bit loads per thread, the next turn's loads
+// cannot be hoisted over this turn's stores): the lines of the turn after next are requested early — into L1 for the
+// scratch rows (a few KB per warp), into L2 only for the TOP ops' channel values (8 KB per warp and turn).
+#ifndef OFDMRX_SCL_PREFETCH
+#define OFDMRX_SCL_PREFETCH 1 // bit 0: scratch rows into L1, bit 1: channel values into L2 (A/B switch)
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) { if (OFDMRX_SCL_PREFETCH & 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { if (OFDMRX_SCL_PREFETCH & 2) asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 // 3-bit-per-level stacks (lane maps, slots) in one 64-bit register
 __device__ __forceinline__ int stk_get(uint64_t s, int l) { return (int)((s >> (3 * l)) & 7ull); }
 __device__ __forceinline__ uint64_t stk_set(uint64_t s, int l, int v) { return (s & ~(7ull << (3 * l))) | ((uint64_t)v << (3 * l)); }
@@ -338,9 +347,14 @@ __device__ __forceinline__ void fused_op(float4 *A, float4 *S5, const uint32_t *
 			const float4 *P = lvl_row(A, l, gbase + ps);
 			const uint32_t *Bw = beta_row(const_cast<uint32_t *>(B), gbase + r) + iw;
 			// per turn two quad pairs: q and q + step when an F step is chained (its two operands), else q and q + 8
-			for (int q0 = j; q0 < step; q0 += chain ? 8 : 16) {
+			const int stride = chain ? 8 : 16;
+			for (int q0 = j; q0 < step; q0 += stride) {
 				const int q1 = q0 + second;
 				const bool two = chain || q1 < step;
+				if (q0 + 2 * stride < step) { // (implies a second pair two turns ahead as well)
+					const int qa = q0 + 2 * stride, qb = qa + second;
+					prefetch_l1(&P[qa]); prefetch_l1(&P[qa + hq]); prefetch_l1(&P[qb]); prefetch_l1(&P[qb + hq]);
+				}
 				const float4 pa0 = P[q0], pb0 = P[q0 + hq];
 				float4 pa1 = pa0, pb1 = pb0;
 				if (two) { pa1 = P[q1]; pb1 = P[q1 + hq]; }
@@ -384,6 +398,10 @@ __device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32
 #pragma unroll 1
 			for (int q0 = j; q0 < 1024; q0 += 8) {
 				float4 z[2];
+				if (q0 + 16 < 1024) {
+#pragma unroll
+					for (int kk = 0; kk < 16; ++kk) prefetch_l2(&C4[q0 + 16 + 1024 * kk]);
+				}
 #pragma unroll
 				for (int h = 0; h < 2; ++h) {
 					const int q = q0 + 1024 * h, wq = q >> 3;

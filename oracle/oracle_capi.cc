@@ -129,6 +129,33 @@ int ref_decode_pcm16(const int16_t *pcm, int64_t n_frames, int channels, int rat
 	return st;
 }
 
+// front-end stage taps of one window: iq_out float2[n_frames + 1], timing_out float[n_frames + 1] (one entry per stream step).
+// pcm16 != NULL: interleaved int16 converted like ReadWAV (v / 32767); else pcmf: interleaved floats as ReadWAV delivers them.
+int64_t ref_front_taps(const int16_t *pcm16, const float *pcmf, int64_t n_frames, int channels, int rate, float *iq_out, float *timing_out)
+{
+	std::vector<float> f((size_t)n_frames * channels);
+	for (size_t i = 0; i < f.size(); ++i) f[i] = pcm16 ? float(pcm16[i]) / 32767.f : pcmf[i];
+	Receiver rx(rate);
+	std::vector<cf> iq;
+	std::vector<float> timing;
+	rx.front_taps(f.data(), (size_t)n_frames, channels, iq, timing);
+	for (size_t i = 0; i < iq.size(); ++i) { iq_out[2 * i] = iq[i].re; iq_out[2 * i + 1] = iq[i].im; timing_out[i] = timing[i]; }
+	return (int64_t)iq.size();
+}
+// float samples as ReadWAV<float> delivers them (8 / 24 / 32-bit files): same receiver, no int16 conversion
+int ref_decode_f32(const float *pcm, int64_t n_frames, int channels, int rate, int skip, uint8_t *out, ref_taps_c *taps)
+{
+	Receiver rx(rate);
+	RxOptions opt;
+	uint8_t buf[kDataBytes];
+	std::memset(buf, 0, sizeof(buf));
+	int st = rx.run(buf, pcm, (size_t)n_frames, channels, skip, opt);
+	descramble(buf);
+	if (out) std::memcpy(out, buf, kDataBytes);
+	if (taps) fill_taps(taps, rx.taps);
+	return st;
+}
+
 // threaded batch: windows of `stride` frames; status[i], payload_out[i*5380]
 void ref_decode_batch_pcm16(const int16_t *pcm, int n, int64_t stride, const int32_t *n_samples, int channels, int rate, int skip,
 	int list_size, uint8_t *payload_out, int32_t *status, int nthreads)
@@ -225,6 +252,18 @@ int ref_polar_decode(const float *llr, int table, int list_size, int r0_max, uin
 		if (flips) *flips = best >= 0 ? fl : -1;
 	}
 	return best;
+}
+// list decoder on an arbitrary (small) code: n = 2^order LLRs, frozen = n/32 mask words (n >= 32) -> lanes[8][n] + metrics[8];
+// for cross-checks against an independent textbook implementation (tests/test_oracle_independent.py)
+void ref_polar_decode_any(int order, const uint32_t *frozen, const float *llr, int r0_max, uint8_t *lanes_out, float *metrics)
+{
+	PolarListDecoder<8> d(order, frozen);
+	d.r0_max = r0_max;
+	std::vector<std::vector<uint8_t>> lanes;
+	float m[8] = {0};
+	d.decode(llr, lanes, m);
+	const int n = 1 << order;
+	for (int k = 0; k < 8; ++k) { std::memcpy(lanes_out + (size_t)k * n, lanes[k].data(), n); metrics[k] = m[k]; }
 }
 int ref_taps_size() { return (int)sizeof(ref_taps_c); }
 

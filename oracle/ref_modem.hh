@@ -466,6 +466,30 @@ public:
 		return true;
 	}
 
+	// Stage taps of the streaming front end, one entry per stream step t = 0..n_frames (the reference takes one step past the
+	// end of the file before it notices, decode.cc:391-396): iq[t] = the sample next_sample() pushed at step t (decode.cc:294-301:
+	// BlockDC + Hilbert for one channel, I/Q as read for two), timing[t] = the matched-filter output of decode.cc:90 at that step.
+	// The trigger logic is left out: these are the inputs it sees.
+	void front_taps(const float *pcm, size_t n_frames, int channels, std::vector<cf> &iq, std::vector<float> &timing)
+	{
+		pcm_ = pcm; n_frames_ = n_frames; channels_ = channels; pos_ = 0; good_ = true; stream_count_ = 0;
+		blockdc_ = BlockDC();
+		blockdc_.samples(2 * (symbol_len_ + guard_len_));
+		hilbert_.reset(new Hilbert(filter_len_));
+		ring_.assign(2 * (size_t)buffer_len_, cf());
+		ring_pos_ = 0;
+		cor_ = SlidingSum<cf>(half_); pwr_ = SlidingSum<float>(2 * half_); match_ = SlidingSum<float>(match_len_);
+		iq.clear(); timing.clear();
+		while (good_) {
+			const cf *samples = next_sample();
+			iq.push_back(samples[buffer_len_ - 1]);
+			cf P = cor_(samples[search_pos_ + half_] * conj(samples[search_pos_ + 2 * half_]));
+			float R = 0.5f * pwr_(norm(samples[search_pos_ + 2 * half_]));
+			R = std::max(R, float(0.0001 * half_));
+			timing.push_back(match_(norm(P) / (R * R)));
+		}
+	}
+
 	// Decoder::Decoder (decode.cc:375-556).  pcm: interleaved float frames as ReadWAV delivers them.
 	// Returns Status; out (5380 B) is written only on ST_OK and is NOT yet de-scrambled (decode.cc:613-615 does that in main).
 	int run(uint8_t *out, const float *pcm, size_t n_frames, int channels, int skip_count, const RxOptions &opt = RxOptions())

@@ -28,14 +28,16 @@ void ofdmrx_destroy(ofdmrx_t *h) { delete h; }
 int ofdmrx_decode_batch(ofdmrx_t *h, const void *samples, int mem_kind, int format, int n_frames, int64_t stride, const int32_t *n_samples,
 	int skip, uint8_t *payload_out, ofdmrx_frame_status *st, void *)
 {
-	if (mem_kind != OFDMRX_MEM_HOST || format > OFDMRX_FMT_S16_IQ) return -22;
-	const int ch = format == OFDMRX_FMT_S16_MONO ? 1 : 2;
+	if (mem_kind != OFDMRX_MEM_HOST || format < 0 || format > OFDMRX_FMT_F32_MONO) return -22;
+	const int ch = (format == OFDMRX_FMT_S16_MONO || format == OFDMRX_FMT_F32_MONO) ? 1 : 2;
+	const bool is_float = format == OFDMRX_FMT_F32_IQ || format == OFDMRX_FMT_F32_MONO;
 	h->ts.assign(n_frames, std::vector<float>(126 * 3, 0.f));
 	for (int i = 0; i < n_frames; ++i) {
 		const int16_t *pcm = (const int16_t *)samples + (size_t)i * stride * ch;
+		const float *flt = (const float *)samples + (size_t)i * stride * ch;
 		const int64_t n = n_samples ? n_samples[i] : stride;
 		std::vector<float> f((size_t)n * ch);
-		for (size_t k = 0; k < f.size(); ++k) f[k] = float(pcm[k]) / 32767.f;
+		for (size_t k = 0; k < f.size(); ++k) f[k] = is_float ? flt[k] : float(pcm[k]) / 32767.f;
 		ref::Receiver rx(h->rate);
 		uint8_t buf[ref::kDataBytes];
 		std::memset(buf, 0, sizeof(buf));

@@ -52,6 +52,10 @@ def lib(fast=False):
     L.ref_decode_pcm16.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_decode_batch_pcm16.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_int]
+    L.ref_front_taps.restype = C.c_int64
+    L.ref_front_taps.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_decode_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_polar_decode_any.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_mls.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.ref_crc16_u64.restype = C.c_uint32
     L.ref_crc16_u64.argtypes = [C.c_uint64]
@@ -133,6 +137,29 @@ def decode(pcm, channels=1, rate=8000, skip=0, list_size=8, r0_max=1 << 16, osd_
     st = lib(fast).ref_decode_pcm16(_p(pcm), n, channels, rate, skip, list_size, r0_max, int(osd_literal), _p(out),
                                     C.byref(taps) if taps is not None else None)
     return st, out, taps
+
+
+def decode_f32(samples, channels=1, rate=8000, skip=0):
+    """float samples as DSP::ReadWAV<float> delivers them (any bit depth) -> (status, payload, taps)"""
+    samples = np.ascontiguousarray(samples, np.float32)
+    out = np.zeros(DATA_BYTES, np.uint8)
+    taps = Taps()
+    st = lib().ref_decode_f32(_p(samples), samples.size // channels, channels, rate, skip, _p(out), C.byref(taps))
+    return st, out, taps
+
+
+def front_taps(pcm, channels=1, rate=8000):
+    """Stream taps of the front end for one window (int16 or float32 samples): (iq complex64 [n + 1], timing float32 [n + 1]),
+    one entry per stream step — what next_sample() pushed (decode.cc:294-301) and the timing metric of decode.cc:90."""
+    pcm = np.asarray(pcm)
+    is_float = pcm.dtype.kind == "f"
+    pcm = np.ascontiguousarray(pcm, np.float32 if is_float else np.int16)
+    n = pcm.size // channels
+    iq = np.zeros(n + 1, np.complex64)
+    timing = np.zeros(n + 1, np.float32)
+    got = lib().ref_front_taps(None if is_float else _p(pcm), _p(pcm) if is_float else None, n, channels, rate, _p(iq), _p(timing))
+    assert got == n + 1, (got, n)
+    return iq, timing
 
 
 def decode_batch(pcm, n_samples=None, channels=1, rate=8000, skip=0, list_size=8, nthreads=None, fast=False):

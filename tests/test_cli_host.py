@@ -62,21 +62,17 @@ def test_quick_start_skip_walk_and_failures(cli, oracle, tmp_path):
 
 
 @needs_reference
-@pytest.mark.parametrize("rate,mode,bits", [(8000, 13, 16), (16000, 9, 16), (48000, 10, 16), (8000, 6, 8), (8000, 7, 24)])
+@pytest.mark.parametrize("rate,mode,bits", [(8000, 13, 16), (16000, 9, 16), (48000, 10, 16), (8000, 6, 8), (8000, 7, 24), (8000, 6, 32)])
 def test_modes_rates_and_sample_widths(cli, oracle, tmp_path, rate, mode, bits):
-    """8- and 24-bit files go through the reference's own encoder (Makefile:14 uses 8 bits); the driver re-quantises them to
-    the 16-bit grid the device ingests, the reference reads them as they are — the payload is the same, the floats may not be"""
+    """8- and 24-bit files go through the reference's own encoder (Makefile:14 uses 8 bits).  The driver hands 16-bit samples to
+    the library as they are and every other depth as floats scaled like DSP::ReadWAV<float> (v / (2^(bits-1) - 1), decode.cc:576),
+    so payload AND every stderr float equal the reference's own main() at all depths."""
     pl = oracle.make_payload(rate + mode + bits)
     (tmp_path / "in.dat").write_bytes(pl.tobytes())
     wav = tmp_path / "e.wav"
     subprocess.run([os.path.join(T.REF, "encode"), str(wav), str(rate), str(bits), "1", "2000", str(mode), "CALLSIGN", str(tmp_path / "in.dat")], check=True, capture_output=True)
-    if bits == 16:
-        out, err = run_both(cli, tmp_path, wav)
-    else:
-        p = subprocess.run([cli, str(tmp_path / "p.dat"), str(wav)], capture_output=True)
-        assert p.returncode == 0 and b"bit flips:" in p.stderr and ("oper mode: %d" % mode).encode() in p.stderr
-        out = (tmp_path / "p.dat").read_bytes()
-    assert out == pl.tobytes()
+    out, err = run_both(cli, tmp_path, wav)
+    assert out == pl.tobytes() and b"bit flips:" in err and ("oper mode: %d" % mode).encode() in err
 
 
 @needs_reference

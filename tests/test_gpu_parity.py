@@ -8,11 +8,21 @@ pytestmark = pytest.mark.gpu
 
 # tolerances of the fp32 front end (FFT twiddle/ordering, atan2f/sincosf implementations, summation order differ
 # between the device and the scalar oracle):
-TOL_CONS = 2e-3       # |cons_gpu - cons_ref|, constellation points have |.| = 1
+# The values of SURVEY.md §8(c) (cons 1e-3, precision 1e-3, LLR 2e-3); profiles/r2_parity_histogram.md holds the measured
+# distributions they were checked against (clean: cons 1e-6, LLR 2e-5; README chain: cons 7e-4, precision 8e-4).
+TOL_CONS = 1e-3       # |cons_gpu - cons_ref|, constellation points have |.| = 1
 TOL_SLOPE_REL = 2e-2  # Theil-Sen slope relative to max|slope| of the frame (the median can move to a neighbouring quotient)
-TOL_YINT = 2e-3       # rad
-TOL_PRECISION = 2e-3  # relative
-TOL_LLR = 1e-2        # max |llr_gpu - llr_ref| / mean |llr_ref|
+TOL_YINT = 2e-3       # rad (an intercept that moves to the neighbouring order statistic: measured max 1.3e-3)
+TOL_PRECISION = 1e-3  # relative
+TOL_LLR = 2e-3        # |llr_gpu - llr_ref| / mean |llr_ref| for 99.9 % of the 65536 values of a window ...
+TOL_LLR_MAX = 1e-2    # ... and for all of them: a row whose intercept is the neighbouring order statistic turns by ~1e-3 rad,
+                      # which moves its largest LLRs by up to 7e-3 of the mean (measured); everything else stays below 2e-4
+
+
+def llr_close(got, ref):
+    d = np.abs(got - ref) / np.abs(ref[:64512]).mean()
+    assert np.quantile(d, 0.999) < TOL_LLR and d.max() < TOL_LLR_MAX, (float(np.quantile(d, 0.999)), float(d.max()))
+
 
 
 def _noisy_llr(oracle, seed, sigma):
@@ -160,7 +170,7 @@ def _compare_frames(rx, oracle, pcm, channels, sent, strict_payload=True):
             assert np.abs(ts[:, 1] - oracle.taps_np(tp, "yint")).max() < TOL_YINT
             assert (np.abs(ts[:, 2] - oracle.taps_np(tp, "precision")) / oracle.taps_np(tp, "precision")).max() < TOL_PRECISION
             ollr = oracle.taps_np(tp, "llr")
-            assert np.abs(rx.taps(M.TAP_LLR, i, 1)[0] - ollr).max() / np.abs(ollr[:64512]).mean() < TOL_LLR
+            llr_close(rx.taps(M.TAP_LLR, i, 1)[0], ollr)
         if ost == 0:
             assert (payload[i] == opay).all() and (payload[i] == sent[i]).all()
             assert s["best_lane"] == tp.best_lane
