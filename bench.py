@@ -34,6 +34,8 @@ FRAME_SAMPLES = 95200
 ALG_BYTES_SCL = 65536 * 4 + 5380            # per window: channel LLRs in, payload out
 ALG_FLOP_SCL = 25690112                     # L*(N/2*log2N)*6 + L*N at L = 8
 ALG_BYTES_CORR = FRAME_SAMPLES * 8          # one float2 read per IQ sample
+ALG_BYTES_TS = 50 * 432 * 4 + 50 * 3 * 4    # per window: the phase errors of 50 rows in, (slope, intercept, sweeps) per row out
+ALG_FLOP_TS = 50 * 2 * 93096                # one subtraction and one division per pairwise slope
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal CUDA-core peak; MEASURED_PEAKS.json has no FP32 figure
 
 
@@ -55,7 +57,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -92,13 +94,15 @@ def make_batch(n, seed0, threads):
 
 
 def run_reference(args, rank, world, json_out):
-    """CPU arm: the oracle port of decode.cc on the box's host cores (the reference itself cannot be built: DESIGN.md)."""
+    """CPU arm: the oracle port of decode.cc on the box's host cores (the reference itself cannot be built: DESIGN.md).
+    Every step decodes 8 x cores windows (>= 8 x nproc frames, so the thread pool's ramp does not weigh), all
+    cores busy; one extra single-core pass over a few windows gives the per-core figure."""
     if rank != 0:
         return
     import oracle_lib as O
     O.build()
     cores = os.cpu_count() or 1
-    sample = max(64, min(2 * cores, 512))
+    sample = max(64, 8 * cores)
     pcm, ns, sent = make_batch(sample, 424242, cores)
     times = []
     for it in range(args.warmup + args.steps):
@@ -111,13 +115,18 @@ def run_reference(args, rank, world, json_out):
     total = sum(times)
     fps = sample * len(times) / total
     val = fps * PAYLOAD_BITS / 1e6
+    n1 = 8
+    t = time.perf_counter()
+    O.decode_batch(pcm[:n1], nthreads=1, fast=True)
+    fps1 = n1 / (time.perf_counter() - t)
     line = {
         "impl": "reference", "metric": "decoded_payload_mbit_per_s", "value": val, "unit": "Mbit/s", "frames_per_s": fps,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, sample_note="bounded sample of %d windows per step on the host cores" % sample),
+        "config": workload_config(args, sample_note="bounded sample of %d windows (8 x %d cores) per step on the host cores" % (sample, cores)),
         "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": cores, "kind": "port",
-                         "sample": "%d clean mode-6 windows per step, %d steps, %d threads, oracle port built -Ofast -march=native" % (sample, len(times), cores)},
+                         "sample": "%d clean mode-6 windows per step, %d steps, %d threads, oracle port built -Ofast -march=native" % (sample, len(times), cores),
+                         "single_core_frames_per_s": fps1, "single_core_sample": "%d windows, one thread" % n1},
         "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -264,44 +273,77 @@ def main():
                 e2e_ms, e2e_mode = float(dt.item()), "two handles on two host threads (H2D of one batch overlaps the decode of the other)"
         except M.OfdmrxError as e:   # e.g. not enough device memory for a second handle
             e2e_mode += " (pipelined variant unavailable: %s)" % e
-    # secondary number: the same batch size on BASELINE configs[2]-type windows (README impairment chain, 2-channel int16);
-    # 148 distinct impaired frames (the CPU resampler is slow) repeated to fill the batch, device-resident, device-timed
-    cfg3 = None
-    if os.environ.get("BENCH_CONFIG3", "1") != "0":
-        import oracle_lib as O
-        uniq = 148
-        imp = O.impair(multipath=True, cfo_hz=234.567, sfo_ppm=147, awgn_db=-30, seed=4242 + rank)
-        if os.environ.get("BENCH_STIM", "cpu") == "device":
-            # every window distinct: payloads, noise and all generated on the GPU (include/ofdmtx.h), nothing replicated
-            uniq = n
-            isent = np.random.default_rng(777 + rank).integers(0, 256, (n, M.PAYLOAD_BYTES), dtype=np.uint8)
-            tx = M.Transmitter(device=local_rank, max_windows=min(n, 2048))
-            c3_stride = tx.window_samples(6)
-            dev_imp = torch.zeros((n, c3_stride * 2), dtype=torch.int16, device="cuda")
-            tx.encode_raw(isent.ctypes.data, M.MEM_HOST, n, 6, int(M.load().ofdmtx_call_sign(b"CALLSIGN")), 2000,
-                          M.impairments(multipath=True, cfo_hz=234.567, sfo_ppm=147.0, awgn_db=-30.0, seed=4242 + 1000003 * rank),
-                          dev_imp.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, c3_stride, None, stream)
-            torch.cuda.synchronize()
-            tx.close()
-            sel = torch.arange(n)
-        else:
-            ipcm, ins, isent = O.encode_batch(uniq, seed0=777 + 1000 * rank, channels=2, imp=imp, nthreads=max(1, cores // world))
-            c3_stride = ipcm.shape[1] // 2
-            sel = torch.arange(n) % uniq
-            dev_imp = torch.from_numpy(ipcm)[sel].cuda()
+    # secondary numbers on impaired windows, every window distinct and generated on the GPU (include/ofdmtx.h: the reference
+    # transmitter + the README.md:49 impairment chain, batched), device-resident and device-timed like `value`:
+    #   config3  BASELINE configs[2]: the README chain on every window, same batch size as the headline
+    #   config5  BASELINE configs[4]: this GPU's shard (1 M / 8 = 125 000 frames) of a batch with MIXED impairments, in
+    #            chunks of `n` windows, one impairment class per chunk, per-window noise from (seed, window)
+    cfg3 = cfg5 = None
+    cs = int(M.load().ofdmtx_call_sign(b"CALLSIGN"))
 
-        def step_cfg3():
-            rx.decode_raw(dev_imp.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, n, c3_stride, None, 0, payload.data_ptr(), status.data_ptr(), stream)
+    def gen_chunk(tx, count, imp, seed, out_pcm, out_sent):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        out_sent[:count] = torch.randint(0, 256, (count, M.PAYLOAD_BYTES), dtype=torch.uint8, device="cuda", generator=g)
+        tx.encode_raw(out_sent.data_ptr(), M.MEM_DEVICE, count, 6, cs, 2000, imp, out_pcm.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ,
+                      out_pcm.shape[1] // 2, None, stream)
+        torch.cuda.synchronize()
 
-        for _ in range(2):
-            step_cfg3()
-        c3_ms, _ = timed(step_cfg3, args.steps)
-        c3_stage, _ = rx.stage_times()
-        c3_err = int(np.unpackbits(payload.cpu().numpy() ^ isent[sel.numpy()], axis=1).sum())
-        cfg3 = {"workload": "README chain (multipath + CFO 234.567 Hz + SFO 147 ppm + AWGN -30 dB), %d windows per GPU from %d distinct frames" % (n, uniq),
-                "frames_per_s": n * world / (c3_ms / args.steps / 1e3), "ms_per_step": c3_ms / args.steps,
-                "payload_bit_errors_vs_sent": c3_err, "stage_ms": c3_stage}
-        del dev_imp
+    if os.environ.get("BENCH_CONFIG3", "1") != "0" or os.environ.get("BENCH_CONFIG5", "1") != "0":
+        tx = M.Transmitter(device=local_rank, max_windows=min(n, 2048))
+        c_stride = tx.window_samples(6) + 64     # slack: a negative sampling-frequency offset stretches the stream
+        rx3 = M.Receiver(device=local_rank, max_frames=n, max_samples=c_stride)
+        dev_imp = torch.zeros((n, c_stride * 2), dtype=torch.int16, device="cuda")
+        dev_sent = torch.empty((n, M.PAYLOAD_BYTES), dtype=torch.uint8, device="cuda")
+
+        def step_imp():
+            rx3.decode_raw(dev_imp.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, n, c_stride, None, 0, payload.data_ptr(), status.data_ptr(), stream)
+
+        def errors_now():
+            stt = status.cpu().numpy().view(M.STATUS_DTYPE).reshape(-1)
+            okm = torch.from_numpy(stt["status"] == 0).cuda()
+            bad = int(np.unpackbits((payload ^ dev_sent)[okm].cpu().numpy()).sum())
+            return bad, int((stt["status"] != 0).sum())
+
+        if os.environ.get("BENCH_CONFIG3", "1") != "0":
+            gen_chunk(tx, n, M.impairments(multipath=True, cfo_hz=234.567, sfo_ppm=147.0, awgn_db=-30.0, seed=4242 + 1000003 * rank), 777 + rank, dev_imp, dev_sent)
+            for _ in range(2):
+                step_imp()
+            c3_ms, _ = timed(step_imp, args.steps)
+            c3_stage, _ = rx3.stage_times()
+            c3_err, c3_fail = errors_now()
+            cfg3 = {"workload": "BASELINE configs[2]: README chain (multipath + CFO 234.567 Hz + SFO 147 ppm + AWGN -30 dB) on %d distinct device-generated windows per GPU" % n,
+                    "frames_per_s": n * world / (c3_ms / args.steps / 1e3), "ms_per_step": c3_ms / args.steps,
+                    "payload_bit_errors_vs_sent": c3_err, "frames_failed": c3_fail, "stage_ms": c3_stage}
+        if os.environ.get("BENCH_CONFIG5", "1") != "0":
+            shard = int(os.environ.get("BENCH_CONFIG5_FRAMES", "125000"))
+            classes = [("clean", None), ("awgn -25", dict(awgn_db=-25.0)), ("awgn -18", dict(awgn_db=-18.0)), ("cfo -180.5 Hz", dict(cfo_hz=-180.5)),
+                       ("multipath", dict(multipath=True)), ("multipath + cfo + awgn -24", dict(multipath=True, cfo_hz=77.7, awgn_db=-24.0)),
+                       ("sfo -120 ppm + awgn -28", dict(sfo_ppm=-120.0, awgn_db=-28.0)), ("README chain", dict(multipath=True, cfo_hz=234.567, sfo_ppm=147.0, awgn_db=-30.0))]
+            done, ms_total, err5, fail5, per_class = 0, 0.0, 0, 0, {}
+            k = 0
+            while done < shard:
+                name, kw = classes[k % len(classes)]
+                cnt = min(n, shard - done)
+                imp = M.impairments(seed=90000 + 1000003 * rank + k, **kw) if kw else None
+                if cnt < n:
+                    dev_imp.zero_()
+                gen_chunk(tx, cnt, imp, 5000 + 97 * k + rank, dev_imp, dev_sent)
+                step_imp()                                   # warm the caches / clocks of this class
+                ms, _ = timed(step_imp, 1)
+                e, f = errors_now()
+                if cnt < n:                                  # the zero-padded tail of the last chunk holds no frames
+                    f -= n - cnt
+                ms_total += ms * cnt / n
+                err5 += e; fail5 += f
+                per_class.setdefault(name, [0, 0.0])
+                per_class[name][0] += cnt; per_class[name][1] += ms * cnt / n
+                done += cnt; k += 1
+            cfg5 = {"workload": "BASELINE configs[4]: 1 M mode-6 frames with mixed impairments sharded over 8 GPUs — this run: %d frames per GPU in chunks of %d, one impairment class per chunk (%s), all windows distinct and device-generated" % (shard, n, "; ".join(c[0] for c in classes)),
+                    "frames_per_gpu": shard, "frames_per_s": shard * world / (ms_total / 1e3), "decode_ms_total": ms_total,
+                    "payload_bit_errors_vs_sent": err5, "frames_failed": fail5,
+                    "frames_per_s_by_class": {kk: v[0] / (v[1] / 1e3) for kk, v in per_class.items()}}
+        tx.close(); rx3.close()
+        del dev_imp, dev_sent
     if world > 1:
         tot = torch.tensor([bit_errors + e2e_err, frames_ok], device="cuda", dtype=torch.int64)
         dist.all_reduce(tot)
@@ -311,8 +353,45 @@ def main():
         fps = n * world / (ms_step / 1e3)
         e2e_fps = n * world / (e2e_ms / args.steps / 1e3)
         hbm_peak, peak_src = measured_peaks()
-        scl_s = stage_ms["polar_scl"] / 1e3
-        corr_s = stage_ms["sync_metric"] / 1e3
+        try:
+            fp32_peak, fp32_src = rx.measure_fp32(), "measured in this run (ofdmrx_measure_fp32: FMA kernel over all SMs)"
+        except M.OfdmrxError:
+            fp32_peak, fp32_src = FP32_PEAK_TFLOPS, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
+        traffic = {}
+        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof))
+            except (ValueError, OSError):
+                traffic = {}
+        step_sum = sum(stage_ms[k] for k in ("frontend", "sync_metric", "sync_detect", "acquire", "demod", "compact_init", "polar_scl"))
+
+        def roof(kernel, stage, alg_bytes, flop=None, note=None):
+            sec = stage_ms[stage] / 1e3
+            r = {"kernel": kernel, "bound": "hbm", "achieved": n_chunk * alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": n_chunk * alg_bytes / sec / 1e9 / hbm_peak, "traffic": traffic.get(kernel + "_dram_bytes_per_window"),
+                 "peak_source": peak_src, "kernel_ms": stage_ms[stage], "share_of_step": stage_ms[stage] / step_sum,
+                 "algorithmic_bytes_per_window": alg_bytes}
+            if r["traffic"] is not None:
+                r["traffic_note"] = "per window, from the committed ncu --set full capture (profiles/)"
+                r["dram_throughput_frac"] = n_chunk * r["traffic"] / sec / 1e9 / hbm_peak
+            if flop:
+                r["fp32"] = {"achieved_tflops": n_chunk * flop / sec / 1e12, "peak_tflops": fp32_peak, "frac": n_chunk * flop / sec / 1e12 / fp32_peak,
+                             "peak_source": fp32_src, "flop_per_window": flop}
+            if note:
+                r["note"] = note
+            return r
+
+        roofs = {
+            "k_polar_scl": roof("k_polar_scl", "polar_scl", ALG_BYTES_SCL, ALG_FLOP_SCL,
+                                "SURVEY 8(d) bounds the list decoder by the FP32 peak: see `fp32` (algorithmic flop at L = 8; on clean frames the "
+                                "kernel computes each distinct path once, so it executes ~1/8 of them) — the HBM view is beside it"),
+            "k_theil_sen": roof("k_theil_sen", "theil_sen", ALG_BYTES_TS, ALG_FLOP_TS,
+                                "neither HBM- nor FP32-bound: an exact order statistic of 93 096 quotients per row by compare/search steps in shared "
+                                "memory (issue-bound, IPC 2.2 of 4; profiles/)"),
+            "k_sync_metric": roof("k_sync_metric", "sync_metric", ALG_BYTES_CORR),
+        }
+        dominant = max(roofs, key=lambda k: roofs[k]["kernel_ms"])
         line = {
             "metric": "decoded_payload_mbit_per_s", "value": fps * PAYLOAD_BITS / 1e6, "unit": "Mbit/s", "frames_per_s": fps,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -324,33 +403,16 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "mode": e2e_mode, "serial_ms_per_step": e2e_serial_ms / args.steps},
             "gpu_launches": launches * args.steps,
             "parity": {"payload_bit_errors_vs_sent": bit_errors, "frames_ok": frames_ok, "frames": n * world},
-            # dominant kernel = polar list decoder (k_polar_scl): share of the step from CUDA events on the launching stream
-            "roofline": {"kernel": "k_polar_scl", "bound": "hbm", "achieved": n_chunk * ALG_BYTES_SCL / scl_s / 1e9, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": n_chunk * ALG_BYTES_SCL / scl_s / 1e9 / hbm_peak, "traffic": None,
-                         "peak_source": peak_src, "kernel_ms": stage_ms["polar_scl"], "share_of_step": stage_ms["polar_scl"] / sum(stage_ms.values()),
-                         "algorithmic_bytes_per_window": ALG_BYTES_SCL,
-                         "fp32": {"achieved_tflops": n_chunk * ALG_FLOP_SCL / scl_s / 1e12, "peak_tflops": FP32_PEAK_TFLOPS,
-                                  "frac": n_chunk * ALG_FLOP_SCL / scl_s / 1e12 / FP32_PEAK_TFLOPS,
-                                  "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (no measured FP32 peak on file)",
-                                  "flop_per_window": ALG_FLOP_SCL}},
-            "roofline_correlator": {"kernel": "k_sync_metric", "bound": "hbm", "achieved": n_chunk * ALG_BYTES_CORR / corr_s / 1e9, "peak": hbm_peak,
-                                    "unit": "GB/s", "frac": n_chunk * ALG_BYTES_CORR / corr_s / 1e9 / hbm_peak, "traffic": None,
-                                    "kernel_ms": stage_ms["sync_metric"], "algorithmic_bytes_per_window": ALG_BYTES_CORR},
-            "stage_ms": stage_ms, "stimulus_gen_s": gen_s, "config3": cfg3,
+            # the kernel with the largest share of the step (CUDA events on the launching stream), then the two the north star names
+            "roofline": roofs[dominant],
+            "roofline_scl": roofs["k_polar_scl"],
+            "roofline_correlator": roofs["k_sync_metric"],
+            "stage_ms": stage_ms, "stimulus_gen_s": gen_s, "config3": cfg3, "config5": cfg5,
         }
-        prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(prof):
-            try:
-                t = json.load(open(prof))
-                line["roofline"]["traffic"] = t.get("k_polar_scl_dram_bytes_per_window")
-                line["roofline_correlator"]["traffic"] = t.get("k_sync_metric_dram_bytes_per_window")
-                line["roofline"]["traffic_note"] = "per window, from the committed ncu --set full capture (profiles/)"
-            except (ValueError, OSError):
-                pass
         # CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N=1 only
         if world == 1:
             import oracle_lib as O
-            sample = args.cpu_sample or max(64, min(2 * cores, 512))
+            sample = args.cpu_sample or max(64, min(4 * cores, 512))
             t = time.perf_counter()
             cst, cout = O.decode_batch(pcm_np[:sample], nthreads=cores, fast=True)
             dt = time.perf_counter() - t

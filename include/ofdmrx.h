@@ -110,11 +110,15 @@ int ofdmrx_get_taps(ofdmrx_t *h, int stage, int frame_first, int frame_count, vo
 /* elements per window of a tap (in units of the tap's element type) */
 int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage);
 
+/* Measured FP32 FMA throughput of the device (TFLOP/s, a dependent-chain-free FMA kernel over all SMs): the roofline
+ * denominator SURVEY.md 8(d) names for the list decoder. */
+int ofdmrx_measure_fp32(ofdmrx_t *h, float *tflops);
 /* kernels launched by the last ofdmrx_decode_batch / ofdmrx_polar_decode call (bench.py's gpu_launches) */
 int ofdmrx_last_launches(ofdmrx_t *h);
 /* CUDA-event durations (ms, on the launching stream) of the stages of the LAST chunk processed by decode_batch:
  * ms[0] frontend, [1] timing metric, [2] detection, [3] acquire (fine sync + header), [4] demod (FFT/Theil-Sen/LLR),
- * [5] compaction + payload init, [6] polar list decoder.  Returns the number of windows in that chunk (<0 on error). */
+ * [5] compaction + payload init, [6] polar list decoder; with n >= 10 also the three kernels of [4]: [7] FFT + differential
+ * demodulation, [8] Theil-Sen, [9] soft demapping.  Returns the number of windows in that chunk (<0 on error). */
 int ofdmrx_stage_times(ofdmrx_t *h, float *ms, int n);
 /* device-side copies of the constant tables, for tests: which = 0 frozen set (2048 u32) / 1 SCL schedule of modes 6..9,
  * 2 / 3 the same for modes 10..13 */

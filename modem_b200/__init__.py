@@ -47,10 +47,10 @@ assert STATUS_DTYPE.itemsize == 112
 MODE_GEOMETRY = {6: (50, 432), 7: (54, 400), 8: (81, 400), 9: (90, 360), 10: (42, 512), 11: (56, 384), 12: (84, 384), 13: (126, 256)}
 EXPORTS = ["ofdmrx_create", "ofdmrx_destroy", "ofdmrx_set_option", "ofdmrx_decode_batch", "ofdmrx_polar_decode",
            "ofdmrx_get_taps", "ofdmrx_tap_elems", "ofdmrx_last_launches", "ofdmrx_stage_times", "ofdmrx_get_table",
-           "ofdmrx_version", "ofdmrx_theil_sen"]
+           "ofdmrx_version", "ofdmrx_theil_sen", "ofdmrx_measure_fp32"]
 TX_EXPORTS = ["ofdmtx_create", "ofdmtx_destroy", "ofdmtx_call_sign", "ofdmtx_window_samples", "ofdmtx_encode_batch",
               "ofdmtx_get_code", "ofdmtx_last_launches"]
-STAGES = ["frontend", "sync_metric", "sync_detect", "acquire", "demod", "compact_init", "polar_scl"]
+STAGES = ["frontend", "sync_metric", "sync_detect", "acquire", "demod", "compact_init", "polar_scl", "demod_fft", "theil_sen", "soft_demap"]
 
 _lib = None
 
@@ -79,6 +79,7 @@ def load():
     L.ofdmrx_tap_elems.argtypes = [C.c_void_p, C.c_int]
     L.ofdmrx_tap_elems.restype = C.c_int64
     L.ofdmrx_last_launches.argtypes = [C.c_void_p]
+    L.ofdmrx_measure_fp32.argtypes = [C.c_void_p, C.c_void_p]
     L.ofdmrx_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.ofdmrx_get_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.ofdmrx_version.restype = C.c_char_p
@@ -206,11 +207,17 @@ class Receiver:
 
     def stage_times(self):
         """CUDA-event durations (ms) of the stages of the last chunk -> (dict, windows in that chunk)."""
-        ms = np.zeros(7, np.float32)
-        n = self._lib.ofdmrx_stage_times(self._h, ms.ctypes.data, 7)
+        ms = np.zeros(10, np.float32)
+        n = self._lib.ofdmrx_stage_times(self._h, ms.ctypes.data, 10)
         if n < 0:
             raise OfdmrxError("ofdmrx_stage_times failed %d" % n)
         return dict(zip(STAGES, [float(x) for x in ms])), int(n)
+
+    def measure_fp32(self):
+        """measured FP32 FMA throughput of the device in TFLOP/s (roofline denominator of the list decoder)"""
+        v = C.c_float(0)
+        _check(self._lib.ofdmrx_measure_fp32(self._h, C.byref(v)), "ofdmrx_measure_fp32")
+        return float(v.value)
 
     @property
     def last_launches(self):

@@ -741,12 +741,13 @@ static void launch_demod_fft_t(const cfx *iq, int64_t iq_stride, int iq_len, con
 }
 
 cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
-	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s)
+	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s, cudaEvent_t ev_fft_done, cudaEvent_t ev_ts_done)
 {
 	if (n_frames <= 0) return cudaSuccess;
 #define OFDMRX_CALL(R) launch_demod_fft_t<R>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s)
 	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
 #undef OFDMRX_CALL
+	if (ev_fft_done) cudaEventRecord(ev_fft_done, s);
 	// chains per window: one when there are windows enough to fill the GPU twice over, more (shorter) ones for small batches
 	int ts_smem;
 	theil_sen_grid(1, n_sm, &ts_smem);
@@ -754,6 +755,7 @@ cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len,
 	const int n_chains = std::max(5, std::min(9, (2 * resident_warps + n_frames - 1) / n_frames)); // >= 5: short items keep the tail short
 	const int grid = theil_sen_grid(n_frames * n_chains, n_sm, &ts_smem);
 	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames * n_chains, n_chains, 0, ts);
+	if (ev_ts_done) cudaEventRecord(ev_ts_done, s);
 	k_soft_demap<<<n_frames, kSdThreads, 0, s>>>(cons_raw, st, ts, cons, llr);
 	return cudaGetLastError();
 }

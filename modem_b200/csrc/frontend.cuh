@@ -41,7 +41,7 @@ cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_le
 // three kernels: FFT + differential demodulation (cons_raw, phase errors yph), Theil-Sen per row (ts[row] = slope, yint,
 // precision), soft demapping (llr; cons = derotated constellation, optional)
 cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
-	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s);
+	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s, cudaEvent_t ev_fft_done = nullptr, cudaEvent_t ev_ts_done = nullptr);
 cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float *ts, int n_sm, cudaStream_t s);
 cudaError_t launch_compact(const FrameState *st, int n_frames, int *cw_list, int *n_cw, cudaStream_t s);
 

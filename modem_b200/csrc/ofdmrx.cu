@@ -259,6 +259,50 @@ int ofdmrx_set_option(ofdmrx_t *h, const char *key, int value)
 
 int ofdmrx_last_launches(ofdmrx_t *h) { return h ? h->launches : -22; }
 
+namespace {
+// roofline denominator of the list decoder (FP32 CUDA-core peak): 16 independent FMA chains per thread
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, int iters)
+{
+	float a[16];
+#pragma unroll
+	for (int k = 0; k < 16; ++k) a[k] = (float)(threadIdx.x + k);
+	const float m = 0.999f, c = 0.001f * (float)blockIdx.x;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], m, c);
+	}
+	float s = 0.f;
+#pragma unroll
+	for (int k = 0; k < 16; ++k) s += a[k];
+	if (s == 12345.678f) out[0] = s; // never true: keeps the chains alive
+}
+} // namespace
+
+int ofdmrx_measure_fp32(ofdmrx_t *h, float *tflops)
+{
+	if (!h || !tflops) return -22;
+	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
+	cudaEvent_t e0, e1;
+	OFDMRX_CUDA_TRY(cudaEventCreate(&e0));
+	OFDMRX_CUDA_TRY(cudaEventCreate(&e1));
+	const int grid = h->n_sm * 8, iters = 8192;
+	float best = 0.f;
+	for (int rep = 0; rep < 4; ++rep) {
+		cudaEventRecord(e0, nullptr);
+		k_fp32_peak<<<grid, 256>>>((float *)h->d_ncw, iters);
+		cudaEventRecord(e1, nullptr);
+		OFDMRX_CUDA_TRY(cudaEventSynchronize(e1));
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		const float tf = 2.f * 16.f * (float)iters * 256.f * (float)grid / (ms * 1e-3f) / 1e12f;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	*tflops = best;
+	return 0;
+}
+
 int ofdmrx_stage_times(ofdmrx_t *h, float *ms, int n)
 {
 	if (!h || !ms || n < 7) return -22;
@@ -266,6 +310,11 @@ int ofdmrx_stage_times(ofdmrx_t *h, float *ms, int n)
 	OFDMRX_CUDA_TRY(cudaSetDevice(h->device));
 	OFDMRX_CUDA_TRY(cudaEventSynchronize(h->ev[7]));
 	for (int i = 0; i < 7; ++i) OFDMRX_CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+	if (n >= 10) { // the three kernels of the demod stage: FFT + differential demodulation, Theil-Sen, soft demapping
+		OFDMRX_CUDA_TRY(cudaEventElapsedTime(&ms[7], h->ev[4], h->ev[8]));
+		OFDMRX_CUDA_TRY(cudaEventElapsedTime(&ms[8], h->ev[8], h->ev[9]));
+		OFDMRX_CUDA_TRY(cudaEventElapsedTime(&ms[9], h->ev[9], h->ev[5]));
+	}
 	return h->last_chunk_frames;
 }
 
@@ -304,7 +353,7 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 	if (record) cudaEventRecord(h->ev[4], s);
 	OFDMRX_CUDA_TRY(launch_demod(h->rate, iq, h->iq_len, h->iq_len, h->d_st + f0, nf, h->d_tw1280, h->d_cons_raw + (size_t)f0 * kMaxCons,
 		h->d_y + (size_t)f0 * kMaxCons, h->keep_taps ? h->d_cons + (size_t)f0 * kMaxCons : nullptr, h->d_ts + (size_t)f0 * kMaxRows * 3,
-		h->d_llr + (size_t)f0 * kCodeLen, h->n_sm, s));
+		h->d_llr + (size_t)f0 * kCodeLen, h->n_sm, s, record ? h->ev[8] : nullptr, record ? h->ev[9] : nullptr));
 	if (record) cudaEventRecord(h->ev[5], s);
 	h->launches += 7;
 	return 0;
