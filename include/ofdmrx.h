@@ -105,7 +105,7 @@ int ofdmrx_polar_decode(ofdmrx_t *h, const float *llr, int n, uint8_t *payload_o
  * host-resident rows of `cols` (<= 512) phase values; out3 receives (slope, yint, pair sweeps the search took) per row. */
 int ofdmrx_theil_sen(ofdmrx_t *h, const float *y, int n_rows, int cols, float *out3);
 
-/* Copies stage outputs of the LAST decode_batch chunk (needs option keep_taps=1 for CONS) to host memory. */
+/* Copies stage outputs of the LAST decode_batch chunk (needs option keep_taps=1 for CONS and TIMING) to host memory. */
 int ofdmrx_get_taps(ofdmrx_t *h, int stage, int frame_first, int frame_count, void *dst, size_t bytes);
 /* elements per window of a tap (in units of the tap's element type) */
 int64_t ofdmrx_tap_elems(ofdmrx_t *h, int stage);

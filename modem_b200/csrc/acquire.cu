@@ -468,11 +468,9 @@ template <int S>
 static cudaError_t launch_acquire_t(const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int det_cap, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s)
 {
-	static bool attr[64] = {};
+	static DeviceOnce once;
 	const size_t smem = kAcqBufOff + 2 * (size_t)Geo<S>::kSymLen * sizeof(cfx);
-	if (first_use_on_device(attr)) {
-		cudaFuncSetAttribute(k_acquire<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	}
+	if (cudaError_t e = set_dynamic_smem_once(once, k_acquire<S>, (int)smem)) return e;
 	k_acquire<S><<<n_frames, kAcqThreads, smem, s>>>(iq, iq_stride, iq_len, det, det_count, det_cap, skip, st, soft_out, ac);
 	return cudaGetLastError();
 }

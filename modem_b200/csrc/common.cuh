@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include "host_tables.h"
 
 namespace ofdmrx {
@@ -16,15 +17,21 @@ namespace ofdmrx {
 		}                                                                                            \
 	} while (0)
 
-// Function attributes (dynamic shared memory limits) are per device: launchers set them once per device, not per process.
-inline bool first_use_on_device(bool (&seen)[64])
+// Function attributes (dynamic shared-memory limits) are per device.  Launchers set them on first use of a device, once,
+// under std::call_once: a second host thread (another handle on the same device) blocks until the attribute is in place
+// instead of launching ahead of it, and the attribute call's error is kept and returned to every caller.
+struct DeviceOnce {
+	std::once_flag flag[64];
+	cudaError_t err[64];
+};
+template <typename Kernel>
+inline cudaError_t set_dynamic_smem_once(DeviceOnce &once, Kernel kernel, int bytes)
 {
 	int d = 0;
 	cudaGetDevice(&d);
 	d &= 63;
-	if (seen[d]) return false;
-	seen[d] = true;
-	return true;
+	std::call_once(once.flag[d], [&] { once.err[d] = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+	return once.err[d];
 }
 
 typedef float2 cfx;

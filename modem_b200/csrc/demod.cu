@@ -21,6 +21,7 @@
 #include "frontend.cuh"
 #include "fft.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace ofdmrx {
 namespace {
@@ -379,7 +380,7 @@ __device__ __noinline__ float ts_slope_bisect(const float *y, int n, int rank, i
 // exact upper median of the pairwise slopes of (x = i - 216, y[i]); one warp, y in s.y (tail padded)
 // hint: expected (Theil-Sen - OLS) of this row, in slope units (0 = none); pilot_out / half_out: the OLS slope and the
 // bracket half-width used, for the caller's running estimate of that gap
-__device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, float hint, float &pilot_out, float &half_out)
+__device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, float hint, float half_k, float &pilot_out, float &half_out)
 {
 	pilot_out = 0.f; half_out = 0.f;
 	// ---- pilot: least-squares line and residual spread (only steers the bracket, so fp32 sums are good enough)
@@ -476,7 +477,7 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 	// (more carriers than 432: the quotient count inside a bracket of given relative width grows like n^1.5; shrink it to
 	// keep ~1100 candidates, which is what the per-row scratch is sized for)
 	const float shrink = d.n > 432 ? scale * sqrtf(scale) : 1.f;
-	float half = fmaxf(1.35e-4f * sigma * shrink, fmaxf(fabsf(c0) * 4e-6f, 1e-12f));
+	float half = fmaxf(half_k * sigma * shrink, fmaxf(fabsf(c0) * 4e-6f, 1e-12f));
 	pilot_out = c0; half_out = half;
 	float blo = c0 + hint - half, bhi = c0 + hint + half;
 	// enclosure of the answer established so far: #(q < L) = cL <= rank < cU = #(q < U)  (exact counts; +-inf = unknown)
@@ -575,7 +576,7 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 // Work items: with a status array, item = (window f, chain c of n_chains): the chain walks a contiguous block of the window's
 // rows (row r: cols(mode) phase values at yph + f * kMaxCons + r * cols) one after the other.  Without a status array (test
 // hook) every item is one dense row of fixed_cols values.
-__global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, FrameState *stv, int n_items, int n_chains, int fixed_cols, float *ts_out)
+__global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, FrameState *stv, int n_items, int n_chains, int fixed_cols, float half_k, float *ts_out)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, F
 			__syncwarp();
 			int sweeps = 0;
 			float pilot, half;
-			const float slope = ts_slope(s, d, lane, sweeps, gap, pilot, half);
+			const float slope = ts_slope(s, d, lane, sweeps, gap, half_k, pilot, half);
 			total_sweeps += sweeps;
 			// intercept: upper median of y_i - slope * x_i
 			__syncwarp();
@@ -708,15 +709,20 @@ __global__ void __launch_bounds__(kSdThreads) k_soft_demap(const cfx *cons_raw, 
 
 static int theil_sen_grid(int rows, int n_sm, int *smem)
 {
-	static bool attr[64] = {};
+	static DeviceOnce once;
 	*smem = (int)(kTsWarps * sizeof(TsShared));
-	if (first_use_on_device(attr)) {
-		cudaFuncSetAttribute(k_theil_sen, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem);
-	}
+	if (set_dynamic_smem_once(once, k_theil_sen, *smem) != cudaSuccess) return -1;
 	int grid = (rows + kTsWarps - 1) / kTsWarps;
 	const int resident = n_sm * (int)((227 * 1024) / (*smem + 1024));
 	if (grid > 4 * resident) grid = 4 * resident; // a few waves of persistent CTAs: rows differ little in cost
 	return grid;
+}
+
+// first bracket of the slope search: +- half_k robust sigmas around the pilot (OFDMRX_TS_HALF overrides for A/B runs)
+static float ts_half_k()
+{
+	static const float k = [] { const char *e = std::getenv("OFDMRX_TS_HALF"); return e ? (float)std::atof(e) : 1.35e-4f; }();
+	return k;
 }
 
 // test hook: n_rows dense rows of `cols` phase values -> (slope, yint, sweeps) per row
@@ -725,28 +731,30 @@ cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float 
 	if (n_rows <= 0) return cudaSuccess;
 	int smem;
 	const int grid = theil_sen_grid(n_rows, n_sm, &smem);
-	k_theil_sen<<<grid, kTsWarps * 32, smem, s>>>(yph, nullptr, n_rows, 1, cols, ts);
+	if (grid < 0) return cudaErrorInvalidValue; // the shared-memory attribute could not be set on this device
+	k_theil_sen<<<grid, kTsWarps * 32, smem, s>>>(yph, nullptr, n_rows, 1, cols, ts_half_k(), ts);
 	return cudaGetLastError();
 }
 
 template <int S>
-static void launch_demod_fft_t(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *st, int n_frames, const cfx *tw,
+static cudaError_t launch_demod_fft_t(const cfx *iq, int64_t iq_stride, int iq_len, const FrameState *st, int n_frames, const cfx *tw,
 	cfx *cons_raw, float *yph, cudaStream_t s)
 {
-	static bool attr[64] = {};
-	if (first_use_on_device(attr)) {
-		cudaFuncSetAttribute(k_demod_fft<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FftShared<S>));
-	}
+	static DeviceOnce once;
+	if (cudaError_t e = set_dynamic_smem_once(once, k_demod_fft<S>, (int)sizeof(FftShared<S>))) return e;
 	k_demod_fft<S><<<n_frames, kDmThreads, sizeof(FftShared<S>), s>>>(iq, iq_stride, iq_len, st, tw, cons_raw, yph);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len, FrameState *st, int n_frames, const cfx *tw1280,
 	cfx *cons_raw, float *yph, cfx *cons, float *ts, float *llr, int n_sm, cudaStream_t s, cudaEvent_t ev_fft_done, cudaEvent_t ev_ts_done)
 {
 	if (n_frames <= 0) return cudaSuccess;
-#define OFDMRX_CALL(R) launch_demod_fft_t<R>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s)
+	cudaError_t e = cudaSuccess;
+#define OFDMRX_CALL(R) e = launch_demod_fft_t<R>(iq, iq_stride, iq_len, st, n_frames, tw1280, cons_raw, yph, s)
 	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
 #undef OFDMRX_CALL
+	if (e != cudaSuccess) return e;
 	if (ev_fft_done) cudaEventRecord(ev_fft_done, s);
 	// chains per window: one when there are windows enough to fill the GPU twice over, more (shorter) ones for small batches
 	int ts_smem;
@@ -754,7 +762,8 @@ cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len,
 	const int resident_warps = n_sm * (int)((227 * 1024) / (ts_smem + 1024)) * kTsWarps;
 	const int n_chains = std::max(5, std::min(9, (2 * resident_warps + n_frames - 1) / n_frames)); // >= 5: short items keep the tail short
 	const int grid = theil_sen_grid(n_frames * n_chains, n_sm, &ts_smem);
-	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames * n_chains, n_chains, 0, ts);
+	if (grid < 0) return cudaErrorInvalidValue;
+	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames * n_chains, n_chains, 0, ts_half_k(), ts);
 	if (ev_ts_done) cudaEventRecord(ev_ts_done, s);
 	k_soft_demap<<<n_frames, kSdThreads, 0, s>>>(cons_raw, st, ts, cons, llr);
 	return cudaGetLastError();

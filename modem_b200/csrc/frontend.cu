@@ -161,26 +161,85 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane)
 	return v;
 }
 
+// One bulk-asynchronous copy (cp.async.bulk, the 1-D form of TMA: SASS UBLKCP) stages the tile's span of the analytic stream
+// in shared memory; it serves both correlator taps (the current stream and the one lagging by half a symbol are the same
+// samples 640 apart).  Its base t0 - (kOffCur + kHalo + kLag) is an even sample index at all four rates, i.e. 16-byte aligned.
+// OFDMRX_SYNC_TMA=0 keeps the round-1 staging (two coalesced register-load streams) for A/B runs.
+#ifndef OFDMRX_SYNC_TMA
+#define OFDMRX_SYNC_TMA 1
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		:: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Outputs: the Schmitt trigger's two comparisons as bit masks (hi: v > high, lo: v < low; one word per 32 stream steps — all
+// k_sync_detect needs to list the edges) and the timing values themselves only for tiles that hold a value >= low (every
+// sample between a rise and its fall does) or when the caller keeps the stage taps (write_all).
 template <int S>
 __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples,
-	int n_default, float *timing, int64_t timing_stride)
+	int n_default, float *timing, int64_t timing_stride, uint32_t *masks, int mask_words, int write_all)
 {
 	constexpr int kMtHalo = Mt<S>::kHalo, kMtExt = Mt<S>::kExt, kMtPer = Mt<S>::kPer, kMtPad = Mt<S>::kPad, kMtThreads = Mt<S>::kThreads;
 	constexpr int kLag = Geo<S>::kHalf, kLen2 = Geo<S>::kSymLen, kBox = Geo<S>::kMatchLen;
-	extern __shared__ float sm[];
+	extern __shared__ __align__(16) float sm[];
 	float *sre = sm;                                    // c.re, then its prefix, later the prefix of m   [kMtPad]
 	float *sim = sre + kMtPad;                          // c.im, then its prefix
 	float *se = sim + kMtPad;                           // e, then its prefix
 	__shared__ float wtot[3][Mt<S>::kThreads / 32];
+	__shared__ __align__(8) uint64_t bar;
 	const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = n_samples ? n_samples[f] : n_default;
 	const int t0 = blockIdx.x * kMtTile;
 	if (t0 > n) return; // stream has n+1 steps: t = 0..n
 	const cfx *a = iq + (size_t)f * iq_stride;
 	const int base = t0 - (Mt<S>::kOffCur + kMtHalo); // extended index j <-> a[t - kOffCur], t = t0 + j - kMtHalo
-	{ // c[j] = a[j - lag] conj(a[j]) and e[j] = |a[j]|^2 straight from coalesced global loads (the lagged stream comes from
-	  // L1/L2); all loads of a thread are issued before the first shared-memory store
+	{ // c[j] = a[j - lag] conj(a[j]) and e[j] = |a[j]|^2
 		cfx cur[kMtPer], old[kMtPer];
+#if OFDMRX_SYNC_TMA
+		static_assert(3 * kMtPad * sizeof(float) >= (size_t)(kMtExt + kLag + 1) * sizeof(cfx), "the staged span fits the three arrays it is unpacked into");
+		static_assert(((Mt<S>::kOffCur + kMtHalo + kLag) & 1) == 0 && (kMtTile & 1) == 0, "16-byte aligned span base");
+		cfx *stage = reinterpret_cast<cfx *>(sm);       // stage[e] = a[lo + e], e in [0, kMtExt + kLag]
+		const int lo = base - kLag;
+		const int c0 = max(lo, 0), c1 = min((lo + kMtExt + kLag + 1) & ~1, iq_len); // copied samples [c0, c1): even bounds
+		const int ncopy = max(c1 - c0, 0);
+		if (tid == 0) mbar_init(&bar, 1);
+		for (int e = tid; e < kMtExt + kLag + 1; e += kMtThreads) { // the parts of the span outside the stream read as zero
+			const int idx = lo + e;
+			if (idx < c0 || idx >= c1) stage[e] = make_float2(0.f, 0.f);
+		}
+		__syncthreads();
+		if (tid == 0 && ncopy > 0) {
+			mbar_expect_tx(&bar, (uint32_t)ncopy * (uint32_t)sizeof(cfx));
+			bulk_g2s(stage + (c0 - lo), a + c0, (uint32_t)ncopy * (uint32_t)sizeof(cfx), &bar);
+		}
+		if (ncopy > 0) mbar_wait(&bar, 0);
+#pragma unroll
+		for (int k = 0; k < kMtPer; ++k) {
+			const int j = tid + k * kMtThreads;
+			cur[k] = j < kMtExt ? stage[j + kLag] : make_float2(0.f, 0.f);
+			old[k] = j < kMtExt ? stage[j] : make_float2(0.f, 0.f);
+		}
+		__syncthreads(); // every thread holds its samples: the span is overwritten by the three arrays below
+#else
+		// straight from coalesced global loads (the lagged stream comes from L1/L2); all loads of a thread are issued before
+		// the first shared-memory store
 #pragma unroll
 		for (int k = 0; k < kMtPer; ++k) {
 			const int j = tid + k * kMtThreads, idx = base + j;
@@ -188,10 +247,11 @@ __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, 
 			const int io = idx - kLag;
 			old[k] = (j >= kLag && j < kMtExt && io >= 0 && io < iq_len) ? __ldg(&a[io]) : make_float2(0.f, 0.f);
 		}
+#endif
 #pragma unroll
 		for (int k = 0; k < kMtPer; ++k) {
 			const int j = tid + k * kMtThreads;
-			const cfx c = cmulc(old[k], cur[k]);
+			const cfx c = j >= kLag ? cmulc(old[k], cur[k]) : make_float2(0.f, 0.f);
 			sre[j] = c.x; sim[j] = c.y; se[j] = cnorm(cur[k]);
 		}
 	}
@@ -244,6 +304,19 @@ __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, 
 #pragma unroll
 	for (int k = 0; k < kMtPer; ++k) sre[j0 + k] = om + mloc[k];
 	__syncthreads();
+	// trigger masks (decode.cc:76,93: low 0.17 x 161, high 0.19 x 161): one ballot pair per 32 stream steps
+	const float low = (float)(0.17 * kBox), high = (float)(0.19 * kBox);
+	uint32_t *mh = masks + (size_t)f * 2 * mask_words, *ml = mh + mask_words;
+	bool keep = false;
+	for (int i = tid; i < kMtTile; i += kMtThreads) {
+		const int t = t0 + i, j = i + kMtHalo;
+		const bool valid = t <= n;
+		const float v = sre[j] - sre[j - kBox];
+		const unsigned h = __ballot_sync(FULL, valid && v > high), l = __ballot_sync(FULL, valid && v < low);
+		if (lane == 0) { mh[t >> 5] = h; ml[t >> 5] = l; }
+		keep |= valid && v >= low;
+	}
+	if (!write_all && !__syncthreads_or(keep)) return; // nothing in this tile can lie between a rise and its fall
 	float *out = timing + (size_t)f * timing_stride;
 	for (int i = tid; i < kMtTile; i += kMtThreads) {
 		const int t = t0 + i;
@@ -256,41 +329,29 @@ __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, 
 // ------------------------------------------------------------------------------------------------ K1b detection
 // Schmitt trigger (low 0.17*161, high 0.19*161) + falling edge + first strict maximum inside each
 // [rise, fall] segment (decode.cc:93-108).  One CTA per window.  The trigger only ever reacts to "v > high" while low
-// and to "v < low" while high, so the stream is first reduced — with coalesced loads, one ballot per 32 samples — to two
-// bit masks per 32-sample word; one thread then walks the words (almost all of them are skipped with one test) and
-// lists the edges in stream order; a warp per (rise, fall) segment finds the maximum.
+// and to "v < low" while high: k_sync_metric hands over those two comparisons as bit masks (one word per 32 samples);
+// one warp walks the words (almost all of them are skipped with one test) and lists the edges in stream order; a warp
+// per (rise, fall) segment finds the maximum among the timing values of the segment (the only ones ever read).
 constexpr int kDtThreads = 256;
 constexpr int kDtTile = 65536;                 // samples per pass (state and edge list carry over)
 constexpr int kDtWords = kDtTile / 32;
 
 template <int S>
-__global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing, int64_t timing_stride, const int32_t *n_samples,
-	int n_default, Detection *det, int32_t *det_count, int det_cap, int32_t *edges)
+__global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing, int64_t timing_stride, const uint32_t *masks, int mask_words,
+	const int32_t *n_samples, int n_default, Detection *det, int32_t *det_count, int det_cap, int32_t *edges)
 {
-	constexpr int kMatchLen = Geo<S>::kMatchLen, kMatchDel = Geo<S>::kMatchDel, kHalf = Geo<S>::kHalf, kGuardLen = Geo<S>::kGuardLen;
+	constexpr int kMatchDel = Geo<S>::kMatchDel, kHalf = Geo<S>::kHalf, kGuardLen = Geo<S>::kGuardLen;
 	__shared__ uint32_t hi_m[kDtWords], lo_m[kDtWords];
 	__shared__ int n_ev_s, state_s;
 	int32_t *ev_t = edges + (size_t)blockIdx.x * (2 * det_cap + 2); // rise / fall stream indices of this window, in order
 	const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = (n_samples ? n_samples[f] : n_default) + 1; // steps t = 0..n_samples
 	const float *tm = timing + (size_t)f * timing_stride;
-	const float low = (float)(0.17 * kMatchLen), high = (float)(0.19 * kMatchLen);
+	const uint32_t *gh = masks + (size_t)f * 2 * mask_words, *gl = gh + mask_words;
 	if (tid == 0) { n_ev_s = 0; state_s = 0; } // the trigger starts low, so the first edge is always a rise
 	for (int t0 = 0; t0 < n; t0 += kDtTile) {
 		const int words = min(kDtWords, (n - t0 + 31) >> 5);
-		for (int w0 = wid * 4; w0 < words; w0 += (kDtThreads / 32) * 4) { // four independent loads in flight per lane
-			float v[4];
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const int t = t0 + 32 * (w0 + k) + lane;
-				v[k] = t < n ? tm[t] : __int_as_float(0x7fc00000); // NaN: neither above high nor below low
-			}
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				const unsigned h = __ballot_sync(FULL, v[k] > high), l = __ballot_sync(FULL, v[k] < low);
-				if (lane == 0 && w0 + k < words) { hi_m[w0 + k] = h; lo_m[w0 + k] = l; }
-			}
-		}
+		for (int w = tid; w < words; w += kDtThreads) { hi_m[w] = gh[(t0 >> 5) + w]; lo_m[w] = gl[(t0 >> 5) + w]; }
 		__syncthreads();
 		if (wid == 0) { // all lanes run the same walk (uniform); 32 words are skipped per step while nothing can happen
 			int s = state_s, ne = n_ev_s;
@@ -321,7 +382,7 @@ __global__ void __launch_bounds__(kDtThreads) k_sync_detect(const float *timing,
 		const int rise = ev_t[2 * sgi], fall = ev_t[2 * sgi + 1];
 		float best = 0.f; // timing_max starts at 0 and only a strictly larger value replaces it
 		int bi = -1;
-		for (int t = rise + lane; t <= fall; t += 32) {
+		for (int t = rise + lane; t < fall; t += 32) { // (the fall step itself is below `low`: it never is the maximum)
 			const float v = tm[t];
 			if (v > best) { best = v; bi = t; }
 		}
@@ -370,34 +431,32 @@ cudaError_t launch_frontend(int rate, int format, const void *samples, int64_t s
 
 template <int S>
 static cudaError_t launch_sync_metric_t(const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
-	float *timing, int64_t timing_stride, cudaStream_t s)
+	float *timing, int64_t timing_stride, uint32_t *masks, int mask_words, int write_all, cudaStream_t s)
 {
-	static bool attr[64] = {};
+	static DeviceOnce once;
 	const size_t smem = (size_t)3 * Mt<S>::kPad * sizeof(float);
-	if (first_use_on_device(attr)) {
-		cudaFuncSetAttribute(k_sync_metric<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	}
+	if (cudaError_t e = set_dynamic_smem_once(once, k_sync_metric<S>, (int)smem)) return e;
 	dim3 g((n_max + 1 + kMtTile - 1) / kMtTile, n_frames);
-	k_sync_metric<S><<<g, Mt<S>::kThreads, smem, s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride);
+	k_sync_metric<S><<<g, Mt<S>::kThreads, smem, s>>>(iq, iq_stride, iq_len, n_samples, n_default, timing, timing_stride, masks, mask_words, write_all);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_sync_metric(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
-	float *timing, int64_t timing_stride, cudaStream_t s)
+	float *timing, int64_t timing_stride, uint32_t *masks, int mask_words, int write_all, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
 	cudaError_t e = cudaSuccess;
-#define OFDMRX_CALL(R) e = launch_sync_metric_t<R>(iq, iq_stride, iq_len, n_samples, n_default, n_max, n_frames, timing, timing_stride, s)
+#define OFDMRX_CALL(R) e = launch_sync_metric_t<R>(iq, iq_stride, iq_len, n_samples, n_default, n_max, n_frames, timing, timing_stride, masks, mask_words, write_all, s)
 	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
 #undef OFDMRX_CALL
 	return e;
 }
 
-cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
-	Detection *det, int32_t *det_count, int det_cap, int32_t *edges, cudaStream_t s)
+cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const uint32_t *masks, int mask_words, const int32_t *n_samples,
+	int n_default, int n_frames, Detection *det, int32_t *det_count, int det_cap, int32_t *edges, cudaStream_t s)
 {
 	if (n_frames <= 0) return cudaSuccess;
-#define OFDMRX_CALL(R) k_sync_detect<R><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, n_samples, n_default, det, det_count, det_cap, edges)
+#define OFDMRX_CALL(R) k_sync_detect<R><<<n_frames, kDtThreads, 0, s>>>(timing, timing_stride, masks, mask_words, n_samples, n_default, det, det_count, det_cap, edges)
 	OFDMRX_FOR_RATE(rate, OFDMRX_CALL)
 #undef OFDMRX_CALL
 	return cudaGetLastError();

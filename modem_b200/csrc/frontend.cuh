@@ -31,11 +31,13 @@ struct AcquireConsts {
 // format: OFDMRX_FMT_* (0 int16 real, 1 int16 I/Q, 2 float2 I/Q, 3 float real)
 cudaError_t launch_frontend(int rate, int format, const void *samples, int64_t stride, const int32_t *n_samples, int n_default, int n_frames,
 	cfx *iq, int64_t iq_stride, int iq_len, const FrontendConsts &fc, cudaStream_t s);
+// masks: [n_frames][2][mask_words] trigger comparisons (v > high | v < low), one bit per stream step; the timing values are stored only
+// for tiles that can lie inside a (rise, fall) segment unless write_all is set (stage taps)
 cudaError_t launch_sync_metric(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const int32_t *n_samples, int n_default, int n_max, int n_frames,
-	float *timing, int64_t timing_stride, cudaStream_t s);
+	float *timing, int64_t timing_stride, uint32_t *masks, int mask_words, int write_all, cudaStream_t s);
 // det: [n_frames][det_cap]; edges: scratch [n_frames][2 * det_cap + 2]
-cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const int32_t *n_samples, int n_default, int n_frames,
-	Detection *det, int32_t *det_count, int det_cap, int32_t *edges, cudaStream_t s);
+cudaError_t launch_sync_detect(int rate, const float *timing, int64_t timing_stride, const uint32_t *masks, int mask_words, const int32_t *n_samples,
+	int n_default, int n_frames, Detection *det, int32_t *det_count, int det_cap, int32_t *edges, cudaStream_t s);
 cudaError_t launch_acquire(int rate, const cfx *iq, int64_t iq_stride, int iq_len, const Detection *det, const int32_t *det_count, int det_cap, int skip,
 	int n_frames, FrameState *st, int8_t *soft_out, const AcquireConsts &ac, cudaStream_t s);
 // three kernels: FFT + differential demodulation (cons_raw, phase errors yph), Theil-Sen per row (ts[row] = slope, yint,

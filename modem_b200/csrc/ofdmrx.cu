@@ -41,6 +41,7 @@ struct ofdmrx_handle {
 	float *d_timing = nullptr;
 	Detection *d_det = nullptr;
 	int32_t *d_detcnt = nullptr, *d_edges = nullptr;
+	uint32_t *d_masks = nullptr; int mask_words = 0;
 	int det_cap = 16;
 	FrameState *d_st = nullptr;
 	int8_t *d_soft = nullptr;
@@ -193,6 +194,8 @@ int ofdmrx_create(ofdmrx_t **out, int device, int rate_hz, int max_frames, int m
 	if (!r) r = dev_alloc(&h->d_nsamp, F);
 	if (!r) r = dev_alloc(&h->d_iq, F * (size_t)h->iq_len);
 	if (!r) r = dev_alloc(&h->d_timing, F * (size_t)h->iq_len);
+	h->mask_words = h->iq_len / 32 + 64; // one bit per stream step, rounded up to whole correlator tiles
+	if (!r) r = dev_alloc(&h->d_masks, F * 2 * (size_t)h->mask_words);
 	h->det_cap = std::max(16, max_samples / pitch + 8); // decode.cc:390-448 walks detections without bound: one per symbol pitch is generous
 	if (!r) r = dev_alloc(&h->d_det, F * h->det_cap);
 	if (!r) r = dev_alloc(&h->d_edges, F * (2 * (size_t)h->det_cap + 2));
@@ -222,7 +225,7 @@ void ofdmrx_destroy(ofdmrx_t *h)
 	if (!h) return;
 	cudaSetDevice(h->device);
 	void *ptrs[] = {h->d_tbl[0], h->d_tbl[1], h->d_scr, h->d_bch, h->d_mls1, h->d_tw1280, h->d_tw640, h->d_kern, h->d_in,
-		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_edges, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr, h->d_y,
+		h->d_nsamp, h->d_iq, h->d_timing, h->d_det, h->d_detcnt, h->d_edges, h->d_masks, h->d_st, h->d_soft, h->d_cons_raw, h->d_cons, h->d_ts, h->d_llr, h->d_y,
 		h->d_cwlist, h->d_ncw, h->d_work, h->d_payload, h->d_A, h->d_B, h->d_xbits};
 	for (void *p : ptrs) if (p) cudaFree(p);
 	for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -342,9 +345,10 @@ static int run_front(ofdmrx_handle *h, const void *d_samples, int format, int f0
 	if (record) cudaEventRecord(h->ev[0], s);
 	OFDMRX_CUDA_TRY(launch_frontend(h->rate, format, d_samples, stride, ns, n_default, nf, iq, h->iq_len, h->iq_len, h->fc, s));
 	if (record) cudaEventRecord(h->ev[1], s);
-	OFDMRX_CUDA_TRY(launch_sync_metric(h->rate, iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, s));
+	uint32_t *masks = h->d_masks + (size_t)f0 * 2 * h->mask_words;
+	OFDMRX_CUDA_TRY(launch_sync_metric(h->rate, iq, h->iq_len, h->iq_len, ns, n_default, n_max, nf, timing, h->iq_len, masks, h->mask_words, h->keep_taps ? 1 : 0, s));
 	if (record) cudaEventRecord(h->ev[2], s);
-	OFDMRX_CUDA_TRY(launch_sync_detect(h->rate, timing, h->iq_len, ns, n_default, nf, h->d_det + (size_t)f0 * h->det_cap, h->d_detcnt + f0, h->det_cap,
+	OFDMRX_CUDA_TRY(launch_sync_detect(h->rate, timing, h->iq_len, masks, h->mask_words, ns, n_default, nf, h->d_det + (size_t)f0 * h->det_cap, h->d_detcnt + f0, h->det_cap,
 		h->d_edges + (size_t)f0 * (2 * h->det_cap + 2), s));
 	if (record) cudaEventRecord(h->ev[3], s);
 	AcquireConsts ac{h->d_tw1280, h->d_tw640, h->d_kern, h->d_mls1, h->d_bch};
@@ -519,7 +523,7 @@ int ofdmrx_get_taps(ofdmrx_t *h, int stage, int first, int count, void *dst, siz
 	case OFDMRX_TAP_PHASE: src = h->d_y; esz = 4; break;
 	default: return -22;
 	}
-	if (!src) return -61; // keep_taps was off
+	if (!src || (stage == OFDMRX_TAP_TIMING && !h->keep_taps)) return -61; // keep_taps was off (the timing metric is then stored only around detections)
 	const size_t per = (size_t)ofdmrx_tap_elems(h, stage) * esz;
 	if (bytes < per * count) return -27;
 	OFDMRX_CUDA_TRY(cudaDeviceSynchronize());

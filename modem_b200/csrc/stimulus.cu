@@ -100,11 +100,8 @@ __global__ void __launch_bounds__(kTxStreamThreads) k_tx_stream_b(TxImpair im, l
 template <int N>
 cudaError_t launch_tx_symbol(const TxParams &p, const uint32_t *code, int n_blocks, int common, cudaStream_t s)
 {
-	static bool attr[64];
-	if (first_use_on_device(attr)) {
-		cudaError_t e = cudaFuncSetAttribute(k_tx_symbol<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tx_symbol_smem<N>());
-		if (e != cudaSuccess) return e;
-	}
+	static DeviceOnce once;
+	if (cudaError_t e = set_dynamic_smem_once(once, k_tx_symbol<N>, (int)tx_symbol_smem<N>())) return e;
 	k_tx_symbol<N><<<n_blocks, tx_symbol_threads<N>(), tx_symbol_smem<N>(), s>>>(p, code, common);
 	return cudaGetLastError();
 }
