@@ -243,8 +243,14 @@ def main():
         step_device()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     total_ms, clocks = timed(step_device, args.steps, sampler)
-    stage_ms, n_chunk = rx.stage_times()
     launches = rx.last_launches + (1 if world > 1 else 0)
+    # per-kernel times: one more step with one list-decoder launch for the whole chunk (the timed steps above overlap the list
+    # decoder of each sub-chunk with the front stages of the next, so their stages do not add up)
+    rx.set_option("sub_chunks", 1)
+    step_device()
+    torch.cuda.synchronize()
+    stage_ms, n_chunk = rx.stage_times()
+    rx.set_option("sub_chunks", 0)
     # parity gate on the timed output (outside the timed region): every payload must equal the sent bytes
     got = payload.cpu().numpy()
     st = status.cpu().numpy().view(M.STATUS_DTYPE).reshape(-1)
@@ -309,7 +315,11 @@ def main():
             for _ in range(2):
                 step_imp()
             c3_ms, _ = timed(step_imp, args.steps)
+            rx3.set_option("sub_chunks", 1)
+            step_imp()
+            torch.cuda.synchronize()
             c3_stage, _ = rx3.stage_times()
+            rx3.set_option("sub_chunks", 0)
             c3_err, c3_fail = errors_now()
             cfg3 = {"workload": "BASELINE configs[2]: README chain (multipath + CFO 234.567 Hz + SFO 147 ppm + AWGN -30 dB) on %d distinct device-generated windows per GPU" % n,
                     "frames_per_s": n * world / (c3_ms / args.steps / 1e3), "ms_per_step": c3_ms / args.steps,

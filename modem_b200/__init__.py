@@ -131,6 +131,11 @@ class Receiver:
         if keep_taps:
             _check(self._lib.ofdmrx_set_option(self._h, b"keep_taps", 1), "set_option")
 
+    def set_option(self, key, value):
+        """ofdmrx_set_option: "keep_taps", "polar_table", "scl_ctas_per_sm", "sub_chunks" (0 = by batch size, 1 = no overlap of the
+        list decoder with the next sub-chunk's front stages: needed for stage_times() on large batches)"""
+        _check(self._lib.ofdmrx_set_option(self._h, key.encode() if isinstance(key, str) else key, int(value)), "set_option")
+
     def close(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

@@ -576,7 +576,7 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 // Work items: with a status array, item = (window f, chain c of n_chains): the chain walks a contiguous block of the window's
 // rows (row r: cols(mode) phase values at yph + f * kMaxCons + r * cols) one after the other.  Without a status array (test
 // hook) every item is one dense row of fixed_cols values.
-__global__ void __launch_bounds__(kTsWarps * 32) k_theil_sen(const float *yph, FrameState *stv, int n_items, int n_chains, int fixed_cols, float half_k, float *ts_out)
+__global__ void __launch_bounds__(kTsWarps * 32, 5) k_theil_sen(const float *yph, FrameState *stv, int n_items, int n_chains, int fixed_cols, float half_k, float *ts_out)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -718,10 +718,12 @@ static int theil_sen_grid(int rows, int n_sm, int *smem)
 	return grid;
 }
 
-// first bracket of the slope search: +- half_k robust sigmas around the pilot (OFDMRX_TS_HALF overrides for A/B runs)
+// first bracket of the slope search: +- half_k robust sigmas around the pilot (OFDMRX_TS_HALF overrides for A/B runs).
+// Measured per 10 000 windows (demod stage, clean / README chain): 1.35e-4 26.1 / 29.4 ms, 0.9e-4 24.4 / 27.5, 0.6e-4 23.8 / 28.8:
+// a narrower bracket queues fewer pairs but misses the rank more often (a second, extrapolated sweep).
 static float ts_half_k()
 {
-	static const float k = [] { const char *e = std::getenv("OFDMRX_TS_HALF"); return e ? (float)std::atof(e) : 1.35e-4f; }();
+	static const float k = [] { const char *e = std::getenv("OFDMRX_TS_HALF"); return e ? (float)std::atof(e) : 0.9e-4f; }();
 	return k;
 }
 

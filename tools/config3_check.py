@@ -17,6 +17,7 @@ t = time.time()
 pcm, ns, sent = windows(n, 31337, channels=2, imp=dict(multipath=True, cfo_hz=234.567, sfo_ppm=147, awgn_db=-30, seed=12345))  # STIM=device: generated on the GPU
 t_enc = time.time() - t
 rx = M.Receiver(max_frames=n)
+rx.set_option("sub_chunks", 1)   # one list-decoder launch per chunk: stage_times() adds up
 d = torch.from_numpy(pcm).cuda()
 out = torch.empty((n, M.PAYLOAD_BYTES), dtype=torch.uint8, device="cuda")
 st = torch.empty((n, 112), dtype=torch.uint8, device="cuda")

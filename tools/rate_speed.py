@@ -13,6 +13,7 @@ pcm_u, ns, pay_u = O.encode_batch(uniq, seed0=5, rate=rate, mode=mode, stride=st
 idx = np.arange(n) % uniq
 pcm = torch.from_numpy(pcm_u)[torch.from_numpy(idx)].cuda()
 rx = M.Receiver(max_frames=n, max_samples=stride, rate=rate)
+rx.set_option("sub_chunks", 1)   # one list-decoder launch per chunk: stage_times() adds up
 payload = torch.empty((n, M.PAYLOAD_BYTES), dtype=torch.uint8, device="cuda")
 status = torch.empty((n, 112), dtype=torch.uint8, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
