@@ -81,8 +81,8 @@ typedef struct ofdmrx_frame_status {
 int ofdmrx_create(ofdmrx_t **h, int device, int rate_hz, int max_frames, int max_samples_per_frame);
 void ofdmrx_destroy(ofdmrx_t *h);
 
-/* Tunables / test switches: "keep_taps" (0/1, default 0), "scl_ctas_per_sm" (resident list-decoder warps per SM, 1..17,
- * before the first decode), "polar_table" (0: modes 6..9, 1: modes 10..13 — code table used by ofdmrx_polar_decode). */
+/* Tunables / test switches: "keep_taps" (0/1, default 0), "scl_ctas_per_sm" (resident list-decoder warps per SM, 1..occupancy,
+ * before the first decode; default: the occupancy limit, 21), "polar_table" (0: modes 6..9, 1: modes 10..13 — code table used by ofdmrx_polar_decode). */
 int ofdmrx_set_option(ofdmrx_t *h, const char *key, int value);
 
 /* Replaces: one `decode OUTPUT INPUT [SKIP]` invocation per window (decode.cc:375-556 + the de-scrambling of

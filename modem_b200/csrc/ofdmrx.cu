@@ -85,7 +85,9 @@ int ensure_scl_scratch(ofdmrx_handle *h)
 	if (h->d_A) return 0;
 	int occ = scl_occupancy_ctas_per_sm();
 	if (occ < 1) occ = 1;
-	int want = h->scl_ctas_per_sm > 0 ? h->scl_ctas_per_sm : kSclCtasPerSm;
+	// as many one-warp CTAs as the SM holds (21 at 96 registers): the kernel is compiled for at least kSclCtasPerSm = 17, which one
+	// pass over 10 000 codewords needs; the extra residency lets batches of up to 12 400 codewords finish in one pass as well
+	int want = h->scl_ctas_per_sm > 0 ? h->scl_ctas_per_sm : occ;
 	if (const char *e = std::getenv("OFDMRX_SCL_CTAS_PER_SM")) want = std::atoi(e);
 	if (want > occ) want = occ;
 	if (want < 1) want = 1;
@@ -97,6 +99,7 @@ int ensure_scl_scratch(ofdmrx_handle *h)
 	while (h->scl_grid > 1 && (h->scl_grid - 1) * (kSclThreads / 32) >= need_warps) { --h->scl_grid; }
 	warps = h->scl_grid * (kSclThreads / 32);
 	h->scl_warps = warps;
+	if (std::getenv("OFDMRX_DEBUG")) std::fprintf(stderr, "ofdmrx: list decoder occupancy %d CTAs per SM, grid %d one-warp CTAs\n", occ, h->scl_grid);
 	// per warp: alpha levels 6..13 back to back (2.1 MB; polar.cuh) + the beta words
 	if (int r = dev_alloc(&h->d_A, (size_t)warps * kSclWarpFloats)) return r;
 	if (int r = dev_alloc(&h->d_B, (size_t)warps * kSclWarpWords)) return r;

@@ -301,12 +301,24 @@ __device__ __forceinline__ float r0_acc(float m, float4 v)
 __device__ __forceinline__ float min_abs4(float m, float4 v) { return fminf(fminf(m, fabsf(v.x)), fminf(fminf(fabsf(v.y), fabsf(v.z)), fabsf(v.w))); }
 __device__ __forceinline__ uint32_t neg_bits4(float4 v) { return (v.x < 0.f ? 1u : 0u) | (v.y < 0.f ? 2u : 0u) | (v.z < 0.f ? 4u : 0u) | (v.w < 0.f ? 8u : 0u); }
 
+// L2 residency: a warp's rows of the low levels are re-read within microseconds and fit the 126 MB L2 for all resident warps
+// (clean frames: 15 KB per warp up to level 9); the channel values (read eight times per codeword, 2.6 GB per 10 000) and the
+// rows of the top levels stream through once per use.  Loads and stores of levels >= kSclStreamLevel and all channel loads
+// carry the evict-first / streaming hint so that they do not push the low levels out.
+#ifndef OFDMRX_SCL_STREAM_LEVEL
+#define OFDMRX_SCL_STREAM_LEVEL 11
+#endif
+constexpr int kSclStreamLevel = OFDMRX_SCL_STREAM_LEVEL; // 99 = no hints (A/B switch)
+__device__ __forceinline__ float4 ld_row(const float4 *p, bool stream) { return stream ? __ldcs(p) : *p; }
+__device__ __forceinline__ float4 ld_chan(const float4 *p) { return kSclStreamLevel < 99 ? __ldcs(p) : __ldg(p); }
+
 // ---- storage of the levels above the words -------------------------------------------------------------------------
 // level l (6..13) of codeword group `gbase` (= codeword * 8), slot s, quad q  ->  A[scl_off4(l) + ((gbase + s) << (l - 2)) + q]
 __device__ __forceinline__ float4 *lvl_row(float4 *A, int l, int gslot) { return A + scl_off4(l) + ((size_t)gslot << (l - 2)); }
 __device__ __forceinline__ void st_lvl(float4 *A, float4 *S5, int l, int gslot, int q, float4 v)
 {
 	if (l == 5) S5[q * kS5Pitch + gslot] = v;
+	else if (l >= kSclStreamLevel) __stcs(&lvl_row(A, l, gslot)[q], v);
 	else lvl_row(A, l, gslot)[q] = v;
 }
 
@@ -355,9 +367,10 @@ __device__ __forceinline__ void fused_op(float4 *A, float4 *S5, const uint32_t *
 					const int qa = q0 + 2 * stride, qb = qa + second;
 					prefetch_l1(&P[qa]); prefetch_l1(&P[qa + hq]); prefetch_l1(&P[qb]); prefetch_l1(&P[qb + hq]);
 				}
-				const float4 pa0 = P[q0], pb0 = P[q0 + hq];
+				const bool strm = l >= kSclStreamLevel;
+				const float4 pa0 = ld_row(&P[q0], strm), pb0 = ld_row(&P[q0 + hq], strm);
 				float4 pa1 = pa0, pb1 = pb0;
-				if (two) { pa1 = P[q1]; pb1 = P[q1 + hq]; }
+				if (two) { pa1 = ld_row(&P[q1], strm); pb1 = ld_row(&P[q1 + hq], strm); }
 				float4 v0, v1;
 				if (is_g) {
 					const uint32_t w0 = Bw[q0 >> 3], w1 = two ? Bw[q1 >> 3] : 0u;
@@ -407,7 +420,7 @@ __device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32
 					const int q = q0 + 1024 * h, wq = q >> 3;
 					float4 c[8];
 #pragma unroll
-					for (int kk = 0; kk < 8; ++kk) c[kk] = __ldg(&C4[q + 2048 * kk]);
+					for (int kk = 0; kk < 8; ++kk) c[kk] = ld_chan(&C4[q + 2048 * kk]);
 					float4 x[4], y[2];
 					if (j2) {
 #pragma unroll
@@ -424,9 +437,9 @@ __device__ __forceinline__ void top_op(float4 *A, const float4 *C4, const uint32
 						for (int mm = 0; mm < 2; ++mm) y[mm] = f_op4(x[mm], x[mm + 2]);
 					}
 					z[h] = j0 ? g_op4(y[0], y[1], (B13[wq] >> sh) & 15u) : f_op4(y[0], y[1]);
-					D13[q] = z[h];
+					if (13 >= kSclStreamLevel) __stcs(&D13[q], z[h]); else D13[q] = z[h];
 				}
-				D12[q0] = f_op4(z[0], z[1]);
+				if (12 >= kSclStreamLevel) __stcs(&D12[q0], f_op4(z[0], z[1])); else D12[q0] = f_op4(z[0], z[1]);
 			}
 		}
 	}
@@ -702,7 +715,7 @@ __global__ void __launch_bounds__(kSclThreads, kSclCtasPerSm) k_polar_scl(SclPar
 					const uint32_t x = Bwin[w];
 					uint32_t neg = 0; // channel hard decisions of the word (decode.cc:549-552)
 #pragma unroll
-					for (int q = 0; q < 8; ++q) neg |= neg_bits4(__ldg(&C4[w * 8 + q])) << (4 * q);
+					for (int q = 0; q < 8; ++q) neg |= neg_bits4(ld_chan(&C4[w * 8 + q])) << (4 * q);
 					uint64_t mbits = x;
 					int k = 32;
 					if (fr != 0xffffffffu || base + 32 > kDataBits) {
