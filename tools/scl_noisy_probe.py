@@ -1,0 +1,28 @@
+"""Developer probe (gpurun, optionally under ncu): the list decoder on 10 000 device-generated windows of one impairment class.
+IMP = clean | chain | awgn25 | awgn18"""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import modem_b200 as M
+n = int(os.environ.get("FRAMES", "10000"))
+kind = os.environ.get("IMP", "chain")
+imp = {"clean": None, "chain": M.impairments(multipath=True, cfo_hz=234.567, sfo_ppm=147.0, awgn_db=-30.0, seed=5),
+       "awgn25": M.impairments(awgn_db=-25.0, seed=6), "awgn18": M.impairments(awgn_db=-18.0, seed=7)}[kind]
+tx = M.Transmitter(max_windows=2048)
+stride = tx.window_samples(6) + 64
+rx = M.Receiver(max_frames=n, max_samples=stride)
+cs = int(M.load().ofdmtx_call_sign(b"CALLSIGN"))
+s = torch.cuda.current_stream().cuda_stream
+sent = torch.randint(0, 256, (n, M.PAYLOAD_BYTES), dtype=torch.uint8, device="cuda")
+pcm = torch.zeros((n, 2 * stride), dtype=torch.int16, device="cuda")
+tx.encode_raw(sent.data_ptr(), M.MEM_DEVICE, n, 6, cs, 2000, imp, pcm.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, stride, None, s)
+pay = torch.empty((n, M.PAYLOAD_BYTES), dtype=torch.uint8, device="cuda"); st = torch.empty((n, 112), dtype=torch.uint8, device="cuda")
+for _ in range(3):
+    rx.decode_raw(pcm.data_ptr(), M.MEM_DEVICE, M.FMT_S16_IQ, n, stride, None, 0, pay.data_ptr(), st.data_ptr(), s)
+torch.cuda.synchronize()
+ms, _ = rx.stage_times()
+stat = st.cpu().numpy().view(M.STATUS_DTYPE).reshape(-1)
+ok = stat["status"] == 0
+err = int(np.unpackbits((pay ^ sent).cpu().numpy()[ok]).sum())
+print("%s: %d windows, ok %d, bit errors %d, stage ms %s" % (kind, n, int(ok.sum()), err, {k: round(v, 2) for k, v in ms.items()}), flush=True)
