@@ -266,14 +266,15 @@ def main():
     e2e_ms, e2e_mode = e2e_serial_ms, "one handle, calls back to back"
     if os.environ.get("BENCH_E2E_PIPELINE", "1") != "0":
         try:
-            e2e_pipelined(2)
+            e2e_pipelined(n_handles)
             barrier()
+            e2e_calls = n_handles * ((args.steps + n_handles - 1) // n_handles)   # every handle makes the same number of calls
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()                      # device idle after the barrier: start of the timed region
-            e2e_pipelined(args.steps)         # every call returns with its results in host memory
+            e2e_pipelined(e2e_calls)          # every call returns with its results in host memory
             ev1.record()
             barrier()
-            dt = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+            dt = torch.tensor([ev0.elapsed_time(ev1) * args.steps / e2e_calls], device="cuda")   # scaled to `steps` calls
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             e2e_err += sum(int(np.unpackbits(j[1].numpy() ^ sent, axis=1).sum()) for j in e2e_state["jobs"][1:args.steps]) if args.steps > 1 else 0
