@@ -32,9 +32,9 @@ constexpr int kDmThreads = 320; // one radix-4 butterfly of the FFT-1280 per thr
 // per-row geometry of the Theil-Sen estimator: n carriers at x = i - n/2 (decode.cc:452,484), ranks as std::nth_element
 // is asked for them (element count/2 of the n(n-1)/2 slopes and of the n intercepts; mode 6: 432 -> 93 096 / 46 548 / 216)
 struct TsDims {
-	int n, half, nblk, pairs, rank_slope, rank_yint;
+	int n, half, nblk, pairs, rank_slope, rank_yint, np;
 	__device__ explicit TsDims(int cols) : n(cols), half(cols / 2), nblk((cols + 31) >> 5), pairs(cols * (cols - 1) / 2),
-		rank_slope(cols * (cols - 1) / 4), rank_yint(cols / 2) {}
+		rank_slope(cols * (cols - 1) / 4), rank_yint(cols / 2), np(cols > 256 ? 512 : cols > 128 ? 256 : cols > 64 ? 128 : 64) {} // np: power of two >= 64 holding the columns
 };
 
 __device__ __forceinline__ int f2ord(float v) { const int i = __float_as_int(v); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -143,6 +143,30 @@ constexpr int kTsRows = kTsPad / 32;   // up to 16 row blocks: lane L owns carri
 
 constexpr int kTsCandCap = 1280;       // in-bracket quotients kept for the final select
 
+// The pair sweep comes in two forms (A/B switch, §3.1 of DESIGN.md): 1 = merge sweep (a merge sort over the columns that
+// counts the pairs below the bracket while it merges), 0 = chunk sweep (32-column chunks sorted once, one binary search per
+// (row, chunk)).
+#ifndef OFDMRX_TS_MERGE
+#define OFDMRX_TS_MERGE 1
+#endif
+
+#if OFDMRX_TS_MERGE
+struct TsSweep {
+	float u[kTsPad];                   // u_k = y_k - blo x_k by column (+inf beyond the row's carriers)
+	uint16_t ia[kTsPad], ib[kTsPad];   // the columns in ascending u inside blocks of 32, 64, ... (ping-pong between merge levels)
+};
+struct TsShared {
+	float y[kTsPad];
+	union {
+		TsSweep sw;
+		int hist[256];                 // after the sweep: scratch of the selects
+	};
+	int cand[kTsCandCap];              // ordered-int images of the exact in-bracket quotients; later the intercepts
+	int ncand;                         // in-bracket quotients found by the sweep (may exceed kTsCandCap: counted, not stored)
+	int pad_[3];
+};
+static_assert(sizeof(TsShared) == 11280, "11 KB per row: five 4-warp CTAs (20 rows in flight) per SM");
+#else
 struct TsSweep {                       // per sweep: every 32-column chunk sorted by u
 	float2 suv[kTsPad];                // (u, v) of the chunk's columns in ascending u
 	uint16_t sj[kTsPad];               // original column of each sorted entry
@@ -160,6 +184,7 @@ struct TsShared {
 };
 static_assert(sizeof(TsSweep) >= kTsCandCap * sizeof(int) && sizeof(TsSweep) >= kTsPad * sizeof(int), "candidate / intercept scratch");
 static_assert(sizeof(TsShared) == 11264, "11 KB per row: five 4-warp CTAs (20 rows in flight) per SM");
+#endif
 
 // k-th smallest (0-based) of the n values v[] (shared memory of this warp; order-preserving integer images of
 // floats, see f2ord), exact: radix select, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
@@ -265,6 +290,149 @@ __device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int
 	return __shfl_sync(FULL, mine_v, __ffs(hit) - 1);
 }
 
+#if OFDMRX_TS_MERGE
+// ---- the pair sweep, merge form -----------------------------------------------------------------------------------
+// With u_k = y_k - blo x_k a pair (i < j) lies below the bracket iff u_j < u_i - eps and inside it (or within the rounding
+// margin eps of an edge) iff u_i - eps <= u_j and u_j - u_i < w (x_j - x_i) + eps, w = bhi - blo >= 0 — two compares and no
+// division; eps covers the roundings of u and of the reference's own fl(fl(y_j - y_i) / d).  Counting the pairs below is
+// counting inversions, which a merge sort does on the side: the columns are sorted by u inside every block of 32 (a warp
+// bitonic sort in registers; its own 496 pairs are settled there with shuffles and a prefix bit-set of column offsets), then
+// blocks are merged 32 -> 64 -> ... -> np.  In a merge every column i of the LEFT block meets the right block's pointer at
+// "number of right columns with u_j < u_i", all of which have j > i: that is its count (minus the few within eps, which are
+// examined), and the right columns that follow while u_j - u_i < w (x_max(right) - x_i) + eps are its in-bracket candidates.
+// Each lane merges np / 32 consecutive outputs of a level after one co-rank search for where its piece starts.
+// Candidates are evaluated on the spot as IEEE quotients, exactly as the reference forms them.
+// ~n log n steps per row instead of one binary search per (column, chunk of 32): n^2 / 64 searches.
+__device__ __forceinline__ void ts_candidate(TsShared &s, int i, int j, float blo, float bhi, int &cb)
+{
+	const float q = __fdiv_rn(s.y[j] - s.y[i], (float)(j - i));
+	if (q < blo) ++cb;
+	else if (q < bhi) {
+		const int slot = atomicAdd(&s.ncand, 1);
+		if (slot < kTsCandCap) s.cand[slot] = f2ord(q);
+	}
+}
+
+// all pairs: returns this lane's count of pairs below the bracket (exact: every pair in doubt was evaluated); the in-bracket
+// quotients are in s.cand[0 .. min(s.ncand, kTsCandCap))
+__device__ __forceinline__ int ts_sweep_merge(TsShared &s, const TsDims &d, int lane, float blo, float bhi, float eps)
+{
+	const float inf = __int_as_float(0x7f800000);
+	const float w = bhi - blo;
+	int cb = 0;
+	if (lane == 0) s.ncand = 0;
+	__syncwarp();
+	// ---- blocks of 32: sort, and the pairs inside the block
+	const float win32 = fmaf(w, 31.f, eps);
+#pragma unroll 1
+	for (int K = 0; K < (d.np >> 5); ++K) {
+		const int j = 32 * K + lane;
+		float key = j < d.n ? fmaf(-blo, (float)(j - d.half), s.y[j]) : inf;
+		s.sw.u[j] = key;
+		if (K >= d.nblk) { s.sw.ia[j] = (uint16_t)j; continue; } // padding only
+		int idx = lane;
+		// bitonic sort of (key, idx) across the warp, ascending
+#pragma unroll
+		for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+			for (int dd = k >> 1; dd > 0; dd >>= 1) {
+				const float ok = __shfl_xor_sync(FULL, key, dd);
+				const int oi = __shfl_xor_sync(FULL, idx, dd);
+				const bool keep_min = ((lane & dd) == 0) == ((lane & k) == 0);
+				const bool other_less = ok < key || (ok == key && oi < idx);
+				if (keep_min == other_less) { key = ok; idx = oi; }
+			}
+		}
+		s.sw.ia[j] = (uint16_t)(32 * K + idx);
+		// the lane now stands for column 32 K + idx (u = key) at sorted position `lane`; partners are the columns of larger
+		// offset.  Sorted neighbours below that are within eps are examined, the rest below are counted by offset.
+		const bool real = key < inf;
+		uint32_t pm = 1u << idx; // offsets among the sorted positions 0..lane
+#pragma unroll
+		for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULL, pm, dd); if (lane >= dd) pm |= o; }
+		int P = lane; // sorted positions 0..P-1 hold u < key - eps
+#pragma unroll 1
+		for (int sft = 1; sft < 32; ++sft) {
+			const float kk = __shfl_up_sync(FULL, key, sft);
+			const int ii = __shfl_up_sync(FULL, idx, sft);
+			const bool near = real && lane >= sft && kk >= key - eps;
+			if (!__any_sync(FULL, near)) break;
+			if (near) {
+				P = lane - sft;
+				if (ii > idx) ts_candidate(s, 32 * K + idx, 32 * K + ii, blo, bhi, cb);
+			}
+		}
+		const uint32_t first_p = __shfl_sync(FULL, pm, max(P - 1, 0));
+		if (real && P > 0) cb += __popc(first_p & (idx == 31 ? 0u : 0xfffffffeu << idx));
+#pragma unroll 1
+		for (int sft = 1; sft < 32; ++sft) {
+			const float kk = __shfl_down_sync(FULL, key, sft);
+			const int ii = __shfl_down_sync(FULL, idx, sft);
+			const bool inwin = real && lane + sft < 32 && kk - key < win32;
+			if (!__any_sync(FULL, inwin)) break;
+			if (inwin && ii > idx && kk - key < fmaf(w, (float)(ii - idx), eps)) ts_candidate(s, 32 * K + idx, 32 * K + ii, blo, bhi, cb);
+		}
+	}
+	__syncwarp();
+	// ---- merges: pairs with i in the left block, j in the right block
+	uint16_t *src = s.sw.ia, *dst = s.sw.ib;
+	const int per = d.np >> 5, g0 = lane * per;
+#pragma unroll 1
+	for (int m = 32; m < d.np; m <<= 1) {
+		const int base = g0 & ~(2 * m - 1), o = g0 - base;
+		if (base + m < d.n) { // (else: no real column in the right block, the block is sorted as it stands)
+			const uint16_t *Lp = src + base, *Rp = Lp + m;
+			// co-rank: the first o outputs of the stable merge (left first on ties) are left[0..ia) and right[0..ib)
+			int lo = max(0, o - m), hi = min(o, m);
+			while (lo < hi) {
+				const int mid = (lo + hi) >> 1;
+				if (s.sw.u[Rp[o - mid - 1]] >= s.sw.u[Lp[mid]]) lo = mid + 1; else hi = mid;
+			}
+			int ia = lo, ib = o - lo;
+			int cL = ia < m ? Lp[ia] : 0, cR = ib < m ? Rp[ib] : 0;
+			float uL = ia < m ? s.sw.u[cL] : inf, uR = ib < m ? s.sw.u[cR] : inf;
+			float uprev = ib > 0 ? s.sw.u[Rp[ib - 1]] : -inf; // u of right[ib - 1]
+			const int jmax = base + 2 * m - 1;
+#pragma unroll 1
+			for (int k = 0; k < per; ++k) {
+				if (ia < m && (ib >= m || uL <= uR)) {
+					if (cL < d.n) {
+						// ib right columns have u_j < u_i: below the bracket, except those within eps
+						int t = ib;
+						if (uprev >= uL - eps) {
+							while (t > 0) {
+								const int cj = Rp[t - 1];
+								if (!(s.sw.u[cj] >= uL - eps)) break;
+								ts_candidate(s, cL, cj, blo, bhi, cb);
+								--t;
+							}
+						}
+						cb += t;
+						const float win = fmaf(w, (float)(jmax - cL), eps);
+						int tt = ib, cj = cR;
+						float uj = uR;
+						while (tt < m && uj - uL < win) {
+							if (uj - uL < fmaf(w, (float)(cj - cL), eps)) ts_candidate(s, cL, cj, blo, bhi, cb);
+							if (++tt < m) { cj = Rp[tt]; uj = s.sw.u[cj]; }
+						}
+					}
+					dst[g0 + k] = (uint16_t)cL;
+					if (++ia < m) { cL = Lp[ia]; uL = s.sw.u[cL]; } else uL = inf;
+				} else {
+					dst[g0 + k] = (uint16_t)cR;
+					uprev = uR;
+					if (++ib < m) { cR = Rp[ib]; uR = s.sw.u[cR]; } else uR = inf;
+				}
+			}
+		} else {
+			for (int k = 0; k < per; ++k) dst[g0 + k] = src[g0 + k];
+		}
+		__syncwarp();
+		uint16_t *tmp = src; src = dst; dst = tmp;
+	}
+	return cb;
+}
+#else
 // ---- the pair sweep ---------------------------------------------------------------------------------------------
 // With u_k = y_k - blo x_k and v_k = y_k - bhi x_k a pair (i < j) lies below the bracket iff u_j < a_i = u_i - eps and
 // inside it (or within the rounding margin eps of an edge) iff additionally v_j < c_i = v_i + eps.  The columns are
@@ -357,6 +525,7 @@ __device__ __forceinline__ int sweep_pairs(TsShared &s, const TsDims &d, int lan
 	}
 	return cb;
 }
+#endif
 
 // fallback for rows that defeat the bracket search: smallest value T with #(quotient <= T) > rank, by a binary
 // search over the ordered-int image of the floats with an exact count (one IEEE division per pair) per step.
@@ -490,6 +659,13 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 		// |u_k| rounding (fma, <= 2^-24 |u|) on both sides plus the two roundings of the reference's quotient
 		const float eps = 6e-7f * (yabs + 432.f * bmax) + 1e-30f;
 		__syncwarp();
+#if OFDMRX_TS_MERGE
+		int cb = ts_sweep_merge(s, d, lane, blo, bhi, eps);
+		__syncwarp();
+		const float width = bhi - blo;
+		{
+			const int nin = s.ncand;
+#else
 		ts_sort_chunks(s, d, lane, blo, bhi);
 		int nql = 0; // pairs this lane queued
 		int cb = sweep_pairs(s, d, lane, blo, bhi, eps, nql);
@@ -530,6 +706,7 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 				if (in && slot < kTsCandCap) s.cand[slot] = f2ord(q);
 				nin += __popc(bal);
 			}
+#endif
 			cb = __reduce_add_sync(FULL, cb);
 			__syncwarp();
 			const int kk = d.rank_slope - cb;
