@@ -32,9 +32,9 @@ constexpr int kDmThreads = 320; // one radix-4 butterfly of the FFT-1280 per thr
 // per-row geometry of the Theil-Sen estimator: n carriers at x = i - n/2 (decode.cc:452,484), ranks as std::nth_element
 // is asked for them (element count/2 of the n(n-1)/2 slopes and of the n intercepts; mode 6: 432 -> 93 096 / 46 548 / 216)
 struct TsDims {
-	int n, half, nblk, pairs, rank_slope, rank_yint, np;
+	int n, half, nblk, pairs, rank_slope, rank_yint;
 	__device__ explicit TsDims(int cols) : n(cols), half(cols / 2), nblk((cols + 31) >> 5), pairs(cols * (cols - 1) / 2),
-		rank_slope(cols * (cols - 1) / 4), rank_yint(cols / 2), np(cols > 256 ? 512 : cols > 128 ? 256 : cols > 64 ? 128 : 64) {} // np: power of two >= 64 holding the columns
+		rank_slope(cols * (cols - 1) / 4), rank_yint(cols / 2) {}
 };
 
 __device__ __forceinline__ int f2ord(float v) { const int i = __float_as_int(v); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -143,33 +143,11 @@ constexpr int kTsRows = kTsPad / 32;   // up to 16 row blocks: lane L owns carri
 
 constexpr int kTsCandCap = 1280;       // in-bracket quotients kept for the final select
 
-// The pair sweep comes in two forms (A/B switch, §3.1 of DESIGN.md): 1 = merge sweep (a merge sort over the columns that
-// counts the pairs below the bracket while it merges), 0 = chunk sweep (32-column chunks sorted once, one binary search per
-// (row, chunk)).
-#ifndef OFDMRX_TS_MERGE
-#define OFDMRX_TS_MERGE 1
-#endif
-
-#if OFDMRX_TS_MERGE
-struct TsSweep {
-	float u[kTsPad];                   // u_k = y_k - blo x_k by column (+inf beyond the row's carriers)
-	uint16_t ia[kTsPad], ib[kTsPad];   // the columns in ascending u inside blocks of 32, 64, ... (ping-pong between merge levels)
-};
-struct TsShared {
-	float y[kTsPad];
-	union {
-		TsSweep sw;
-		int hist[256];                 // after the sweep: scratch of the selects
-	};
-	int cand[kTsCandCap];              // ordered-int images of the exact in-bracket quotients; later the intercepts
-	int ncand;                         // in-bracket quotients found by the sweep (may exceed kTsCandCap: counted, not stored)
-	int pad_[3];
-};
-static_assert(sizeof(TsShared) == 11280, "11 KB per row: five 4-warp CTAs (20 rows in flight) per SM");
-#else
+constexpr int kTsTaskCap = 16;         // scan continuations a lane can park per sweep (beyond that they run on the spot)
 struct TsSweep {                       // per sweep: every 32-column chunk sorted by u
-	float2 suv[kTsPad];                // (u, v) of the chunk's columns in ascending u
+	float su[kTsPad];                  // u of the chunk's columns in ascending order
 	uint16_t sj[kTsPad];               // original column of each sorted entry
+	uint16_t task[32 * kTsTaskCap];    // parked scans (row block << 9 | chunk << 5 | sorted position), one private list per lane
 };
 struct TsShared {
 	float y[kTsPad];
@@ -182,9 +160,8 @@ struct TsShared {
 		int hist[256];                 // after their evaluation: scratch of the radix selects
 	};
 };
-static_assert(sizeof(TsSweep) >= kTsCandCap * sizeof(int) && sizeof(TsSweep) >= kTsPad * sizeof(int), "candidate / intercept scratch");
+static_assert(sizeof(TsSweep) <= kTsCandCap * sizeof(int) && kTsCandCap >= kTsPad, "the sweep scratch sits under the candidate / intercept scratch");
 static_assert(sizeof(TsShared) == 11264, "11 KB per row: five 4-warp CTAs (20 rows in flight) per SM");
-#endif
 
 // k-th smallest (0-based) of the n values v[] (shared memory of this warp; order-preserving integer images of
 // floats, see f2ord), exact: radix select, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
@@ -290,167 +267,27 @@ __device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int
 	return __shfl_sync(FULL, mine_v, __ffs(hit) - 1);
 }
 
-#if OFDMRX_TS_MERGE
-// ---- the pair sweep, merge form -----------------------------------------------------------------------------------
-// With u_k = y_k - blo x_k a pair (i < j) lies below the bracket iff u_j < u_i - eps and inside it (or within the rounding
-// margin eps of an edge) iff u_i - eps <= u_j and u_j - u_i < w (x_j - x_i) + eps, w = bhi - blo >= 0 — two compares and no
-// division; eps covers the roundings of u and of the reference's own fl(fl(y_j - y_i) / d).  Counting the pairs below is
-// counting inversions, which a merge sort does on the side: the columns are sorted by u inside every block of 32 (a warp
-// bitonic sort in registers; its own 496 pairs are settled there with shuffles and a prefix bit-set of column offsets), then
-// blocks are merged 32 -> 64 -> ... -> np.  In a merge every column i of the LEFT block meets the right block's pointer at
-// "number of right columns with u_j < u_i", all of which have j > i: that is its count (minus the few within eps, which are
-// examined), and the right columns that follow while u_j - u_i < w (x_max(right) - x_i) + eps are its in-bracket candidates.
-// Each lane merges np / 32 consecutive outputs of a level after one co-rank search for where its piece starts.
-// Candidates are evaluated on the spot as IEEE quotients, exactly as the reference forms them.
-// ~n log n steps per row instead of one binary search per (column, chunk of 32): n^2 / 64 searches.
-__device__ __forceinline__ void ts_candidate(TsShared &s, int i, int j, float blo, float bhi, int &cb)
-{
-	const float q = __fdiv_rn(s.y[j] - s.y[i], (float)(j - i));
-	if (q < blo) ++cb;
-	else if (q < bhi) {
-		const int slot = atomicAdd(&s.ncand, 1);
-		if (slot < kTsCandCap) s.cand[slot] = f2ord(q);
-	}
-}
-
-// all pairs: returns this lane's count of pairs below the bracket (exact: every pair in doubt was evaluated); the in-bracket
-// quotients are in s.cand[0 .. min(s.ncand, kTsCandCap))
-__device__ __forceinline__ int ts_sweep_merge(TsShared &s, const TsDims &d, int lane, float blo, float bhi, float eps)
-{
-	const float inf = __int_as_float(0x7f800000);
-	const float w = bhi - blo;
-	int cb = 0;
-	if (lane == 0) s.ncand = 0;
-	__syncwarp();
-	// ---- blocks of 32: sort, and the pairs inside the block
-	const float win32 = fmaf(w, 31.f, eps);
-#pragma unroll 1
-	for (int K = 0; K < (d.np >> 5); ++K) {
-		const int j = 32 * K + lane;
-		float key = j < d.n ? fmaf(-blo, (float)(j - d.half), s.y[j]) : inf;
-		s.sw.u[j] = key;
-		if (K >= d.nblk) { s.sw.ia[j] = (uint16_t)j; continue; } // padding only
-		int idx = lane;
-		// bitonic sort of (key, idx) across the warp, ascending
-#pragma unroll
-		for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-			for (int dd = k >> 1; dd > 0; dd >>= 1) {
-				const float ok = __shfl_xor_sync(FULL, key, dd);
-				const int oi = __shfl_xor_sync(FULL, idx, dd);
-				const bool keep_min = ((lane & dd) == 0) == ((lane & k) == 0);
-				const bool other_less = ok < key || (ok == key && oi < idx);
-				if (keep_min == other_less) { key = ok; idx = oi; }
-			}
-		}
-		s.sw.ia[j] = (uint16_t)(32 * K + idx);
-		// the lane now stands for column 32 K + idx (u = key) at sorted position `lane`; partners are the columns of larger
-		// offset.  Sorted neighbours below that are within eps are examined, the rest below are counted by offset.
-		const bool real = key < inf;
-		uint32_t pm = 1u << idx; // offsets among the sorted positions 0..lane
-#pragma unroll
-		for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULL, pm, dd); if (lane >= dd) pm |= o; }
-		int P = lane; // sorted positions 0..P-1 hold u < key - eps
-#pragma unroll 1
-		for (int sft = 1; sft < 32; ++sft) {
-			const float kk = __shfl_up_sync(FULL, key, sft);
-			const int ii = __shfl_up_sync(FULL, idx, sft);
-			const bool near = real && lane >= sft && kk >= key - eps;
-			if (!__any_sync(FULL, near)) break;
-			if (near) {
-				P = lane - sft;
-				if (ii > idx) ts_candidate(s, 32 * K + idx, 32 * K + ii, blo, bhi, cb);
-			}
-		}
-		const uint32_t first_p = __shfl_sync(FULL, pm, max(P - 1, 0));
-		if (real && P > 0) cb += __popc(first_p & (idx == 31 ? 0u : 0xfffffffeu << idx));
-#pragma unroll 1
-		for (int sft = 1; sft < 32; ++sft) {
-			const float kk = __shfl_down_sync(FULL, key, sft);
-			const int ii = __shfl_down_sync(FULL, idx, sft);
-			const bool inwin = real && lane + sft < 32 && kk - key < win32;
-			if (!__any_sync(FULL, inwin)) break;
-			if (inwin && ii > idx && kk - key < fmaf(w, (float)(ii - idx), eps)) ts_candidate(s, 32 * K + idx, 32 * K + ii, blo, bhi, cb);
-		}
-	}
-	__syncwarp();
-	// ---- merges: pairs with i in the left block, j in the right block
-	uint16_t *src = s.sw.ia, *dst = s.sw.ib;
-	const int per = d.np >> 5, g0 = lane * per;
-#pragma unroll 1
-	for (int m = 32; m < d.np; m <<= 1) {
-		const int base = g0 & ~(2 * m - 1), o = g0 - base;
-		if (base + m < d.n) { // (else: no real column in the right block, the block is sorted as it stands)
-			const uint16_t *Lp = src + base, *Rp = Lp + m;
-			// co-rank: the first o outputs of the stable merge (left first on ties) are left[0..ia) and right[0..ib)
-			int lo = max(0, o - m), hi = min(o, m);
-			while (lo < hi) {
-				const int mid = (lo + hi) >> 1;
-				if (s.sw.u[Rp[o - mid - 1]] >= s.sw.u[Lp[mid]]) lo = mid + 1; else hi = mid;
-			}
-			int ia = lo, ib = o - lo;
-			int cL = ia < m ? Lp[ia] : 0, cR = ib < m ? Rp[ib] : 0;
-			float uL = ia < m ? s.sw.u[cL] : inf, uR = ib < m ? s.sw.u[cR] : inf;
-			float uprev = ib > 0 ? s.sw.u[Rp[ib - 1]] : -inf; // u of right[ib - 1]
-			const int jmax = base + 2 * m - 1;
-#pragma unroll 1
-			for (int k = 0; k < per; ++k) {
-				if (ia < m && (ib >= m || uL <= uR)) {
-					if (cL < d.n) {
-						// ib right columns have u_j < u_i: below the bracket, except those within eps
-						int t = ib;
-						if (uprev >= uL - eps) {
-							while (t > 0) {
-								const int cj = Rp[t - 1];
-								if (!(s.sw.u[cj] >= uL - eps)) break;
-								ts_candidate(s, cL, cj, blo, bhi, cb);
-								--t;
-							}
-						}
-						cb += t;
-						const float win = fmaf(w, (float)(jmax - cL), eps);
-						int tt = ib, cj = cR;
-						float uj = uR;
-						while (tt < m && uj - uL < win) {
-							if (uj - uL < fmaf(w, (float)(cj - cL), eps)) ts_candidate(s, cL, cj, blo, bhi, cb);
-							if (++tt < m) { cj = Rp[tt]; uj = s.sw.u[cj]; }
-						}
-					}
-					dst[g0 + k] = (uint16_t)cL;
-					if (++ia < m) { cL = Lp[ia]; uL = s.sw.u[cL]; } else uL = inf;
-				} else {
-					dst[g0 + k] = (uint16_t)cR;
-					uprev = uR;
-					if (++ib < m) { cR = Rp[ib]; uR = s.sw.u[cR]; } else uR = inf;
-				}
-			}
-		} else {
-			for (int k = 0; k < per; ++k) dst[g0 + k] = src[g0 + k];
-		}
-		__syncwarp();
-		uint16_t *tmp = src; src = dst; dst = tmp;
-	}
-	return cb;
-}
-#else
 // ---- the pair sweep ---------------------------------------------------------------------------------------------
-// With u_k = y_k - blo x_k and v_k = y_k - bhi x_k a pair (i < j) lies below the bracket iff u_j < a_i = u_i - eps and
-// inside it (or within the rounding margin eps of an edge) iff additionally v_j < c_i = v_i + eps.  The columns are
-// sorted by u inside every chunk of 32 (one warp bitonic sort per chunk), so for a row i and a chunk the count below
-// is a 6-step binary search instead of 32 compares, and the in-bracket columns are the few sorted entries that follow:
-// v_j < c_i needs u_j < c_i + w x_j <= c_i + w x_max(chunk), w = bhi - blo >= 0, which bounds the scan.  The chunk
-// holding i itself only counts columns j > i: a prefix bit-set over the sorted order (one warp scan per row block, kept
-// in registers) turns that into a shuffle and a popcount.
+// With u_k = y_k - blo x_k and w = bhi - blo >= 0 a pair (i < j) lies below the bracket iff u_j < a_i = u_i - eps and inside
+// it (or within the rounding margin eps of an edge) iff additionally u_j - u_i < w (x_j - x_i) + eps — compares only, no
+// division; eps covers the roundings of u and of the reference's own fl(fl(y_j - y_i) / d) with a factor > 2 to spare.
+// The columns are sorted by u inside every chunk of 32 (one warp bitonic sort per chunk), so for a row i and a chunk the
+// count below is a 6-step binary search instead of 32 compares, and the in-bracket columns are among the few sorted entries
+// that follow: u_j < t = u_i + w (x_max(chunk) - x_i) + 2 eps bounds the scan.  The chunk holding i itself only counts
+// columns j > i: a prefix bit-set over the sorted order (one warp scan per row block, kept in registers) turns that into a
+// shuffle and a popcount.
 // Lane L owns the rows i = 32 R + L; in-bracket pairs go to the lane's private sub-queue s.q[32 n + L].
-__device__ __forceinline__ void ts_sort_chunks(TsShared &s, const TsDims &d, int lane, float blo, float bhi)
+// A third of the (row, chunk) visits find an entry inside the scan bound, one in fourteen a second one — but a loop over
+// "my entries" runs as long as the slowest lane's for all 32 (3.7 trips on average: it was half of this function).  So a
+// visit examines the first entry in line, and a second entry inside the bound parks the rest of the scan in a per-lane task
+// list; the parked scans run afterwards in one flat loop where every lane advances its own list at its own pace.
+__device__ __forceinline__ void ts_sort_chunks(TsShared &s, const TsDims &d, int lane, float blo)
 {
 	const float inf = __int_as_float(0x7f800000);
 #pragma unroll 1
 	for (int K = 0; K < d.nblk; ++K) {
 		const int j = 32 * K + lane;
-		const float yj = s.y[j], x = (float)(j - d.half);
-		float key = j < d.n ? fmaf(-blo, x, yj) : inf;
-		const float v = j < d.n ? fmaf(-bhi, x, yj) : inf;
+		float key = j < d.n ? fmaf(-blo, (float)(j - d.half), s.y[j]) : inf;
 		int idx = lane;
 		// bitonic sort of (key, idx) across the warp, ascending
 #pragma unroll
@@ -464,68 +301,128 @@ __device__ __forceinline__ void ts_sort_chunks(TsShared &s, const TsDims &d, int
 				if (keep_min == other_less) { key = ok; idx = oi; }
 			}
 		}
-		const float vs = __shfl_sync(FULL, v, idx);
-		s.sw.suv[j] = make_float2(key, vs);
+		s.sw.su[j] = key;
 		s.sw.sj[j] = (uint16_t)(32 * K + idx);
 	}
 	__syncwarp();
 }
 
-// number of entries of the sorted chunk with u < a (0..32)
-__device__ __forceinline__ int ts_lower_bound(const float2 *chunk, float a)
+// number of entries of the sorted chunk with u < a (0..32), for two chunks at once (two independent chains of six dependent
+// shared-memory loads); one word per entry: 32 lanes hit 32 banks or the same word
+__device__ __forceinline__ void ts_lower_bound2(const float *c0, const float *c1, float a, int &p0, int &p1)
 {
-	int p = 0;
+	p0 = 0; p1 = 0;
 #pragma unroll
-	for (int st = 16; st > 0; st >>= 1) p += chunk[p + st - 1].x < a ? st : 0;
-	p += chunk[p].x < a ? 1 : 0; // p <= 31 here
-	return p;
+	for (int st = 16; st > 0; st >>= 1) {
+		const float e0 = c0[p0 + st - 1], e1 = c1[p1 + st - 1];
+		p0 += e0 < a ? st : 0;
+		p1 += e1 < a ? st : 0;
+	}
+	const float e0 = c0[p0], e1 = c1[p1]; // p <= 31 here
+	p0 += e0 < a ? 1 : 0;
+	p1 += e1 < a ? 1 : 0;
+}
+
+struct TsLane { int cb, nq, ntask; };
+
+// row i = 32 R + lane against chunk K, p = entries of the chunk below a: count, examine the first entry inside the scan
+// bound, park the scan if a second one follows
+__device__ __forceinline__ void ts_visit(TsShared &s, TsLane &ln, int lane, int R, int K, int p, int i, float ui, float w, float eps, uint32_t first_p_set)
+{
+	const float *chunk = s.sw.su + 32 * K;
+	ln.cb += K == R ? __popc(first_p_set) : p;
+	// in-bracket candidates: sorted entries from p on while u < t (rows beyond the carriers: t = -inf)
+	const float t = ui + fmaf(w, (float)(32 * K + 31 - i), eps + eps);
+	const float u0 = chunk[min(p, 31)];
+	if (p < 32 && u0 < t) {
+		const int j = s.sw.sj[32 * K + p];
+		if (u0 - ui < fmaf(w, (float)(j - i), eps) && (K != R || j > i)) {
+			if (ln.nq < kTsLaneCap) s.q[32 * ln.nq + lane] = (uint16_t)((R << 9) | j);
+			++ln.nq;
+		}
+		++p;
+		if (p < 32 && chunk[p] < t) {
+			if (ln.ntask < kTsTaskCap) {
+				s.sw.task[32 * ln.ntask + lane] = (uint16_t)((R << 9) | (K << 5) | p);
+				++ln.ntask;
+			} else { // (no room to park it: finish the scan here)
+				do {
+					const int jj = s.sw.sj[32 * K + p];
+					if (chunk[p] - ui < fmaf(w, (float)(jj - i), eps) && (K != R || jj > i)) {
+						if (ln.nq < kTsLaneCap) s.q[32 * ln.nq + lane] = (uint16_t)((R << 9) | jj);
+						++ln.nq;
+					}
+					++p;
+				} while (p < 32 && chunk[p] < t);
+			}
+		}
+	}
 }
 
 // all pairs: returns this lane's count of pairs definitely below the bracket; nq = pairs this lane queued
-// (searching several chunks at once for more loads in flight was tried and measured slower)
 __device__ __forceinline__ int sweep_pairs(TsShared &s, const TsDims &d, int lane, float blo, float bhi, float eps, int &nq)
 {
 	const float ninf = __int_as_float(0xff800000);
-	const float w = bhi - blo;
+	const float w = bhi - blo, eps2 = eps + eps;
 	const uint32_t above = lane == 31 ? 0u : 0xfffffffeu << lane; // column offsets beyond the lane's own
-	int cb = 0;
+	TsLane ln;
+	ln.cb = 0; ln.nq = nq; ln.ntask = 0;
 #pragma unroll 1
 	for (int R = 0; R < d.nblk; ++R) {
 		const int i = 32 * R + lane;
-		const float yi = s.y[i], x = (float)(i - d.half);
-		const float a = i < d.n ? fmaf(-blo, x, yi) - eps : ninf;
-		const float c = i < d.n ? fmaf(-bhi, x, yi) + eps : ninf;
+		const float ui = i < d.n ? fmaf(-blo, (float)(i - d.half), s.y[i]) : ninf; // (the value the sort stored for column i)
+		const float a = ui - eps;
 		// own chunk: set of in-chunk column offsets among the first p sorted entries, p = lane + 1 (inclusive scan)
 		uint32_t pm = 1u << (s.sw.sj[32 * R + lane] & 31);
 #pragma unroll
 		for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(FULL, pm, dd); if (lane >= dd) pm |= o; }
 #pragma unroll 1
-		for (int K = R; K < d.nblk; ++K) {
-			const float2 *chunk = s.sw.suv + 32 * K;
-			int p = ts_lower_bound(chunk, a);
+		for (int K = R; K < d.nblk; K += 2) {
+			const bool two = K + 1 < d.nblk; // (warp-uniform)
+			int p0, p1;
+			ts_lower_bound2(s.sw.su + 32 * K, s.sw.su + 32 * (two ? K + 1 : K), a, p0, p1);
+			uint32_t own = 0u;
 			if (K == R) {
-				const uint32_t first_p = __shfl_sync(FULL, pm, max(p - 1, 0)); // every lane takes part; p = 0 -> empty set
-				cb += __popc((p > 0 ? first_p : 0u) & above);
-			} else {
-				cb += p;
+				const uint32_t first_p = __shfl_sync(FULL, pm, max(p0 - 1, 0)); // every lane takes part; p = 0 -> empty set
+				own = (p0 > 0 ? first_p : 0u) & above;
 			}
-			// in-bracket candidates: sorted entries from p on while u < c + w x_max(K) (+ eps for the roundings of u and v)
-			const float t = c + fmaf(w, (float)(32 * K + 31 - d.half), eps);
-			while (p < 32) {
-				const float2 e = chunk[p];
-				if (!(e.x < t)) break;
+			ts_visit(s, ln, lane, R, K, p0, i, ui, w, eps, own);
+			if (two) ts_visit(s, ln, lane, R, K + 1, p1, i, ui, w, eps, 0u);
+		}
+	}
+	int ntask = ln.ntask;
+	nq = ln.nq;
+	int cb = ln.cb;
+	// the parked scans: entry p of chunk K is inside row i's bound
+	{
+		int tn = 0, R = 0, K = 0, p = 0, i = 0;
+		float ui = 0.f, t = 0.f;
+		bool have = false;
+		for (;;) {
+			if (!have && tn < ntask) {
+				const uint32_t code = s.sw.task[32 * tn + lane];
+				++tn;
+				R = (int)(code >> 9); K = (int)((code >> 5) & 15u); p = (int)(code & 31u);
+				i = 32 * R + lane;
+				ui = fmaf(-blo, (float)(i - d.half), s.y[i]);
+				t = ui + fmaf(w, (float)(32 * K + 31 - i), eps2);
+				have = true;
+			}
+			if (!__any_sync(FULL, have)) break;
+			if (have) {
+				const float uj = s.sw.su[32 * K + p];
 				const int j = s.sw.sj[32 * K + p];
-				if (e.y < c && (K != R || j > i)) {
+				if (uj - ui < fmaf(w, (float)(j - i), eps) && (K != R || j > i)) {
 					if (nq < kTsLaneCap) s.q[32 * nq + lane] = (uint16_t)((R << 9) | j);
 					++nq;
 				}
 				++p;
+				have = p < 32 && s.sw.su[32 * K + p] < t;
 			}
 		}
 	}
 	return cb;
 }
-#endif
 
 // fallback for rows that defeat the bracket search: smallest value T with #(quotient <= T) > rank, by a binary
 // search over the ordered-int image of the floats with an exact count (one IEEE division per pair) per step.
@@ -659,14 +556,7 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 		// |u_k| rounding (fma, <= 2^-24 |u|) on both sides plus the two roundings of the reference's quotient
 		const float eps = 6e-7f * (yabs + 432.f * bmax) + 1e-30f;
 		__syncwarp();
-#if OFDMRX_TS_MERGE
-		int cb = ts_sweep_merge(s, d, lane, blo, bhi, eps);
-		__syncwarp();
-		const float width = bhi - blo;
-		{
-			const int nin = s.ncand;
-#else
-		ts_sort_chunks(s, d, lane, blo, bhi);
+		ts_sort_chunks(s, d, lane, blo);
 		int nql = 0; // pairs this lane queued
 		int cb = sweep_pairs(s, d, lane, blo, bhi, eps, nql);
 		__syncwarp();
@@ -706,7 +596,6 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 				if (in && slot < kTsCandCap) s.cand[slot] = f2ord(q);
 				nin += __popc(bal);
 			}
-#endif
 			cb = __reduce_add_sync(FULL, cb);
 			__syncwarp();
 			const int kk = d.rank_slope - cb;
