@@ -142,6 +142,12 @@ constexpr int kTsPad = kMaxCols;       // 16 x 32 columns, the tail beyond the m
 constexpr int kTsRows = kTsPad / 32;   // up to 16 row blocks: lane L owns carriers i = 32 R + L
 
 constexpr int kTsCandCap = 1280;       // in-bracket quotients kept for the final select
+// The row's phase values: a copy in shared memory (1) or read where they lie through the read-only path (0).  Without the
+// copy a row needs 9 KB instead of 11 KB and six 4-warp CTAs fit an SM instead of five (A/B switch).
+#ifndef OFDMRX_TS_Y_SMEM
+#define OFDMRX_TS_Y_SMEM 0
+#endif
+constexpr int kTsCtasPerSm = OFDMRX_TS_Y_SMEM ? 5 : 6;
 
 constexpr int kTsTaskCap = 16;         // scan continuations a lane can park per sweep (beyond that they run on the spot)
 struct TsSweep {                       // per sweep: every 32-column chunk sorted by u
@@ -150,7 +156,9 @@ struct TsSweep {                       // per sweep: every 32-column chunk sorte
 	uint16_t task[32 * kTsTaskCap];    // parked scans (row block << 9 | chunk << 5 | sorted position), one private list per lane
 };
 struct TsShared {
+#if OFDMRX_TS_Y_SMEM
 	float y[kTsPad];
+#endif
 	union {
 		TsSweep sw;
 		int cand[kTsCandCap];          // after the sweep: ordered-int images of the exact in-bracket quotients
@@ -161,13 +169,15 @@ struct TsShared {
 	};
 };
 static_assert(sizeof(TsSweep) <= kTsCandCap * sizeof(int) && kTsCandCap >= kTsPad, "the sweep scratch sits under the candidate / intercept scratch");
-static_assert(sizeof(TsShared) == 11264, "11 KB per row: five 4-warp CTAs (20 rows in flight) per SM");
+static_assert(sizeof(TsShared) == (OFDMRX_TS_Y_SMEM ? 11264 : 9216), "11 KB per row: five 4-warp CTAs (20 rows in flight) per SM; 9 KB: six");
+static_assert(kTsCtasPerSm * (kTsWarps * sizeof(TsShared) + 1024) <= 228 * 1024, "shared memory of the resident CTAs");
 
 // k-th smallest (0-based) of the n values v[] (shared memory of this warp; order-preserving integer images of
 // floats, see f2ord), exact: radix select, 8 bits per level inside the [min,max] range; hist = 256 ints of warp scratch.
 __device__ __noinline__ int warp_select_radix(const int *v, int n, int k, int *hist, int lane)
 {
 	int mn = 0x7fffffff, mx = (int)0x80000000;
+#pragma unroll 1
 	for (int i = lane; i < n; i += 32) { const int o = v[i]; mn = min(mn, o); mx = max(mx, o); }
 	mn = __reduce_min_sync(FULL, mn);
 	mx = __reduce_max_sync(FULL, mx);
@@ -177,6 +187,7 @@ __device__ __noinline__ int warp_select_radix(const int *v, int n, int k, int *h
 #pragma unroll
 		for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0;
 		__syncwarp();
+#pragma unroll 1
 		for (int i = lane; i < n; i += 32) {
 			const unsigned b = ((unsigned)v[i] - (unsigned)lo) >> sh; // values below lo wrap to huge bins
 			if (b < 256u) atomicAdd(&hist[b], 1);
@@ -217,6 +228,7 @@ __device__ __noinline__ int warp_select_radix(const int *v, int n, int k, int *h
 __device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int lane)
 {
 	float mn = __int_as_float(0x7f800000), mx = -mn;
+#pragma unroll 2
 	for (int i = lane; i < n; i += 32) { const float x = ord2f(v[i]); mn = fminf(mn, x); mx = fmaxf(mx, x); }
 #pragma unroll
 	for (int d = 16; d; d >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL, mn, d)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d)); }
@@ -225,6 +237,7 @@ __device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int
 #pragma unroll
 	for (int b = 0; b < 8; ++b) hist[lane + 32 * b] = 0;
 	__syncwarp();
+#pragma unroll 2
 	for (int i = lane; i < n; i += 32) atomicAdd(&hist[min(255, __float2int_rz((ord2f(v[i]) - mn) * sc))], 1);
 	__syncwarp();
 	int h[8], sum = 0;
@@ -249,6 +262,7 @@ __device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int
 	kk = __shfl_sync(FULL, kk, src);
 	// members of that bucket, compacted to the front of v[] (reads run ahead of the writes: slot <= i)
 	int m = 0;
+#pragma unroll 1
 	for (int i0 = 0; i0 < n; i0 += 32) {
 		const int i = i0 + lane;
 		const int o = i < n ? v[i] : 0;
@@ -262,10 +276,18 @@ __device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int
 	if (m > 32) return warp_select_radix(v, m, kk, hist, lane);
 	const int mine_v = lane < m ? v[lane] : 0x7fffffff;
 	int rank = 0;
+#pragma unroll 2
 	for (int e = 0; e < m; ++e) { const int o = v[e]; rank += (o < mine_v) || (o == mine_v && e < lane); }
 	const unsigned hit = __ballot_sync(FULL, lane < m && rank == kk);
 	return __shfl_sync(FULL, mine_v, __ffs(hit) - 1);
 }
+
+// the row's phase values (valid indices only: 0 <= i < n)
+#if OFDMRX_TS_Y_SMEM
+#define TS_Y(i) s.y[i]
+#else
+#define TS_Y(i) __ldg(&yrow[i])
+#endif
 
 // ---- the pair sweep ---------------------------------------------------------------------------------------------
 // With u_k = y_k - blo x_k and w = bhi - blo >= 0 a pair (i < j) lies below the bracket iff u_j < a_i = u_i - eps and inside
@@ -281,13 +303,13 @@ __device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int
 // "my entries" runs as long as the slowest lane's for all 32 (3.7 trips on average: it was half of this function).  So a
 // visit examines the first entry in line, and a second entry inside the bound parks the rest of the scan in a per-lane task
 // list; the parked scans run afterwards in one flat loop where every lane advances its own list at its own pace.
-__device__ __forceinline__ void ts_sort_chunks(TsShared &s, const TsDims &d, int lane, float blo)
+__device__ __forceinline__ void ts_sort_chunks(TsShared &s, const float *yrow, const TsDims &d, int lane, float blo)
 {
 	const float inf = __int_as_float(0x7f800000);
 #pragma unroll 1
 	for (int K = 0; K < d.nblk; ++K) {
 		const int j = 32 * K + lane;
-		float key = j < d.n ? fmaf(-blo, (float)(j - d.half), s.y[j]) : inf;
+		float key = j < d.n ? fmaf(-blo, (float)(j - d.half), TS_Y(j)) : inf;
 		int idx = lane;
 		// bitonic sort of (key, idx) across the warp, ascending
 #pragma unroll
@@ -360,7 +382,7 @@ __device__ __forceinline__ void ts_visit(TsShared &s, TsLane &ln, int lane, int 
 }
 
 // all pairs: returns this lane's count of pairs definitely below the bracket; nq = pairs this lane queued
-__device__ __forceinline__ int sweep_pairs(TsShared &s, const TsDims &d, int lane, float blo, float bhi, float eps, int &nq)
+__device__ __forceinline__ int sweep_pairs(TsShared &s, const float *yrow, const TsDims &d, int lane, float blo, float bhi, float eps, int &nq)
 {
 	const float ninf = __int_as_float(0xff800000);
 	const float w = bhi - blo, eps2 = eps + eps;
@@ -370,7 +392,7 @@ __device__ __forceinline__ int sweep_pairs(TsShared &s, const TsDims &d, int lan
 #pragma unroll 1
 	for (int R = 0; R < d.nblk; ++R) {
 		const int i = 32 * R + lane;
-		const float ui = i < d.n ? fmaf(-blo, (float)(i - d.half), s.y[i]) : ninf; // (the value the sort stored for column i)
+		const float ui = i < d.n ? fmaf(-blo, (float)(i - d.half), TS_Y(i)) : ninf; // (the value the sort stored for column i)
 		const float a = ui - eps;
 		// own chunk: set of in-chunk column offsets among the first p sorted entries, p = lane + 1 (inclusive scan)
 		uint32_t pm = 1u << (s.sw.sj[32 * R + lane] & 31);
@@ -404,7 +426,7 @@ __device__ __forceinline__ int sweep_pairs(TsShared &s, const TsDims &d, int lan
 				++tn;
 				R = (int)(code >> 9); K = (int)((code >> 5) & 15u); p = (int)(code & 31u);
 				i = 32 * R + lane;
-				ui = fmaf(-blo, (float)(i - d.half), s.y[i]);
+				ui = fmaf(-blo, (float)(i - d.half), TS_Y(i));
 				t = ui + fmaf(w, (float)(32 * K + 31 - i), eps2);
 				have = true;
 			}
@@ -443,26 +465,28 @@ __device__ __noinline__ float ts_slope_bisect(const float *y, int n, int rank, i
 	return ord2f(lo);
 }
 
-// exact upper median of the pairwise slopes of (x = i - 216, y[i]); one warp, y in s.y (tail padded)
+// exact upper median of the pairwise slopes of (x = i - 216, y[i]); one warp, yrow = the row's n values
 // hint: expected (Theil-Sen - OLS) of this row, in slope units (0 = none); pilot_out / half_out: the OLS slope and the
 // bracket half-width used, for the caller's running estimate of that gap
-__device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, float hint, float half_k, float &pilot_out, float &half_out)
+__device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int lane, int &sweeps, float hint, float half_k, float &pilot_out, float &half_out)
 {
 	pilot_out = 0.f; half_out = 0.f;
-	// ---- pilot: least-squares line and residual spread (only steers the bracket, so fp32 sums are good enough)
-	float yv[kTsRows];
+	// ---- pilot: least-squares line and residual spread (only steers the bracket, so fp32 sums are good enough).
+	// The passes over the row are rolled loops that re-read the values (L1 / shared memory) instead of holding sixteen of them
+	// in registers under sixteen-fold unrolled code: this kernel runs out of instruction cache before anything else
+	// (7 200 instructions, 24 warps at different places of them).
 	float a0 = 0.f, a1 = 0.f;
 	float ymin = __int_as_float(0x7f800000), ymax = -ymin;
-#pragma unroll
-	for (int r = 0; r < kTsRows; ++r) {
+	const float x0 = (float)(lane - d.half) + 0.5f; // centred abscissa of column `lane`; column 32 r + lane: x0 + 32 r
+#pragma unroll 2
+	for (int r = 0; r < d.nblk; ++r) {
 		const int i = 32 * r + lane;
-		const bool ok = i < d.n;
-		yv[r] = ok ? s.y[i] : 0.f;
-		if (ok) {
-			a0 += yv[r];
-			a1 = fmaf((float)(i - d.half) + 0.5f, yv[r], a1);
-			ymin = fminf(ymin, yv[r]);
-			ymax = fmaxf(ymax, yv[r]);
+		if (i < d.n) {
+			const float yv = TS_Y(i);
+			a0 += yv;
+			a1 = fmaf(x0 + (float)(32 * r), yv, a1);
+			ymin = fminf(ymin, yv);
+			ymax = fmaxf(ymax, yv);
 		}
 	}
 #pragma unroll
@@ -473,15 +497,15 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 		ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, dd));
 	}
 	if (ymin == ymax) return 0.f; // erased row: every difference is 0, every quotient +0
-	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(s.y, d.n, d.rank_slope, lane); // non-finite input: stay total
+	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(yrow, d.n, d.rank_slope, lane); // non-finite input: stay total
 	const float sxx = (float)d.n * ((float)d.n * (float)d.n - 1.f) / 12.f;
 	float c0 = a1 / sxx, icpt = a0 / (float)d.n; // least-squares line through the centred abscissa x + 0.5
 	float r2 = 0.f;
-#pragma unroll
-	for (int r = 0; r < kTsRows; ++r) {
+#pragma unroll 2
+	for (int r = 0; r < d.nblk; ++r) {
 		const int i = 32 * r + lane;
 		if (i < d.n) {
-			const float e = yv[r] - icpt - c0 * ((float)(i - d.half) + 0.5f);
+			const float e = TS_Y(i) - icpt - c0 * (x0 + (float)(32 * r));
 			r2 = fmaf(e, e, r2);
 		}
 	}
@@ -498,11 +522,11 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 		for (int it = 0; it < 4; ++it) {
 			const float cap = kh * srob;
 			float acc = 0.f;
-#pragma unroll
-			for (int r = 0; r < kTsRows; ++r) {
+#pragma unroll 2
+			for (int r = 0; r < d.nblk; ++r) {
 				const int i = 32 * r + lane;
 				if (i < d.n) {
-					const float e = yv[r] - icpt - c0 * ((float)(i - d.half) + 0.5f);
+					const float e = TS_Y(i) - icpt - c0 * (x0 + (float)(32 * r));
 					acc += fminf(e * e, cap * cap);
 				}
 			}
@@ -511,15 +535,15 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 			srob = sqrtf(acc / ((float)d.n * beta));
 			const float lim = kh * srob;
 			float sw = 0.f, swx = 0.f, swy = 0.f, swxx = 0.f, swxy = 0.f;
-#pragma unroll
-			for (int r = 0; r < kTsRows; ++r) {
+#pragma unroll 2
+			for (int r = 0; r < d.nblk; ++r) {
 				const int i = 32 * r + lane;
 				if (i < d.n) {
-					const float x = (float)(i - d.half) + 0.5f;
-					const float e = fabsf(yv[r] - icpt - c0 * x);
+					const float x = x0 + (float)(32 * r), yv = TS_Y(i);
+					const float e = fabsf(yv - icpt - c0 * x);
 					const float w = e <= lim ? 1.f : __fdividef(lim, e);
-					sw += w; swx = fmaf(w, x, swx); swy = fmaf(w, yv[r], swy);
-					swxx = fmaf(w * x, x, swxx); swxy = fmaf(w * x, yv[r], swxy);
+					sw += w; swx = fmaf(w, x, swx); swy = fmaf(w, yv, swy);
+					swxx = fmaf(w * x, x, swxx); swxy = fmaf(w * x, yv, swxy);
 				}
 			}
 #pragma unroll
@@ -556,9 +580,9 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 		// |u_k| rounding (fma, <= 2^-24 |u|) on both sides plus the two roundings of the reference's quotient
 		const float eps = 6e-7f * (yabs + 432.f * bmax) + 1e-30f;
 		__syncwarp();
-		ts_sort_chunks(s, d, lane, blo);
+		ts_sort_chunks(s, yrow, d, lane, blo);
 		int nql = 0; // pairs this lane queued
-		int cb = sweep_pairs(s, d, lane, blo, bhi, eps, nql);
+		int cb = sweep_pairs(s, yrow, d, lane, blo, bhi, eps, nql);
 		__syncwarp();
 		const int nq = __reduce_add_sync(FULL, nql), nqmax = __reduce_max_sync(FULL, nql);
 		const float width = bhi - blo;
@@ -586,7 +610,7 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 				if (n < nql) {
 					const uint32_t code = s.q[32 * n + lane];
 					const int i = 32 * (int)(code >> 9) + lane, j = (int)(code & 511u);
-					q = __fdiv_rn(s.y[j] - s.y[i], (float)(j - i));
+					q = __fdiv_rn(TS_Y(j) - TS_Y(i), (float)(j - i));
 					if (q < blo) ++cb;
 					else in = q < bhi;
 				}
@@ -636,13 +660,13 @@ __device__ float ts_slope(TsShared &s, const TsDims &d, int lane, int &sweeps, f
 		if (!(blo < bhi)) break;
 	}
 	sweeps += 100;
-	return ts_slope_bisect(s.y, d.n, d.rank_slope, lane);
+	return ts_slope_bisect(yrow, d.n, d.rank_slope, lane);
 }
 
 // Work items: with a status array, item = (window f, chain c of n_chains): the chain walks a contiguous block of the window's
 // rows (row r: cols(mode) phase values at yph + f * kMaxCons + r * cols) one after the other.  Without a status array (test
 // hook) every item is one dense row of fixed_cols values.
-__global__ void __launch_bounds__(kTsWarps * 32, 5) k_theil_sen(const float *yph, FrameState *stv, int n_items, int n_chains, int fixed_cols, float half_k, float *ts_out)
+__global__ void __launch_bounds__(kTsWarps * 32, kTsCtasPerSm) k_theil_sen(const float *yph, FrameState *stv, int n_items, int n_chains, int fixed_cols, float half_k, float *ts_out)
 {
 	extern __shared__ __align__(16) unsigned char smraw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -666,25 +690,27 @@ __global__ void __launch_bounds__(kTsWarps * 32, 5) k_theil_sen(const float *yph
 		const TsDims d(cols);
 		const float gap = 0.f; // no re-centring: the Huber pilot leaves no systematic gap to the Theil-Sen slope
 		for (int r = r0; r < r1; ++r) {
-			const float *y = ybase + (size_t)r * cols;
+			const float *yrow = ybase + (size_t)r * cols;
 			__syncwarp();
+#if OFDMRX_TS_Y_SMEM
 #pragma unroll
 			for (int k = 0; k < kTsRows; ++k) {
 				const int i = 32 * k + lane;
-				s.y[i] = i < d.n ? y[i] : __int_as_float(0x7f800000);
+				s.y[i] = i < d.n ? yrow[i] : __int_as_float(0x7f800000);
 			}
 			__syncwarp();
+#endif
 			int sweeps = 0;
 			float pilot, half;
-			const float slope = ts_slope(s, d, lane, sweeps, gap, half_k, pilot, half);
+			const float slope = ts_slope(s, yrow, d, lane, sweeps, gap, half_k, pilot, half);
 			total_sweeps += sweeps;
 			// intercept: upper median of y_i - slope * x_i
 			__syncwarp();
 			int *z = s.cand;
-#pragma unroll
-			for (int k = 0; k < kTsRows; ++k) {
+#pragma unroll 2
+			for (int k = 0; k < d.nblk; ++k) {
 				const int i = 32 * k + lane;
-				if (i < d.n) z[i] = f2ord(__fsub_rn(s.y[i], __fmul_rn(slope, (float)(i - d.half))));
+				if (i < d.n) z[i] = f2ord(__fsub_rn(TS_Y(i), __fmul_rn(slope, (float)(i - d.half))));
 			}
 			__syncwarp();
 			const float yint = ord2f(warp_select_kth(z, d.n, d.rank_yint, s.hist, lane));
