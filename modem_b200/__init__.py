@@ -18,7 +18,7 @@ import struct
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libofdmrx.so")
+LIB_PATH = os.environ.get("OFDMRX_LIB") or os.path.join(PKG, "libofdmrx.so")  # OFDMRX_LIB: another build of the same library (A/B runs)
 
 PAYLOAD_BYTES = 5380
 CODE_LEN = 65536

@@ -148,6 +148,12 @@ constexpr int kTsCandCap = 1280;       // in-bracket quotients kept for the fina
 #define OFDMRX_TS_Y_SMEM 0
 #endif
 constexpr int kTsCtasPerSm = OFDMRX_TS_Y_SMEM ? 5 : 6;
+#ifndef OFDMRX_TS_HUBER_ITS
+#define OFDMRX_TS_HUBER_ITS 4 // re-weighted least-squares steps of the pilot at most (A/B switch)
+#endif
+#ifndef OFDMRX_TS_CONV
+#define OFDMRX_TS_CONV 0.4f  // ... fewer when a step moved the slope by less than this fraction of the bracket's half-width
+#endif
 
 constexpr int kTsTaskCap = 16;         // scan continuations a lane can park per sweep (beyond that they run on the spot)
 struct TsSweep {                       // per sweep: every 32-column chunk sorted by u
@@ -225,13 +231,17 @@ __device__ __noinline__ int warp_select_radix(const int *v, int n, int k, int *h
 // value between min and max (a monotone map, so the k-th smallest lies in the bucket where the running count passes k),
 // then the few members of that bucket are ranked against each other.  Crowded buckets (ties, outliers that stretch the
 // range) go to the radix select, on the bucket's members only.  v[] is overwritten from its start with those members.
-__device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int lane)
+// (lo <= every value < hi when the caller knows such bounds — the slope candidates lie inside their bracket —, else lo > hi)
+__device__ __noinline__ int warp_select_kth(int *v, int n, int k, int *hist, int lane, float lo, float hi)
 {
-	float mn = __int_as_float(0x7f800000), mx = -mn;
+	float mn = lo, mx = hi;
+	if (!(lo < hi)) {
+		mn = __int_as_float(0x7f800000); mx = -mn;
 #pragma unroll 2
-	for (int i = lane; i < n; i += 32) { const float x = ord2f(v[i]); mn = fminf(mn, x); mx = fmaxf(mx, x); }
+		for (int i = lane; i < n; i += 32) { const float x = ord2f(v[i]); mn = fminf(mn, x); mx = fmaxf(mx, x); }
 #pragma unroll
-	for (int d = 16; d; d >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL, mn, d)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d)); }
+		for (int d = 16; d; d >>= 1) { mn = fminf(mn, __shfl_xor_sync(FULL, mn, d)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, d)); }
+	}
 	if (!(mx - mn < 3.0e38f) || !(mx > mn)) return warp_select_radix(v, n, k, hist, lane); // all equal, or not finite
 	const float sc = 256.f / (mx - mn);
 #pragma unroll
@@ -518,8 +528,9 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 	// stays within ~0.4 bracket widths of the Theil-Sen slope on clean, AWGN and multipath rows alike.
 	{
 		const float kh = 1.345f, beta = 0.71016f; // beta = E[min(z^2, k^2)], z ~ N(0,1)
+		const float conv_scale = (432.f / (float)d.n) * sqrtf(432.f / (float)d.n) * (d.n > 432 ? (432.f / (float)d.n) * sqrtf(432.f / (float)d.n) : 1.f); // sigma and shrink factors of the bracket below
 #pragma unroll 1
-		for (int it = 0; it < 4; ++it) {
+		for (int it = 0; it < OFDMRX_TS_HUBER_ITS; ++it) {
 			const float cap = kh * srob;
 			float acc = 0.f;
 #pragma unroll 2
@@ -553,8 +564,13 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 			}
 			const float den = sw * swxx - swx * swx;
 			if (!(den > 0.f) || !(srob > 0.f)) break; // degenerate weights: keep the previous line
-			c0 = (sw * swxy - swx * swy) / den;
+			const float c1 = (sw * swxy - swx * swy) / den;
+			const float moved = fabsf(c1 - c0);
+			c0 = c1;
 			icpt = (swy - c0 * swx) / sw;
+			// converged as far as the bracket cares: the step was under 0.4 of its half-width (the next one is a few times
+			// smaller).  Rows with Gaussian residuals stop after two steps, rows with outlying carriers take all four.
+			if (moved < OFDMRX_TS_CONV * half_k * srob * conv_scale) break;
 		}
 	}
 	// robust residual scale, rescaled so that the bracket below (sized for 432 carriers) keeps its width in units of the
@@ -624,7 +640,7 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 			__syncwarp();
 			const int kk = d.rank_slope - cb;
 			if (kk >= 0 && kk < nin) {
-				if (nin <= kTsCandCap) return ord2f(warp_select_kth(s.cand, nin, kk, s.hist, lane));
+				if (nin <= kTsCandCap) return ord2f(warp_select_kth(s.cand, nin, kk, s.hist, lane, blo, bhi));
 				// the rank is inside but the bracket holds more quotients than the select scratch: zoom in (counts are exact)
 				L = blo; cL = cb; U = bhi; cU = cb + nin;
 				const float centre = blo + width * (((float)kk + 0.5f) / (float)nin);
@@ -713,7 +729,7 @@ __global__ void __launch_bounds__(kTsWarps * 32, kTsCtasPerSm) k_theil_sen(const
 				if (i < d.n) z[i] = f2ord(__fsub_rn(TS_Y(i), __fmul_rn(slope, (float)(i - d.half))));
 			}
 			__syncwarp();
-			const float yint = ord2f(warp_select_kth(z, d.n, d.rank_yint, s.hist, lane));
+			const float yint = ord2f(warp_select_kth(z, d.n, d.rank_yint, s.hist, lane, 1.f, 0.f));
 			if (lane == 0) {
 				float *t = tbase + (size_t)(stv ? r : 0) * 3;
 				t[0] = slope;
@@ -819,6 +835,13 @@ static float ts_half_k()
 	return k;
 }
 
+// chains per window (OFDMRX_TS_CHAINS overrides for A/B runs; 0 = by batch size)
+static int ts_chains_override()
+{
+	static const int k = [] { const char *e = std::getenv("OFDMRX_TS_CHAINS"); return e ? std::atoi(e) : 0; }();
+	return k;
+}
+
 // test hook: n_rows dense rows of `cols` phase values -> (slope, yint, sweeps) per row
 cudaError_t launch_theil_sen_rows(const float *yph, int n_rows, int cols, float *ts, int n_sm, cudaStream_t s)
 {
@@ -854,7 +877,8 @@ cudaError_t launch_demod(int rate, const cfx *iq, int64_t iq_stride, int iq_len,
 	int ts_smem;
 	theil_sen_grid(1, n_sm, &ts_smem);
 	const int resident_warps = n_sm * (int)((227 * 1024) / (ts_smem + 1024)) * kTsWarps;
-	const int n_chains = std::max(5, std::min(9, (2 * resident_warps + n_frames - 1) / n_frames)); // >= 5: short items keep the tail short
+	int n_chains = std::max(5, std::min(9, (2 * resident_warps + n_frames - 1) / n_frames)); // >= 5: short items keep the tail short
+	if (ts_chains_override() > 0) n_chains = ts_chains_override();
 	const int grid = theil_sen_grid(n_frames * n_chains, n_sm, &ts_smem);
 	if (grid < 0) return cudaErrorInvalidValue;
 	k_theil_sen<<<grid, kTsWarps * 32, ts_smem, s>>>(yph, st, n_frames * n_chains, n_chains, 0, ts_half_k(), ts);
