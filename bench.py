@@ -324,9 +324,12 @@ def main():
             c3_stage, _ = rx3.stage_times()
             rx3.set_option("sub_chunks", 0)
             c3_err, c3_fail = errors_now()
+            c3_stt = status.cpu().numpy().view(M.STATUS_DTYPE).reshape(-1)
+            c3_sweeps = float(c3_stt["ts_sweeps"][c3_stt["status"] == 0].mean()) / 50.0 if (c3_stt["status"] == 0).any() else None
             cfg3 = {"workload": "BASELINE configs[2]: README chain (multipath + CFO 234.567 Hz + SFO 147 ppm + AWGN -30 dB) on %d distinct device-generated windows per GPU" % n,
                     "frames_per_s": n * world / (c3_ms / args.steps / 1e3), "ms_per_step": c3_ms / args.steps,
-                    "payload_bit_errors_vs_sent": c3_err, "frames_failed": c3_fail, "stage_ms": c3_stage}
+                    "payload_bit_errors_vs_sent": c3_err, "frames_failed": c3_fail, "stage_ms": c3_stage,
+                    "theil_sen_sweeps_per_row": c3_sweeps}
         if os.environ.get("BENCH_CONFIG5", "1") != "0":
             shard = int(os.environ.get("BENCH_CONFIG5_FRAMES", "125000"))
             classes = [("clean", None), ("awgn -25", dict(awgn_db=-25.0)), ("awgn -18", dict(awgn_db=-18.0)), ("cfo -180.5 Hz", dict(cfo_hz=-180.5)),

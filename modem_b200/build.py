@@ -24,7 +24,7 @@ CC = ["host_tables.cc", "tx_tables.cc"]
 HDRS = ["common.cuh", "polar.cuh", "frontend.cuh", "fft.cuh", "host_tables.h", "stimulus.cuh", "tx_tables.h",
         os.path.join("..", "..", "include", "ofdmrx.h"), os.path.join("..", "..", "include", "ofdmtx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-Xptxas", "-v"] + [("-D%s=%s" % (k, os.environ[k])) for k in ("OFDMRX_SCL_CTAS", "OFDMRX_SCL_PREFETCH", "OFDMRX_SYNC_TMA", "OFDMRX_MT_TILE", "OFDMRX_SCL_STREAM_LEVEL", "OFDMRX_TS_Y_SMEM", "OFDMRX_TS_HUBER_ITS", "OFDMRX_TS_CONV") if os.environ.get(k)]
+              "-Xptxas", "-v"] + [("-D%s=%s" % (k, os.environ[k])) for k in ("OFDMRX_SCL_CTAS", "OFDMRX_SCL_PREFETCH", "OFDMRX_SYNC_TMA", "OFDMRX_MT_TILE", "OFDMRX_SCL_STREAM_LEVEL", "OFDMRX_TS_Y_SMEM", "OFDMRX_TS_HUBER_ITS", "OFDMRX_TS_CONV", "OFDMRX_TS_MIN_ITS") if os.environ.get(k)]
 
 
 def _nvcc():

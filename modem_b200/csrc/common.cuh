@@ -24,13 +24,20 @@ struct DeviceOnce {
 	std::once_flag flag[64];
 	cudaError_t err[64];
 };
+// max_carveout: also ask for the largest shared-memory carve-out.  Without the hint the driver picks the L1 / shared split of
+// a launch from the kernel's needs AND from what the SM was last configured for; a kernel whose CTAs per SM are set by shared
+// memory (k_theil_sen: six CTAs need 222 KB) then runs with fewer resident CTAs after some predecessors than after others.
 template <typename Kernel>
-inline cudaError_t set_dynamic_smem_once(DeviceOnce &once, Kernel kernel, int bytes)
+inline cudaError_t set_dynamic_smem_once(DeviceOnce &once, Kernel kernel, int bytes, bool max_carveout = false)
 {
 	int d = 0;
 	cudaGetDevice(&d);
 	d &= 63;
-	std::call_once(once.flag[d], [&] { once.err[d] = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+	std::call_once(once.flag[d], [&] {
+		once.err[d] = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		if (once.err[d] == cudaSuccess && max_carveout)
+			once.err[d] = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+	});
 	return once.err[d];
 }
 

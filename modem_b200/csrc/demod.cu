@@ -151,8 +151,14 @@ constexpr int kTsCtasPerSm = OFDMRX_TS_Y_SMEM ? 5 : 6;
 #ifndef OFDMRX_TS_HUBER_ITS
 #define OFDMRX_TS_HUBER_ITS 4 // re-weighted least-squares steps of the pilot at most (A/B switch)
 #endif
+#ifndef OFDMRX_TS_MIN_ITS
+#define OFDMRX_TS_MIN_ITS 1     // ... but at least this many
+#endif
 #ifndef OFDMRX_TS_CONV
-#define OFDMRX_TS_CONV 0.4f  // ... fewer when a step moved the slope by less than this fraction of the bracket's half-width
+#define OFDMRX_TS_CONV 0.0f  // ... fewer when a step moved the slope by less than this fraction of the bracket's half-width (0: never).
+// Measured with 0.4: 0.8 ms faster per 10 000 clean windows, but one README-chain row in 500 000 then starts so far off that the
+// bracket search gives up after 16 sweeps and the row goes through the exact bisection, 60 rows' worth of work at the tail of the
+// launch (+4 ms).  Off until the search itself copes with such rows.
 #endif
 
 constexpr int kTsTaskCap = 16;         // scan continuations a lane can park per sweep (beyond that they run on the spot)
@@ -485,6 +491,10 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 	// The passes over the row are rolled loops that re-read the values (L1 / shared memory) instead of holding sixteen of them
 	// in registers under sixteen-fold unrolled code: this kernel runs out of instruction cache before anything else
 	// (7 200 instructions, 24 warps at different places of them).
+	// (the pilot's passes read a copy of the row in the candidate scratch, which is free until the first sweep sorts into it;
+	// every lane reads back only the columns it stored.  Re-reading the row from L1 / L2 up to ten times made the kernel's time
+	// depend on what the L2 happened to hold: 16.4 ms or 20 - 24 ms for the same README-chain batch.)
+	float *ys = reinterpret_cast<float *>(s.cand);
 	float a0 = 0.f, a1 = 0.f;
 	float ymin = __int_as_float(0x7f800000), ymax = -ymin;
 	const float x0 = (float)(lane - d.half) + 0.5f; // centred abscissa of column `lane`; column 32 r + lane: x0 + 32 r
@@ -493,6 +503,7 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 		const int i = 32 * r + lane;
 		if (i < d.n) {
 			const float yv = TS_Y(i);
+			ys[i] = yv;
 			a0 += yv;
 			a1 = fmaf(x0 + (float)(32 * r), yv, a1);
 			ymin = fminf(ymin, yv);
@@ -515,7 +526,7 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 	for (int r = 0; r < d.nblk; ++r) {
 		const int i = 32 * r + lane;
 		if (i < d.n) {
-			const float e = TS_Y(i) - icpt - c0 * (x0 + (float)(32 * r));
+			const float e = ys[i] - icpt - c0 * (x0 + (float)(32 * r));
 			r2 = fmaf(e, e, r2);
 		}
 	}
@@ -537,7 +548,7 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 			for (int r = 0; r < d.nblk; ++r) {
 				const int i = 32 * r + lane;
 				if (i < d.n) {
-					const float e = TS_Y(i) - icpt - c0 * (x0 + (float)(32 * r));
+					const float e = ys[i] - icpt - c0 * (x0 + (float)(32 * r));
 					acc += fminf(e * e, cap * cap);
 				}
 			}
@@ -550,7 +561,7 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 			for (int r = 0; r < d.nblk; ++r) {
 				const int i = 32 * r + lane;
 				if (i < d.n) {
-					const float x = x0 + (float)(32 * r), yv = TS_Y(i);
+					const float x = x0 + (float)(32 * r), yv = ys[i];
 					const float e = fabsf(yv - icpt - c0 * x);
 					const float w = e <= lim ? 1.f : __fdividef(lim, e);
 					sw += w; swx = fmaf(w, x, swx); swy = fmaf(w, yv, swy);
@@ -568,9 +579,8 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 			const float moved = fabsf(c1 - c0);
 			c0 = c1;
 			icpt = (swy - c0 * swx) / sw;
-			// converged as far as the bracket cares: the step was under 0.4 of its half-width (the next one is a few times
-			// smaller).  Rows with Gaussian residuals stop after two steps, rows with outlying carriers take all four.
-			if (moved < OFDMRX_TS_CONV * half_k * srob * conv_scale) break;
+			// (optional early stop: the step was under OFDMRX_TS_CONV of the bracket's half-width)
+			if (it + 1 >= OFDMRX_TS_MIN_ITS && moved < OFDMRX_TS_CONV * half_k * srob * conv_scale) break;
 		}
 	}
 	// robust residual scale, rescaled so that the bracket below (sized for 432 carriers) keeps its width in units of the
@@ -819,7 +829,7 @@ static int theil_sen_grid(int rows, int n_sm, int *smem)
 {
 	static DeviceOnce once;
 	*smem = (int)(kTsWarps * sizeof(TsShared));
-	if (set_dynamic_smem_once(once, k_theil_sen, *smem) != cudaSuccess) return -1;
+	if (set_dynamic_smem_once(once, k_theil_sen, *smem, true) != cudaSuccess) return -1;
 	int grid = (rows + kTsWarps - 1) / kTsWarps;
 	const int resident = n_sm * (int)((227 * 1024) / (*smem + 1024));
 	if (grid > 4 * resident) grid = 4 * resident; // a few waves of persistent CTAs: rows differ little in cost
