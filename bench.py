@@ -404,7 +404,7 @@ def main():
                                 "kernel computes each distinct path once, so it executes ~1/8 of them) — the HBM view is beside it"),
             "k_theil_sen": roof("k_theil_sen", "theil_sen", ALG_BYTES_TS, ALG_FLOP_TS,
                                 "neither HBM- nor FP32-bound: an exact order statistic of 93 096 quotients per row by compare/search steps in shared "
-                                "memory (issue-bound, IPC 2.2 of 4; profiles/)"),
+                                "memory (time follows the instruction count, IPC 2.3 of 4; profiles/r2m_ncu_theil_sen.md)"),
             "k_sync_metric": roof("k_sync_metric", "sync_metric", ALG_BYTES_CORR),
         }
         # `roofline` = the list decoder (the kernel VERDICT.md names and the north star's FP32-roofline stage) unless another kernel
