@@ -464,9 +464,13 @@ __device__ __forceinline__ int sweep_pairs(TsShared &s, const float *yrow, const
 
 // fallback for rows that defeat the bracket search: smallest value T with #(quotient <= T) > rank, by a binary
 // search over the ordered-int image of the floats with an exact count (one IEEE division per pair) per step.
-__device__ __noinline__ float ts_slope_bisect(const float *y, int n, int rank, int lane)
+// L <= answer < U when the caller's bracket search has established such bounds (exact counts on both sides), else -inf / +inf:
+// the search then starts inside them (two ordered-int steps of slack for the -0 / +0 pair).
+__device__ __noinline__ float ts_slope_bisect(const float *y, int n, int rank, int lane, float L, float U)
 {
 	int lo = (int)0x80000000, hi = 0x7fffffff; // answer in [lo, hi]
+	if (L > __int_as_float(0xff800000)) lo = f2ord(L) - 2;
+	if (U < __int_as_float(0x7f800000)) hi = f2ord(U) + 1;
 	while (lo < hi) {
 		const int mid = (int)(((long long)lo + (long long)hi) >> 1);
 		const float t = ord2f(mid);
@@ -518,7 +522,7 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 		ymax = fmaxf(ymax, __shfl_xor_sync(FULL, ymax, dd));
 	}
 	if (ymin == ymax) return 0.f; // erased row: every difference is 0, every quotient +0
-	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(yrow, d.n, d.rank_slope, lane); // non-finite input: stay total
+	if (!(ymax - ymin < 3.0e38f)) return ts_slope_bisect(yrow, d.n, d.rank_slope, lane, __int_as_float(0xff800000), __int_as_float(0x7f800000)); // non-finite input: stay total
 	const float sxx = (float)d.n * ((float)d.n * (float)d.n - 1.f) / 12.f;
 	float c0 = a1 / sxx, icpt = a0 / (float)d.n; // least-squares line through the centred abscissa x + 0.5
 	float r2 = 0.f;
@@ -686,7 +690,7 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 		if (!(blo < bhi)) break;
 	}
 	sweeps += 100;
-	return ts_slope_bisect(yrow, d.n, d.rank_slope, lane);
+	return ts_slope_bisect(yrow, d.n, d.rank_slope, lane, L, U);
 }
 
 // Work items: with a status array, item = (window f, chain c of n_chains): the chain walks a contiguous block of the window's
