@@ -9,14 +9,14 @@
 //   k_soft_demap  one CTA per window: derotation, cumulative Es/N0 -> precision, PhaseShiftKeying<8>::soft ->
 //                 code[3*(432 j + i) + b], lengthen()                 (decode.cc:493-495,505-529, psk.hh:125-130)
 //
-// Theil–Sen without sorting 93 096 quotients: an ordinary-least-squares pilot c and its residual sigma give a bracket
-// [blo, bhi) a few 1e-4 sigma wide that almost always holds rank 46 548.  With u_k = y_k - blo k and v_k = y_k - bhi k
-// a pair (i < j) lies below the bracket iff u_j < u_i and at or above it iff v_j >= v_i, so ONE sweep over all pairs
-// costs two compares per pair and no division; only pairs inside the bracket (or within a rounding margin of its
-// edges) are evaluated as IEEE quotients, exactly as the reference forms them, and the answer is selected among those
-// by a radix select — the result is the exact order statistic std::nth_element returns.  If the rank falls outside, the
-// counts are exact with respect to the bracket edges, so the neighbouring bracket is swept next; rows that defeat the
-// bracket search altogether (long runs of tied quotients) take a bit-wise binary search with exact counting.
+// Theil–Sen without sorting 93 096 quotients: a robust pilot line (Huber M-estimate) and its residual scale give a bracket
+// [blo, bhi) ~2e-4 sigma wide that almost always holds rank 46 548.  With u_k = y_k - blo x_k and w = bhi - blo a pair
+// (i < j) lies below the bracket iff u_j < u_i and inside it iff additionally u_j - u_i < w (x_j - x_i), so ONE sweep over
+// all pairs costs compares and no division; only pairs inside the bracket (or within a rounding margin of its edges) are
+// evaluated as IEEE quotients, exactly as the reference forms them, and the answer is selected among those — the result
+// is the exact order statistic std::nth_element returns.  If the rank falls outside, the counts are exact with respect
+// to the bracket edges, so the enclosure tightens and the next bracket is extrapolated; rows that defeat the bracket search
+// altogether (long runs of tied quotients) take a bit-wise binary search with exact counting inside that enclosure.
 #include "common.cuh"
 #include "frontend.cuh"
 #include "fft.cuh"
