@@ -156,9 +156,10 @@ constexpr int kTsCtasPerSm = OFDMRX_TS_Y_SMEM ? 5 : 6;
 #endif
 #ifndef OFDMRX_TS_CONV
 #define OFDMRX_TS_CONV 0.0f  // ... fewer when a step moved the slope by less than this fraction of the bracket's half-width (0: never).
-// Measured with 0.4: 0.8 ms faster per 10 000 clean windows, but one README-chain row in 500 000 then starts so far off that the
-// bracket search gives up after 16 sweeps and the row goes through the exact bisection, 60 rows' worth of work at the tail of the
-// launch (+4 ms).  Off until the search itself copes with such rows.
+// Measured with 0.4: 0.8 ms faster per 10 000 clean windows, but one README-chain row in 500 000 then went through the exact
+// bisection (60 rows' worth of work at the tail of the launch, +4 ms): one lane's sub-queue ran over while the bracket was far
+// from full, and the overflow zoom of the time did not zoom (ts_slope below).  That is fixed; the early
+// stop stays off until the fixed build has been timed.
 #endif
 
 constexpr int kTsTaskCap = 16;         // scan continuations a lane can park per sweep (beyond that they run on the spot)
@@ -624,8 +625,12 @@ __device__ float ts_slope(TsShared &s, const float *yrow, const TsDims &d, int l
 			if (kd < 0) { U = blo; cU = cd; }
 			else if (kd >= nq) { L = bhi; cL = cd + nq; }
 			else {
+				// zoom in around where the rank should sit: to ~cap/3 queued pairs in all, and — when it is ONE lane's sub-queue
+				// that ran over while the bracket as a whole is far from full (a carrier lying on the median line pairs up with
+				// many others) — far enough for that lane to fit.  (Without the second bound such a bracket was "zoomed" to more
+				// than its own width, i.e. not at all, sixteen times over, and the row went through the bisection below.)
 				const float centre = blo + width * (((float)kd + 0.5f) / (float)nq);
-				const float hw = width * ((float)kTsCap / (6.f * (float)nq));
+				const float hw = 0.5f * width * fminf((float)kTsCap / (3.f * (float)nq), (0.75f * (float)kTsLaneCap) / (float)nqmax);
 				blo = fmaxf(centre - hw, blo);
 				bhi = fminf(centre + hw, bhi);
 				if (!(blo < bhi)) break;
