@@ -43,7 +43,7 @@ dem = subprocess.run(["c++filt"], input="\n".join(spills), capture_output=True, 
 bad = sorted((re.sub(r"\(anonymous namespace\)::|ofdmrx::|^void |\(.*\)$", "", d), v) for d, v in zip(dem, spills.values()) if v != (0, 0))
 print("\nRegister spills (ptxas -v, most recent build): " + ("none." if not bad else
       "; ".join("`%s` %d B stores / %d B loads" % (k, v[0], v[1]) for k, v in bad) +
-      " — small frames around the `__noinline__` helpers of these two kernels at the register counts ptxas settles on under their"
-      " occupancy targets (17 resident list-decoder warps, 20 Theil-Sen rows per SM; forcing more registers measured slower, DESIGN.md §4);"
+      " — small frames around the `__noinline__` helpers of the list decoder at the register count ptxas settles on under its"
+      " occupancy target (96 registers: 20 resident one-warp CTAs per SM; forcing more registers measured slower, DESIGN.md §4);"
       " every other kernel: none.  The remaining stack is local arrays (fork sort, OSD selection) and the double-precision"
       " sin/cos/log slow paths of the stimulus stream kernels."))
