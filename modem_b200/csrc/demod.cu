@@ -139,7 +139,7 @@ constexpr int kTsWarps = 4;            // rows in flight per CTA (one per warp)
 constexpr int kTsCap = 2048;           // in-bracket pairs a warp can queue ...
 constexpr int kTsLaneCap = kTsCap / 32; // ... as 32 private sub-queues
 constexpr int kTsPad = kMaxCols;       // 16 x 32 columns, the tail beyond the mode's carrier count holds +inf
-constexpr int kTsRows = kTsPad / 32;   // up to 16 row blocks: lane L owns carriers i = 32 R + L
+[[maybe_unused]] constexpr int kTsRows = kTsPad / 32;   // up to 16 row blocks: lane L owns carriers i = 32 R + L
 
 constexpr int kTsCandCap = 1280;       // in-bracket quotients kept for the final select
 // The row's phase values: a copy in shared memory (1) or read where they lie through the read-only path (0).  Without the

@@ -149,7 +149,7 @@ struct Mt {
 	static constexpr int kPad = kThreads * kPer;                                                // 3584
 	// newest sample is buffer tap kBufferLen - 1: the correlator's taps search_pos + half and search_pos + symbol_len
 	// (decode.cc:86) are the stream samples t - kOffOld and t - kOffCur
-	static constexpr int kOffOld = G::kBufferLen - 1 - (G::kSearchPos + G::kHalf);              // 5119
+	// (the other tap, t - kOffOld with kOffOld = kBufferLen - 1 - (kSearchPos + kHalf) = 5119, is kOffCur + kHalf: the same stream, lagged)
 	static constexpr int kOffCur = G::kBufferLen - 1 - (G::kSearchPos + G::kSymLen);            // 4479
 };
 
@@ -171,6 +171,7 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane)
 #ifndef OFDMRX_SYNC_TMA
 #define OFDMRX_SYNC_TMA 0 // measured per 10 000 windows at 8 kHz: 6.90 ms with the bulk copy, 6.27 ms without
 #endif
+#if OFDMRX_SYNC_TMA
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
 {
@@ -191,6 +192,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 	asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
 		:: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif
 
 // Outputs: the Schmitt trigger's two comparisons as bit masks (hi: v > high, lo: v < low; one word per 32 stream steps — all
 // k_sync_detect needs to list the edges) and the timing values themselves only for tiles that hold a value >= low (every
@@ -206,7 +208,9 @@ __global__ void __launch_bounds__(Mt<S>::kThreads) k_sync_metric(const cfx *iq, 
 	float *sim = sre + kMtPad;                          // c.im, then its prefix
 	float *se = sim + kMtPad;                           // e, then its prefix
 	__shared__ float wtot[3][Mt<S>::kThreads / 32];
+#if OFDMRX_SYNC_TMA
 	__shared__ __align__(8) uint64_t bar;
+#endif
 	const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int n = n_samples ? n_samples[f] : n_default;
 	const int t0 = blockIdx.x * kMtTile;
